@@ -1,0 +1,161 @@
+/*
+ * sonde_b200.h — C ABI of the B200 batched radiosonde demod + sync + FEC path.
+ *
+ * This is the drop-in boundary for the hot path of dbdexter-dev/sdrpp_radiosonde
+ * (reference paths below are relative to /root/reference, "SD/" =
+ * src/decode/sondedump/).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * What each entry point replaces in the reference:
+ *
+ *   sonde_b200_create / _destroy
+ *       N x  xxx_decoder_init(samplerate) / xxx_decoder_deinit()
+ *       (SD/include/rs41.h:14,21  dfm09.h  m10.h  ims100.h  mrzn1.h  imet4.h  c50.h;
+ *        called from src/decode/decoder.hpp:39,28)
+ *
+ *   sonde_b200_process_fm[_device]
+ *       the "while (xxx_decode(dec, &frag, buf, len) != PROCEED)" loop of
+ *       src/decode/decoder.hpp:61 / SD/main.c:333 for every channel of the batch:
+ *       one call == one reference buffer of `len` float FM samples per channel.
+ *
+ *   sonde_b200_process_iq[_device]
+ *       the same, preceded by dsp::demod::FM<float> (src/main.hpp:33, src/main.cpp:57)
+ *       i.e. the quadrature discriminator over complex IQ.
+ *
+ *   sonde_b200_fetch
+ *       the per-PARSED results: one sonde_frame_rec per framer window
+ *       (raw frame after framer_read SD/decode/framer.c:51, frame bytes after
+ *       descramble + FEC, FEC status) in the order the reference would return them.
+ *
+ * Threading: a handle is not thread safe; distinct handles are independent
+ * (same contract as the reference decoders).
+ */
+#ifndef SONDE_B200_H
+#define SONDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SONDE_API __attribute__((visibility("default")))
+#else
+#define SONDE_API
+#endif
+
+/* Sonde (decoder) types: the seven decoders of the reference (SD/include/*.h). */
+enum sonde_type {
+	SONDE_RS41   = 0,   /* Vaisala RS41-SG          SD/sonde/rs41/   */
+	SONDE_DFM09  = 1,   /* GRAW DFM06/09/17         SD/sonde/dfm09/  */
+	SONDE_M10    = 2,   /* Meteomodem M10 / M20     SD/sonde/m10/    */
+	SONDE_IMS100 = 3,   /* Meisei iMS-100 / RS-11G  SD/sonde/ims100/ */
+	SONDE_MRZN1  = 4,   /* MRZ-N1                   SD/sonde/mrz-n1/ */
+	SONDE_IMET4  = 5,   /* InterMet iMet-1/4        SD/sonde/imet4/  */
+	SONDE_C50    = 6,   /* Meteolabor SRS-C50       SD/sonde/c50/    */
+	SONDE_NTYPES = 7
+};
+
+/* Error codes (all entry points return 0 on success, <0 on failure). */
+enum sonde_err {
+	SONDE_OK            =  0,
+	SONDE_ERR_ARG       = -1,   /* bad argument                          */
+	SONDE_ERR_CUDA      = -2,   /* CUDA runtime failure (see last_error) */
+	SONDE_ERR_NODEVICE  = -3,   /* no sm_100 device: there is NO CPU fallback */
+	SONDE_ERR_TOOLONG   = -4,   /* len > max_chunk_len given at create   */
+	SONDE_ERR_STATE     = -5    /* call sequence violated                */
+};
+
+#define SONDE_REC_BYTES 520     /* >= largest frame (RS41: 518 B, SD/sonde/rs41/protocol.h:19) */
+
+/*
+ * One record per framer window (== one PARSED return of xxx_decode()).
+ *
+ *  status  RS41   : rs41_frame_correct() result (sum of RS errors, -1 on failure)  SD/sonde/rs41/frame.c:39
+ *          DFM    : dfm09_frame_correct() result                                   SD/sonde/dfm09/frame.c:41
+ *          M10    : m10_frame_correct()   0 / -1                                   SD/sonde/m10/frame.c:22
+ *          iMS-100: ims100_frame_error_correct() result                            SD/sonde/ims100/frame.c:21
+ *          MRZ-N1 : mrzn1_frame_correct() 0 / -1                                   SD/sonde/mrz-n1/frame.c:6
+ *          iMet-4 : number of subframes whose CRC16 matched                        SD/sonde/imet4/imet4.c:97-106
+ *          C50    : c50_frame_correct()   0 / -1                                   SD/sonde/c50/frame.c:27
+ *  ok      1 when the window passes the reference's "decodable" gate
+ *  aux     DFM: 1 if the unpacked frame is not all-zero; iMS: 24-bit valid mask;
+ *          iMet: byte index `i` reached by the subframe walk (framer_adjust when >0)
+ *  raw     first frame_len bits of the aligned, de-inverted frame (framer output)
+ *  data    frame bytes after descramble + FEC:
+ *          RS41 518 B | DFM 35 B ECC frame, 18 B unpacked at +64 | M10 104 B |
+ *          iMS 75 B ECC frame, 52 B unpacked at +80 | MRZ 51 B | iMet 60 B | C50 9 B
+ */
+typedef struct {
+	int32_t  type;
+	int32_t  chunk;        /* index of the process_*() call in which the frame completed */
+	int32_t  sync_offset;  /* correlate() result, SD/decode/correlator/correlator.c:19 */
+	int32_t  inverted;
+	int32_t  status;
+	int32_t  ok;
+	int32_t  aux;
+	int32_t  data_len;
+	uint64_t bit_pos;      /* index, in the channel's demodulated bit stream, of the window start */
+	uint8_t  raw[SONDE_REC_BYTES];
+	uint8_t  data[SONDE_REC_BYTES];
+} sonde_frame_rec;
+
+typedef struct sonde_b200 sonde_b200;   /* opaque batch decoder */
+
+typedef struct {
+	int32_t n_channels;       /* C                                                   */
+	int32_t samplerate;       /* per-channel input rate, e.g. 48000                  */
+	int32_t max_chunk_len;    /* largest `len` that will be passed to process_*()    */
+	int32_t device;           /* CUDA device ordinal                                 */
+	const int32_t *types;     /* [C] enum sonde_type per channel                     */
+	float   fm_gain;          /* discriminator gain (1/deviation); 0 -> 2/pi, i.e.
+	                             dsp::demod::FM(samplerate=bw, bandwidth=bw/2)  src/main.cpp:57 */
+	int32_t keep_soft;        /* !=0: keep soft symbols for sonde_b200_fetch_soft()  */
+	int32_t reserved;
+} sonde_b200_config;
+
+SONDE_API int  sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg);
+SONDE_API void sonde_b200_destroy(sonde_b200 *h);
+
+/* Host-buffer entry points: H2D copy + kernels are enqueued; results are ready after fetch. */
+SONDE_API int  sonde_b200_process_iq(sonde_b200 *h, const float *iq /*[C][len][2]*/, size_t len);
+SONDE_API int  sonde_b200_process_fm(sonde_b200 *h, const float *fm /*[C][len]*/,    size_t len);
+
+/* Device-buffer entry points (inputs already resident in HBM). row_stride in samples. */
+SONDE_API int  sonde_b200_process_iq_device(sonde_b200 *h, const void *d_iq, size_t len, size_t row_stride);
+SONDE_API int  sonde_b200_process_fm_device(sonde_b200 *h, const void *d_fm, size_t len, size_t row_stride);
+
+/* Capacity (records per channel per process call) of the fetch arrays. */
+SONDE_API int  sonde_b200_max_frames(const sonde_b200 *h);
+
+/* Copy the records of the last process call: recs[C][max_frames], counts[C].  Synchronises. */
+SONDE_API int  sonde_b200_fetch(sonde_b200 *h, sonde_frame_rec *recs, int32_t *counts);
+
+/* Only the per-channel counters of the last call (cheap D2H): frames[C], ok[C]. Synchronises. */
+SONDE_API int  sonde_b200_fetch_counts(sonde_b200 *h, int32_t *frames, int32_t *ok);
+
+/* Parity taps for the last process call.
+ *  bits : demodulated hard bits, MSB first, bits[C][bits_stride_bytes]; nbits[C]
+ *  soft : soft symbols at symbol instants (needs keep_soft), soft[C][soft_stride]; nsoft[C] */
+SONDE_API int  sonde_b200_bits_stride(const sonde_b200 *h);
+SONDE_API int  sonde_b200_fetch_bits(sonde_b200 *h, uint8_t *bits, int32_t *nbits);
+SONDE_API int  sonde_b200_soft_stride(const sonde_b200 *h);
+SONDE_API int  sonde_b200_fetch_soft(sonde_b200 *h, float *soft, int32_t *nsoft);
+
+/* Block until everything enqueued so far has finished. */
+SONDE_API int  sonde_b200_sync(sonde_b200 *h);
+
+/* CUDA-event timing of the kernels of the last process call, in ms (demod, frame). */
+SONDE_API int  sonde_b200_last_kernel_ms(sonde_b200 *h, float *demod_ms, float *frame_ms);
+
+/* Number of kernels launched by this handle so far. */
+SONDE_API long sonde_b200_launch_count(const sonde_b200 *h);
+
+SONDE_API const char *sonde_b200_last_error(const sonde_b200 *h);
+SONDE_API const char *sonde_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONDE_B200_H */
