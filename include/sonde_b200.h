@@ -143,6 +143,23 @@ SONDE_API int  sonde_b200_fetch_bits(sonde_b200 *h, uint8_t *bits, int32_t *nbit
 SONDE_API int  sonde_b200_soft_stride(const sonde_b200 *h);
 SONDE_API int  sonde_b200_fetch_soft(sonde_b200 *h, float *soft, int32_t *nsoft);
 
+/* Loop state after the last call, state[C][8] = agc.bias, agc.moving_avg, timing.phase,
+ * timing.freq, timing.prev, timing.state, discriminator phase, 0  (parity tap). */
+SONDE_API int  sonde_b200_fetch_state(sonde_b200 *h, float *state);
+
+/* Host-only (no GPU needed): the demodulator constants the kernels use for (type, samplerate),
+ * i.e. what gfsk_init()/afsk_init() derive (SD/demod/gfsk.c:17-35, afsk.c:16-48).
+ * taps[phase*49+i] as SD/demod/dsp/filter.c:21-25 lays them out; consts[8] = timing.freq, alpha,
+ * beta, max_fdev, num_phases, afsk boxcar len, f_mark, f_space.  Returns the tap count or <0. */
+SONDE_API int  sonde_b200_modem_info(int type, int samplerate, float *taps, int taps_cap, float *consts);
+
+/* Pinned host memory for the host-buffer entry points (plain malloc'd memory also works, slower). */
+SONDE_API void *sonde_b200_host_alloc(size_t bytes);
+SONDE_API void  sonde_b200_host_free(void *p);
+
+/* The CUDA stream (cudaStream_t) all work of this handle is enqueued on. */
+SONDE_API void *sonde_b200_stream(sonde_b200 *h);
+
 /* Block until everything enqueued so far has finished. */
 SONDE_API int  sonde_b200_sync(sonde_b200 *h);
 

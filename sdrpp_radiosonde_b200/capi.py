@@ -1,0 +1,269 @@
+"""ctypes binding of the C-ABI library (include/sonde_b200.h -> libsonde_b200.so).
+
+This is the only way the Python side reaches the kernels; there is no CPU fallback.
+If the library is missing, or no sm_100 device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsonde_b200.so")
+
+REC_BYTES = 520
+
+SONDE_OK, ERR_ARG, ERR_CUDA, ERR_NODEVICE, ERR_TOOLONG, ERR_STATE = 0, -1, -2, -3, -4, -5
+_ERR_NAMES = {ERR_ARG: "SONDE_ERR_ARG", ERR_CUDA: "SONDE_ERR_CUDA", ERR_NODEVICE: "SONDE_ERR_NODEVICE",
+              ERR_TOOLONG: "SONDE_ERR_TOOLONG", ERR_STATE: "SONDE_ERR_STATE"}
+
+# every symbol include/sonde_b200.h declares (tests/test_abi.py checks the .so exports all of them)
+EXPORTS = [
+    "sonde_b200_create", "sonde_b200_destroy", "sonde_b200_process_iq", "sonde_b200_process_fm",
+    "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
+    "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
+    "sonde_b200_soft_stride", "sonde_b200_fetch_soft", "sonde_b200_fetch_state", "sonde_b200_modem_info",
+    "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_stream", "sonde_b200_sync",
+    "sonde_b200_last_kernel_ms", "sonde_b200_launch_count", "sonde_b200_last_error", "sonde_b200_version",
+]
+
+
+class FrameRec(ctypes.Structure):
+    """sonde_frame_rec"""
+    _fields_ = [
+        ("type", ctypes.c_int32), ("chunk", ctypes.c_int32), ("sync_offset", ctypes.c_int32),
+        ("inverted", ctypes.c_int32), ("status", ctypes.c_int32), ("ok", ctypes.c_int32),
+        ("aux", ctypes.c_int32), ("data_len", ctypes.c_int32), ("bit_pos", ctypes.c_uint64),
+        ("raw", ctypes.c_uint8 * REC_BYTES), ("data", ctypes.c_uint8 * REC_BYTES),
+    ]
+
+
+REC_DTYPE = np.dtype([
+    ("type", "<i4"), ("chunk", "<i4"), ("sync_offset", "<i4"), ("inverted", "<i4"), ("status", "<i4"),
+    ("ok", "<i4"), ("aux", "<i4"), ("data_len", "<i4"), ("bit_pos", "<u8"),
+    ("raw", "u1", (REC_BYTES,)), ("data", "u1", (REC_BYTES,)),
+])
+assert REC_DTYPE.itemsize == ctypes.sizeof(FrameRec) == 40 + 2 * REC_BYTES
+
+
+class Config(ctypes.Structure):
+    """sonde_b200_config"""
+    _fields_ = [
+        ("n_channels", ctypes.c_int32), ("samplerate", ctypes.c_int32), ("max_chunk_len", ctypes.c_int32),
+        ("device", ctypes.c_int32), ("types", ctypes.POINTER(ctypes.c_int32)), ("fm_gain", ctypes.c_float),
+        ("keep_soft", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    ]
+
+
+class SondeError(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__(f"{_ERR_NAMES.get(code, code)}: {msg}")
+
+
+_lib = None
+
+
+def load():
+    """Load libsonde_b200.so (raises if it has not been built: run `python __graft_entry__.py`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not built; run __graft_entry__.build()")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError:
+        # libcudart.so.12 not on the loader path: take the one PyTorch ships
+        import torch  # noqa: F401  (loads libcudart into the process)
+        lib = ctypes.CDLL(LIB_PATH)
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    i32p, f32p = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)
+    sig = {
+        "sonde_b200_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.POINTER(Config)]),
+        "sonde_b200_destroy": (None, [vp]),
+        "sonde_b200_process_iq": (ctypes.c_int, [vp, vp, sz]),
+        "sonde_b200_process_fm": (ctypes.c_int, [vp, vp, sz]),
+        "sonde_b200_process_iq_device": (ctypes.c_int, [vp, vp, sz, sz]),
+        "sonde_b200_process_fm_device": (ctypes.c_int, [vp, vp, sz, sz]),
+        "sonde_b200_max_frames": (ctypes.c_int, [vp]),
+        "sonde_b200_fetch": (ctypes.c_int, [vp, vp, i32p]),
+        "sonde_b200_fetch_counts": (ctypes.c_int, [vp, i32p, i32p]),
+        "sonde_b200_bits_stride": (ctypes.c_int, [vp]),
+        "sonde_b200_fetch_bits": (ctypes.c_int, [vp, vp, i32p]),
+        "sonde_b200_soft_stride": (ctypes.c_int, [vp]),
+        "sonde_b200_fetch_soft": (ctypes.c_int, [vp, f32p, i32p]),
+        "sonde_b200_fetch_state": (ctypes.c_int, [vp, f32p]),
+        "sonde_b200_modem_info": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, f32p, ctypes.c_int, f32p]),
+        "sonde_b200_host_alloc": (vp, [sz]),
+        "sonde_b200_host_free": (None, [vp]),
+        "sonde_b200_stream": (vp, [vp]),
+        "sonde_b200_sync": (ctypes.c_int, [vp]),
+        "sonde_b200_last_kernel_ms": (ctypes.c_int, [vp, f32p, f32p]),
+        "sonde_b200_launch_count": (ctypes.c_long, [vp]),
+        "sonde_b200_last_error": (ctypes.c_char_p, [vp]),
+        "sonde_b200_version": (ctypes.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def modem_info(stype: int, samplerate: int = 48000):
+    """(taps[P*49], consts[8]) the kernels use — host-only, no GPU needed."""
+    lib = load()
+    taps = np.zeros(128, dtype=np.float32)
+    consts = np.zeros(8, dtype=np.float32)
+    n = lib.sonde_b200_modem_info(stype, samplerate, taps.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 128,
+                                  consts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    if n < 0:
+        raise SondeError(n, "modem_info")
+    return taps[:n].copy(), consts
+
+
+def _f32p(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _i32p(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+class PinnedBuffer:
+    """Page-locked host memory from sonde_b200_host_alloc(), viewed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = self.lib.sonde_b200_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("sonde_b200_host_alloc failed")
+        buf = (ctypes.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.sonde_b200_host_free(self.ptr)
+            self.ptr = None
+
+
+class BatchDecoder:
+    """One handle of the C ABI: C channels, one sonde type per channel.
+
+    Mirrors the reference call protocol batched over channels: one process_*() call is one
+    reference buffer of `len` samples per channel (the `while (xxx_decode(...) != PROCEED)`
+    loop of src/decode/decoder.hpp:61); fetch() returns one record per PARSED return.
+    """
+
+    def __init__(self, types, max_chunk_len, samplerate=48000, device=0, fm_gain=0.0, keep_soft=False):
+        self.lib = load()
+        self.types = np.ascontiguousarray(types, dtype=np.int32)
+        self.C = int(self.types.size)
+        self.max_chunk_len = int(max_chunk_len)
+        cfg = Config(self.C, samplerate, self.max_chunk_len, device, _i32p(self.types), fm_gain,
+                     1 if keep_soft else 0, 0)
+        h = ctypes.c_void_p()
+        rc = self.lib.sonde_b200_create(ctypes.byref(h), ctypes.byref(cfg))
+        if rc != SONDE_OK:
+            raise SondeError(rc, "sonde_b200_create")
+        self.h = h
+        self.max_frames = self.lib.sonde_b200_max_frames(h)
+        self.bits_stride = self.lib.sonde_b200_bits_stride(h)
+        self.soft_stride = self.lib.sonde_b200_soft_stride(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sonde_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != SONDE_OK:
+            raise SondeError(rc, (self.lib.sonde_b200_last_error(self.h) or b"").decode())
+
+    # -- host buffers ---------------------------------------------------------------------
+    def process_fm(self, fm: np.ndarray):
+        fm = np.ascontiguousarray(fm, dtype=np.float32)
+        assert fm.ndim == 2 and fm.shape[0] == self.C, fm.shape
+        self._ck(self.lib.sonde_b200_process_fm(self.h, fm.ctypes.data, fm.shape[1]))
+
+    def process_iq(self, iq: np.ndarray):
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        assert iq.ndim == 2 and iq.shape[0] == self.C, iq.shape
+        self._ck(self.lib.sonde_b200_process_iq(self.h, iq.ctypes.data, iq.shape[1]))
+
+    def process_host_ptr(self, ptr: int, length: int, is_iq=True):
+        fn = self.lib.sonde_b200_process_iq if is_iq else self.lib.sonde_b200_process_fm
+        self._ck(fn(self.h, ptr, length))
+
+    # -- device buffers (raw pointers, e.g. torch.Tensor.data_ptr()) ------------------------
+    def process_iq_device(self, ptr: int, length: int, row_stride: int | None = None):
+        self._ck(self.lib.sonde_b200_process_iq_device(self.h, ptr, length, row_stride or length))
+
+    def process_fm_device(self, ptr: int, length: int, row_stride: int | None = None):
+        self._ck(self.lib.sonde_b200_process_fm_device(self.h, ptr, length, row_stride or length))
+
+    # -- results ------------------------------------------------------------------------------
+    def fetch(self):
+        """-> (recs[C][max_frames] structured array, counts[C])"""
+        recs = np.zeros((self.C, self.max_frames), dtype=REC_DTYPE)
+        counts = np.zeros(self.C, dtype=np.int32)
+        self._ck(self.lib.sonde_b200_fetch(self.h, recs.ctypes.data, _i32p(counts)))
+        return recs, counts
+
+    def fetch_counts(self):
+        frames = np.zeros(self.C, dtype=np.int32)
+        ok = np.zeros(self.C, dtype=np.int32)
+        self._ck(self.lib.sonde_b200_fetch_counts(self.h, _i32p(frames), _i32p(ok)))
+        return frames, ok
+
+    def fetch_bits(self):
+        """-> list of per-channel 0/1 arrays demodulated by the last call"""
+        buf = np.zeros((self.C, self.bits_stride), dtype=np.uint8)
+        n = np.zeros(self.C, dtype=np.int32)
+        self._ck(self.lib.sonde_b200_fetch_bits(self.h, buf.ctypes.data, _i32p(n)))
+        return [np.unpackbits(buf[c])[: n[c]] for c in range(self.C)]
+
+    def fetch_soft(self):
+        buf = np.zeros((self.C, self.soft_stride), dtype=np.float32)
+        n = np.zeros(self.C, dtype=np.int32)
+        self._ck(self.lib.sonde_b200_fetch_soft(self.h, _f32p(buf), _i32p(n)))
+        return [buf[c, : n[c]].copy() for c in range(self.C)]
+
+    def fetch_state(self):
+        st = np.zeros((self.C, 8), dtype=np.float32)
+        self._ck(self.lib.sonde_b200_fetch_state(self.h, _f32p(st)))
+        return st
+
+    def sync(self):
+        self._ck(self.lib.sonde_b200_sync(self.h))
+
+    def last_kernel_ms(self):
+        a, b = ctypes.c_float(), ctypes.c_float()
+        self._ck(self.lib.sonde_b200_last_kernel_ms(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    @property
+    def launch_count(self):
+        return int(self.lib.sonde_b200_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.sonde_b200_stream(self.h)

@@ -1,0 +1,353 @@
+/*
+ * demod.cu — K1: IQ / FM samples -> hard bits (+ optional soft symbols), batched over channels.
+ *
+ * One CTA owns DEMOD_G channels of the same sonde type and walks the chunk in tiles of
+ * DEMOD_T samples.  Per tile:
+ *
+ *   S1  load + discriminate   all threads, coalesced        (upstream dsp::demod::FM, src/main.cpp:57)
+ *   S2  AGC recurrences       1 lane / channel (serial IIR)  (demod/dsp/agc.c:19-34)
+ *   S3  AGC gain apply        all threads (5/avg is off the recurrence)
+ *   S4  49-tap FIR at EVERY sample position and polyphase branch, all threads,
+ *       accumulated in the reference's order                 (demod/dsp/filter.c:41-64)
+ *   S5  Gardner loop + slicer 1 lane / channel; only *selects* precomputed FIR outputs
+ *                                                            (demod/dsp/timing.c:28-76, demod/gfsk.c:75-125)
+ *
+ * The only truly serial parts of the reference chain are the two AGC recurrences and the
+ * timing NCO; filter_get() is a pure function of the AGC output at a position, so it is
+ * evaluated speculatively everywhere in parallel and the timing lane picks what it needs
+ * (SURVEY.md §7 "Design note for K1").  All arithmetic goes through strict_math.cuh, so soft
+ * symbols are bit-identical to the CPU reference.
+ *
+ * The demodulator free-runs over the chunk: `interm` is cleared at chunk
+ * start (gfsk.c:73), bits are appended to the channel's bit ring at absolute positions; the
+ * framer is a separate kernel (frame.cu).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_state.h"
+#include "strict_math.cuh"
+
+static __constant__ sonde_modem c_modem[SONDE_NTYPES_];
+
+extern "C" cudaError_t sonde_upload_modems(const sonde_modem *m)
+{
+	return cudaMemcpyToSymbol(c_modem, m, sizeof(sonde_modem) * SONDE_NTYPES_);
+}
+
+namespace {
+
+constexpr int G  = DEMOD_G;
+constexpr int T  = DEMOD_T;
+constexpr int NT = DEMOD_THREADS;
+constexpr int RS = T + 4;                       /* row stride of the per-tile arrays (bank spread, 16 B aligned) */
+constexpr int AS = SONDE_FIR_HIST + T + 4;      /* row stride of the FIR input array (48 history + tile)         */
+constexpr int R  = 8;                           /* FIR outputs per thread                                         */
+
+static_assert(G * T / R == NT, "one FIR segment per thread");
+static_assert(T % 32 == 0 && T / R == 32, "a warp covers one channel row in S4");
+
+struct smem_t {
+	float x[G][RS];                /* S1 out: discriminator output / FM input             */
+	float s[G][RS];                /* S2 out: bias-removed sample                         */
+	float v[G][RS];                /* S2 out: moving_avg BEFORE this sample's update      */
+	float a[G][AS];                /* S3 out: AGC output, [0,48) = previous tile's tail   */
+	float y[SONDE_MAX_PHASES][G][RS];   /* S4 out: FIR output per polyphase branch       */
+	float ph[G][RS];               /* S1 scratch: phases, ph[g][0] = previous sample      */
+	float taps[SONDE_MAX_PHASES * SONDE_FIR_TAPS];
+};
+
+/* ---- S2: the two AGC recurrences for one channel over n samples ---------------------- */
+template <bool CHECK_ZERO>
+__device__ __forceinline__ void agc_chains(const float *x, float *s, float *v, int n, float &bias, float &avg)
+{
+	const float kb1 = fsub(1.0f, 0.01f), kb0 = 0.01f;     /* agc.c:8,25  */
+	const float kg1 = fsub(1.0f, 0.001f), kg0 = 0.001f;   /* agc.c:9,28  */
+#pragma unroll 4
+	for (int i = 0; i < n; i++) {
+		const float xi = x[i];
+		if (CHECK_ZERO && xi == 0.0f) {               /* agc.c:23: exact zero bypasses the AGC */
+			s[i] = 0.0f;
+			v[i] = 5.0f;
+			continue;
+		}
+		const float si = fsub(xi, bias);
+		bias = fadd(fmul(bias, kb1), fmul(si, kb0));
+		s[i] = si;
+		v[i] = avg;
+		avg = fadd(fmul(avg, kg1), fmul(fabsf(si), kg0));
+	}
+}
+
+/* ---- S5: Gardner loop + slicer for one channel over n samples ------------------------- */
+struct timing_regs {
+	float prev, phase, freq, interm;
+	int   state;
+	uint32_t acc;
+	int   cnt;
+	uint64_t nbits;
+	int   nsoft;
+};
+
+__device__ __forceinline__ void emit_bit(timing_regs &t, float sym, uint8_t *ring, uint32_t ring_mask,
+                                         float *soft, int soft_cap)
+{
+	t.acc = (t.acc << 1) | (sym > 0.0f ? 1u : 0u);            /* gfsk.c:107 */
+	t.cnt++;
+	if (soft && t.nsoft < soft_cap) soft[t.nsoft] = sym;
+	t.nsoft++;
+	if (t.cnt == 8) {
+		ring[(uint32_t)(t.nbits >> 3) & ring_mask] = (uint8_t)t.acc;
+		t.acc = 0;
+		t.cnt = 0;
+	}
+	t.nbits++;
+}
+
+template <int P>
+__device__ __forceinline__ void timing_run(const smem_t &sm, int g, int n, timing_regs &t,
+                                           float center, float alpha, float beta, float max_fdev,
+                                           uint8_t *ring, uint32_t ring_mask, float *soft, int soft_cap)
+{
+	for (int i = 0; i < n; i++) {
+#pragma unroll
+		for (int ph = 0; ph < P; ph++) {
+			t.phase = fadd(t.phase, t.freq);                     /* timing.c:32 */
+			if (t.phase >= (float)t.state) {                     /* timing.c:35 */
+				/* filter_get(phase) uses polyphase branch P-1-phase (filter.c:54) */
+				const float yv = sm.y[P - 1 - ph][g][i];
+				if (t.state == 1) {
+					t.interm = yv;
+					t.state = 2;
+				} else {
+					/* retime(): timing.c:45-76 */
+					const float err = (fmul(yv, t.prev) < 0.0f) ? fmul(fsub(yv, t.prev), t.interm) : 0.0f;
+					t.prev = yv;
+					float fd = fsub(t.freq, center);
+					const float ea = fmul(err, alpha);
+					const float lo = (2.0f < ea) ? 2.0f : ea;
+					const float cl = (-2.0f > lo) ? -2.0f : lo;
+					t.phase = fsub(t.phase, fsub(2.0f, cl));
+					fd = fadd(fd, fmul(err, beta));
+					const float fl = (max_fdev < fd) ? max_fdev : fd;
+					fd = (-max_fdev > fl) ? -max_fdev : fl;
+					t.freq = fadd(center, fd);
+					t.state = 1;
+					emit_bit(t, yv, ring, ring_mask, soft, soft_cap);
+				}
+			}
+		}
+	}
+}
+
+/* ---- S4: FIR at R consecutive positions, reference summation order -------------------- */
+template <int P>
+__device__ __forceinline__ void fir_segment(smem_t &sm, int g, int seg)
+{
+	/* window of inputs a[n-48 .. n] for n = seg*R .. seg*R+R-1  ->  R+48 values */
+	float w[R + SONDE_FIR_HIST];
+	const float4 *src = reinterpret_cast<const float4 *>(&sm.a[g][seg * R]);
+#pragma unroll
+	for (int k = 0; k < (R + SONDE_FIR_HIST) / 4; k++) {
+		const float4 q = src[k];
+		w[4 * k + 0] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+	}
+#pragma unroll
+	for (int br = 0; br < P; br++) {
+		float acc[R];
+#pragma unroll
+		for (int r = 0; r < R; r++) acc[r] = 0.0f;
+#pragma unroll
+		for (int i = 0; i < SONDE_FIR_TAPS; i++) {
+			const float c = sm.taps[br * SONDE_FIR_TAPS + i];
+#pragma unroll
+			for (int r = 0; r < R; r++) acc[r] = fadd(acc[r], fmul(w[r + i], c));   /* filter.c:59-61 */
+		}
+		float4 *dst = reinterpret_cast<float4 *>(&sm.y[br][g][seg * R]);
+		dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+		dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+	}
+}
+
+template <int P>
+__global__ void __launch_bounds__(NT, 1)
+demod_gfsk_kernel(const demod_params p, const int group_base)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	smem_t &sm = *reinterpret_cast<smem_t *>(smem_raw);
+
+	const int tid = threadIdx.x;
+	const int grp = group_base + blockIdx.x;
+	const int type = p.group_type[grp];
+	const sonde_modem &md = c_modem[type];
+	const int *chans = p.group_chan + (size_t)grp * G;
+
+	for (int i = tid; i < P * SONDE_FIR_TAPS; i += NT) sm.taps[i] = md.taps[i];
+
+	/* channel owned by this thread in the serial stages (warp 0, lane g) */
+	const bool serial_lane = tid < G;
+	const int my_ch = serial_lane ? chans[tid] : -1;
+	float bias = 0, avg = 0;
+	timing_regs tr = {};
+	const float center = md.freq0, alpha = md.alpha, beta = md.beta, max_fdev = md.max_fdev;
+	uint8_t *my_ring = nullptr;
+	float *my_soft = nullptr;
+	if (my_ch >= 0) {
+		const demod_state &st = p.st[my_ch];
+		bias = st.agc_bias; avg = st.agc_avg;
+		tr.prev = st.t_prev; tr.phase = st.t_phase; tr.freq = st.t_freq; tr.state = st.t_state;
+		tr.interm = 0.0f;                                 /* gfsk.c:73 */
+		tr.acc = st.bit_acc; tr.cnt = st.bit_cnt; tr.nbits = st.nbits; tr.nsoft = 0;
+		my_ring = p.ring + (size_t)my_ch * p.ring_bytes;
+		if (p.soft) my_soft = p.soft + (size_t)my_ch * p.soft_stride;
+		sm.ph[tid][0] = st.disc_prev;
+	}
+	/* FIR history */
+	for (int i = tid; i < G * SONDE_FIR_HIST; i += NT) {
+		const int g = i / SONDE_FIR_HIST, k = i % SONDE_FIR_HIST;
+		const int ch = chans[g];
+		sm.a[g][k] = (ch >= 0) ? p.st[ch].hist[k] : 0.0f;
+	}
+	__syncthreads();
+
+	const uint32_t ring_mask = p.ring_bytes - 1;
+
+	for (int base = 0; base < p.len; base += T) {
+		const int n = min(T, p.len - base);
+
+		/* ---- S1: load (+ discriminate) ------------------------------------------------ */
+		int any_zero;
+		if (p.is_iq) {
+			const float2 *in = static_cast<const float2 *>(p.in);
+#pragma unroll
+			for (int k = 0; k < G * T / NT; k++) {
+				const int idx = tid + k * NT;
+				const int g = idx / T, i = idx % T;
+				const int ch = chans[g];
+				float phv = 0.0f;
+				if (ch >= 0 && i < n) {
+					const float2 q = __ldg(&in[(size_t)ch * p.row_stride + base + i]);
+					phv = det_phase(q.x, q.y);
+				}
+				sm.ph[g][i + 1] = phv;
+			}
+			__syncthreads();
+			int zero = 0;
+#pragma unroll
+			for (int k = 0; k < G * T / NT; k++) {
+				const int idx = tid + k * NT;
+				const int g = idx / T, i = idx % T;
+				const float xv = disc_step(sm.ph[g][i + 1], sm.ph[g][i], p.fm_gain);
+				sm.x[g][i] = xv;
+				zero |= (i < n && chans[g] >= 0 && xv == 0.0f);
+			}
+			any_zero = __syncthreads_or(zero);
+			if (tid < G) sm.ph[tid][0] = sm.ph[tid][n];      /* carry the last phase */
+		} else {
+			const float *in = static_cast<const float *>(p.in);
+			int zero = 0;
+#pragma unroll
+			for (int k = 0; k < G * T / NT; k++) {
+				const int idx = tid + k * NT;
+				const int g = idx / T, i = idx % T;
+				const int ch = chans[g];
+				float xv = 0.0f;
+				if (ch >= 0 && i < n) xv = __ldg(&in[(size_t)ch * p.row_stride + base + i]);
+				sm.x[g][i] = xv;
+				zero |= (i < n && ch >= 0 && xv == 0.0f);
+			}
+			any_zero = __syncthreads_or(zero);
+		}
+
+		/* ---- S2: AGC recurrences ------------------------------------------------------ */
+		if (my_ch >= 0) {
+			if (any_zero) agc_chains<true>(sm.x[tid], sm.s[tid], sm.v[tid], n, bias, avg);
+			else          agc_chains<false>(sm.x[tid], sm.s[tid], sm.v[tid], n, bias, avg);
+		}
+		__syncthreads();
+
+		/* ---- S3: gain apply: out = s * (5 / avg_before)  (agc.c:27,31) ----------------- */
+#pragma unroll
+		for (int k = 0; k < G * T / NT; k++) {
+			const int idx = tid + k * NT;
+			const int g = idx / T, i = idx % T;
+			float o = 0.0f;
+			if (i < n && chans[g] >= 0) o = fmul(sm.s[g][i], fdiv(5.0f, sm.v[g][i]));
+			sm.a[g][SONDE_FIR_HIST + i] = o;
+		}
+		__syncthreads();
+
+		/* ---- S4: FIR everywhere -------------------------------------------------------- */
+		fir_segment<P>(sm, tid / 32, tid % 32);
+		__syncthreads();
+
+		/* ---- S5: timing + slicer ------------------------------------------------------- */
+		if (my_ch >= 0)
+			timing_run<P>(sm, tid, n, tr, center, alpha, beta, max_fdev, my_ring, ring_mask, my_soft, p.soft_stride);
+
+		/* ---- slide the FIR history: a[g][0..48) <- a[g][n..n+48) ----------------------- */
+		float hv[2];
+#pragma unroll
+		for (int k = 0; k < 2; k++) {
+			const int idx = tid + k * NT;
+			hv[k] = (idx < G * SONDE_FIR_HIST) ? sm.a[idx / SONDE_FIR_HIST][n + idx % SONDE_FIR_HIST] : 0.0f;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < 2; k++) {
+			const int idx = tid + k * NT;
+			if (idx < G * SONDE_FIR_HIST) sm.a[idx / SONDE_FIR_HIST][idx % SONDE_FIR_HIST] = hv[k];
+		}
+		__syncthreads();
+	}
+
+	/* ---- save state ---------------------------------------------------------------------- */
+	if (my_ch >= 0) {
+		demod_state &st = p.st[my_ch];
+		st.agc_bias = bias; st.agc_avg = avg;
+		st.t_prev = tr.prev; st.t_phase = tr.phase; st.t_freq = tr.freq; st.t_state = tr.state;
+		st.bit_acc = tr.acc; st.bit_cnt = tr.cnt; st.nbits = tr.nbits; st.nsoft = tr.nsoft;
+		if (p.is_iq) st.disc_prev = sm.ph[tid][0];
+		if (tr.cnt)                                       /* left-aligned partial byte, gfsk.c:78 */
+			my_ring[(uint32_t)(tr.nbits >> 3) & ring_mask] = (uint8_t)(tr.acc << (8 - tr.cnt));
+	}
+	for (int i = tid; i < G * SONDE_FIR_HIST; i += NT) {
+		const int g = i / SONDE_FIR_HIST, k = i % SONDE_FIR_HIST;
+		const int ch = chans[g];
+		if (ch >= 0) p.st[ch].hist[k] = sm.a[g][k];
+	}
+}
+
+}  // namespace
+
+extern "C" size_t sonde_demod_smem_bytes(void) { return sizeof(smem_t); }
+
+/* Launches the GFSK demodulator over groups [group_base, group_base + n_groups) that share
+ * the polyphase count `phases`. */
+extern "C" cudaError_t sonde_launch_demod_gfsk(const demod_params *p, int group_base, int n_groups,
+                                               int phases, cudaStream_t stream)
+{
+	static bool attr_done = false;
+	if (!attr_done) {
+		cudaError_t e = cudaFuncSetAttribute(demod_gfsk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                     (int)sizeof(smem_t));
+		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(demod_gfsk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                         (int)sizeof(smem_t));
+		if (e != cudaSuccess) return e;
+		attr_done = true;
+	}
+	if (n_groups <= 0) return cudaSuccess;
+	if (phases == 1)
+		demod_gfsk_kernel<1><<<n_groups, NT, sizeof(smem_t), stream>>>(*p, group_base);
+	else
+		demod_gfsk_kernel<2><<<n_groups, NT, sizeof(smem_t), stream>>>(*p, group_base);
+	return cudaGetLastError();
+}
+
+#ifndef SONDE_HAVE_AFSK
+extern "C" cudaError_t sonde_launch_demod_afsk(const demod_params *, int, int n_groups, cudaStream_t)
+{
+	return n_groups > 0 ? cudaErrorNotSupported : cudaSuccess;
+}
+#endif

@@ -1,0 +1,459 @@
+/*
+ * sonde_b200.cu — the extern "C" shim declared in include/sonde_b200.h.
+ *
+ * Owns the per-channel state in HBM, sorts channels into type-homogeneous CTA groups,
+ * and enqueues K1 (demod.cu) + K2 (frame.cu) per process call on one CUDA stream.
+ * There is no CPU fallback: without an sm_100 device create() fails with
+ * SONDE_ERR_NODEVICE.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_state.h"
+
+extern "C" cudaError_t sonde_upload_modems(const sonde_modem *m);
+extern "C" cudaError_t sonde_upload_modems_frame(const sonde_modem *m);
+extern "C" cudaError_t sonde_launch_demod_gfsk(const demod_params *p, int group_base, int n_groups, int phases,
+                                               cudaStream_t stream);
+extern "C" cudaError_t sonde_launch_demod_afsk(const demod_params *p, int group_base, int n_groups,
+                                               cudaStream_t stream);
+extern "C" cudaError_t sonde_launch_frames(const frame_params *p, cudaStream_t stream);
+
+struct sonde_b200 {
+	sonde_b200_config cfg;
+	std::vector<int32_t> types;
+	sonde_modem modems[SONDE_NTYPES_];
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+
+	/* CTA groups, sorted: GFSK 1-phase | GFSK 2-phase | AFSK */
+	int n_groups = 0, groups_p1 = 0, groups_p2 = 0, groups_afsk = 0;
+	int32_t *d_group_chan = nullptr, *d_group_type = nullptr, *d_types = nullptr;
+
+	demod_state *d_demod = nullptr;
+	afsk_state *d_afsk = nullptr;
+	framer_state *d_framer = nullptr;
+	uint8_t *d_ring = nullptr;
+	uint32_t ring_bytes = 0;
+	sonde_frame_rec *d_recs = nullptr;
+	int32_t *d_counts = nullptr;
+	float *d_soft = nullptr;
+	int max_frames = 0, soft_stride = 0, bits_stride = 0;
+	void *d_in = nullptr;            /* staging for the host-buffer entry points */
+	size_t d_in_bytes = 0;
+	int32_t *h_counts = nullptr;     /* pinned */
+
+	int chunk_index = 0;
+	uint64_t bits_before_last = 0;
+	long launches = 0;
+	bool have_timing = false;
+	std::string err;
+};
+
+namespace {
+
+int fail(sonde_b200 *h, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+	if (h) {
+		h->err = what;
+		if (e != cudaSuccess) {
+			h->err += ": ";
+			h->err += cudaGetErrorString(e);
+		}
+	}
+	return code;
+}
+
+#define CK(call)                                                        \
+	do {                                                                \
+		cudaError_t e_ = (call);                                        \
+		if (e_ != cudaSuccess) return fail(h, SONDE_ERR_CUDA, #call, e_); \
+	} while (0)
+
+uint32_t next_pow2(uint32_t v)
+{
+	uint32_t p = 1;
+	while (p < v) p <<= 1;
+	return p;
+}
+
+/* most bits one call of `len` samples can add to a channel's stream: the NCO increment is
+ * clamped to centre + max_fdev (timing.c:73-75), two NCO counts per bit */
+int max_new_bits(const sonde_modem &m, int len)
+{
+	const double per_slot = ((double)m.freq0 + (double)m.max_fdev) / 2.0;
+	return (int)std::ceil((double)len * m.num_phases * per_slot) + 2;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sonde_b200_version(void) { return "sonde_b200 0.1 (sm_100a)"; }
+
+const char *sonde_b200_last_error(const sonde_b200 *h) { return h ? h->err.c_str() : "null handle"; }
+
+int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
+{
+	if (!out) return SONDE_ERR_ARG;
+	*out = nullptr;
+	if (!cfg || cfg->n_channels <= 0 || cfg->samplerate <= 0 || cfg->max_chunk_len <= 0 || !cfg->types)
+		return SONDE_ERR_ARG;
+	for (int c = 0; c < cfg->n_channels; c++)
+		if (cfg->types[c] < 0 || cfg->types[c] >= SONDE_NTYPES) return SONDE_ERR_ARG;
+
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev)
+		return SONDE_ERR_NODEVICE;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+		return SONDE_ERR_NODEVICE;       /* kernels are built for sm_100a only */
+
+	sonde_b200 *h = new sonde_b200();
+	h->cfg = *cfg;
+	h->types.assign(cfg->types, cfg->types + cfg->n_channels);
+	h->cfg.types = h->types.data();
+	h->device = cfg->device;
+	if (h->cfg.fm_gain == 0.0f) h->cfg.fm_gain = 0.636619747f;
+
+	auto bail = [&](int code) { sonde_b200_destroy(h); return code; };
+
+	for (int t = 0; t < SONDE_NTYPES; t++)
+		if (sonde_modem_init(&h->modems[t], t, cfg->samplerate)) {
+			/* a type that does not exist at this rate is only an error if a channel uses it */
+			for (int c = 0; c < cfg->n_channels; c++)
+				if (cfg->types[c] == t) return bail(SONDE_ERR_ARG);
+			memset(&h->modems[t], 0, sizeof(sonde_modem));
+		}
+
+	if (cudaSetDevice(h->device) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (sonde_upload_modems(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (sonde_upload_modems_frame(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	for (auto &e : h->ev)
+		if (cudaEventCreate(&e) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+
+	/* ---- channel groups: type-homogeneous CTAs, ordered by kernel variant ---------------- */
+	const int C = cfg->n_channels;
+	std::vector<int32_t> gchan, gtype;
+	auto add_groups = [&](auto pred) {
+		int added = 0;
+		for (int t = 0; t < SONDE_NTYPES; t++) {
+			if (!pred(h->modems[t])) continue;
+			std::vector<int32_t> ch;
+			for (int c = 0; c < C; c++)
+				if (h->types[c] == t) ch.push_back(c);
+			for (size_t i = 0; i < ch.size(); i += DEMOD_G) {
+				for (int k = 0; k < DEMOD_G; k++) gchan.push_back(i + k < ch.size() ? ch[i + k] : -1);
+				gtype.push_back(t);
+				added++;
+			}
+		}
+		return added;
+	};
+	h->groups_p1 = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 1; });
+	h->groups_p2 = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 2; });
+	h->groups_afsk = add_groups([](const sonde_modem &m) { return m.baud && m.afsk; });
+	h->n_groups = (int)gtype.size();
+
+	/* ---- sizes ----------------------------------------------------------------------------- */
+	int bits_max = 0, frames_max = 0;
+	uint32_t ring_need = 0;
+	for (int t = 0; t < SONDE_NTYPES; t++) {
+		if (std::find(h->types.begin(), h->types.end(), t) == h->types.end()) continue;
+		const sonde_modem &m = h->modems[t];
+		const int nb = max_new_bits(m, cfg->max_chunk_len);
+		bits_max = std::max(bits_max, nb);
+		frames_max = std::max(frames_max, nb / m.frame_bits + 2);
+		ring_need = std::max(ring_need, (uint32_t)((2 * m.frame_bits + m.sync_len + nb) / 8 + 64));
+	}
+	h->ring_bytes = next_pow2(ring_need);
+	h->max_frames = frames_max;
+	h->soft_stride = bits_max;
+	h->bits_stride = (bits_max + 7) / 8 + 1;
+
+#define CKB(call) do { if ((call) != cudaSuccess) { h->err = #call; return bail(SONDE_ERR_CUDA); } } while (0)
+	CKB(cudaMalloc(&h->d_group_chan, gchan.size() * sizeof(int32_t)));
+	CKB(cudaMalloc(&h->d_group_type, gtype.size() * sizeof(int32_t)));
+	CKB(cudaMalloc(&h->d_types, C * sizeof(int32_t)));
+	CKB(cudaMemcpy(h->d_group_chan, gchan.data(), gchan.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+	CKB(cudaMemcpy(h->d_group_type, gtype.data(), gtype.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+	CKB(cudaMemcpy(h->d_types, h->types.data(), C * sizeof(int32_t), cudaMemcpyHostToDevice));
+
+	CKB(cudaMalloc(&h->d_demod, (size_t)C * sizeof(demod_state)));
+	CKB(cudaMalloc(&h->d_framer, (size_t)C * sizeof(framer_state)));
+	CKB(cudaMalloc(&h->d_ring, (size_t)C * h->ring_bytes));
+	CKB(cudaMalloc(&h->d_recs, (size_t)C * h->max_frames * sizeof(sonde_frame_rec)));
+	CKB(cudaMalloc(&h->d_counts, (size_t)C * 2 * sizeof(int32_t)));
+	CKB(cudaMallocHost(&h->h_counts, (size_t)C * 2 * sizeof(int32_t)));
+	CKB(cudaMemset(h->d_ring, 0, (size_t)C * h->ring_bytes));
+	CKB(cudaMemset(h->d_framer, 0, (size_t)C * sizeof(framer_state)));
+	CKB(cudaMemset(h->d_counts, 0, (size_t)C * 2 * sizeof(int32_t)));
+	if (cfg->keep_soft) CKB(cudaMalloc(&h->d_soft, (size_t)C * h->soft_stride * sizeof(float)));
+	if (h->groups_afsk) {
+		CKB(cudaMalloc(&h->d_afsk, (size_t)C * sizeof(afsk_state)));
+		CKB(cudaMemset(h->d_afsk, 0, (size_t)C * sizeof(afsk_state)));
+	}
+
+	/* initial demodulator state: agc_init (agc.c:12-16), timing_init (timing.c:14-25), zero filter memory */
+	{
+		std::vector<demod_state> st(C);
+		memset(st.data(), 0, st.size() * sizeof(demod_state));
+		for (int c = 0; c < C; c++) {
+			st[c].agc_avg = 5.0f;
+			st[c].t_freq = h->modems[h->types[c]].freq0;
+			st[c].t_state = 1;
+		}
+		CKB(cudaMemcpy(h->d_demod, st.data(), st.size() * sizeof(demod_state), cudaMemcpyHostToDevice));
+	}
+#undef CKB
+	*out = h;
+	return SONDE_OK;
+}
+
+void sonde_b200_destroy(sonde_b200 *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->device);
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	cudaFree(h->d_group_chan); cudaFree(h->d_group_type); cudaFree(h->d_types);
+	cudaFree(h->d_demod); cudaFree(h->d_afsk); cudaFree(h->d_framer); cudaFree(h->d_ring);
+	cudaFree(h->d_recs); cudaFree(h->d_counts); cudaFree(h->d_soft); cudaFree(h->d_in);
+	if (h->h_counts) cudaFreeHost(h->h_counts);
+	for (auto &e : h->ev)
+		if (e) cudaEventDestroy(e);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+}
+
+static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_stride, int is_iq)
+{
+	if (!h) return SONDE_ERR_ARG;
+	if (!d_in || len == 0) return fail(h, SONDE_ERR_ARG, "null input or zero length");
+	if (len > (size_t)h->cfg.max_chunk_len) return fail(h, SONDE_ERR_TOOLONG, "len > max_chunk_len");
+	if (row_stride < len) return fail(h, SONDE_ERR_ARG, "row_stride < len");
+	CK(cudaSetDevice(h->device));
+
+	demod_params dp;
+	memset(&dp, 0, sizeof(dp));
+	dp.in = d_in;
+	dp.row_stride = row_stride;
+	dp.len = (int32_t)len;
+	dp.is_iq = is_iq;
+	dp.fm_gain = h->cfg.fm_gain;
+	dp.n_groups = h->n_groups;
+	dp.group_chan = h->d_group_chan;
+	dp.group_type = h->d_group_type;
+	dp.st = h->d_demod;
+	dp.ast = h->d_afsk;
+	dp.ring = h->d_ring;
+	dp.ring_bytes = h->ring_bytes;
+	dp.soft = h->d_soft;
+	dp.soft_stride = h->soft_stride;
+
+	CK(cudaEventRecord(h->ev[0], h->stream));
+	if (h->groups_p1) { CK(sonde_launch_demod_gfsk(&dp, 0, h->groups_p1, 1, h->stream)); h->launches++; }
+	if (h->groups_p2) { CK(sonde_launch_demod_gfsk(&dp, h->groups_p1, h->groups_p2, 2, h->stream)); h->launches++; }
+	if (h->groups_afsk) {
+		CK(sonde_launch_demod_afsk(&dp, h->groups_p1 + h->groups_p2, h->groups_afsk, h->stream));
+		h->launches++;
+	}
+	CK(cudaEventRecord(h->ev[1], h->stream));
+
+	frame_params fp;
+	memset(&fp, 0, sizeof(fp));
+	fp.n_channels = h->cfg.n_channels;
+	fp.types = h->d_types;
+	fp.dst = h->d_demod;
+	fp.fst = h->d_framer;
+	fp.ring = h->d_ring;
+	fp.ring_bytes = h->ring_bytes;
+	fp.recs = h->d_recs;
+	fp.max_frames = h->max_frames;
+	fp.chunk_index = h->chunk_index;
+	fp.counts = h->d_counts;
+	CK(sonde_launch_frames(&fp, h->stream));
+	h->launches++;
+	CK(cudaEventRecord(h->ev[2], h->stream));
+	h->have_timing = true;
+	h->chunk_index++;
+	return SONDE_OK;
+}
+
+int sonde_b200_process_iq_device(sonde_b200 *h, const void *d_iq, size_t len, size_t row_stride)
+{
+	return run_chunk(h, d_iq, len, row_stride, 1);
+}
+
+int sonde_b200_process_fm_device(sonde_b200 *h, const void *d_fm, size_t len, size_t row_stride)
+{
+	return run_chunk(h, d_fm, len, row_stride, 0);
+}
+
+static int process_host(sonde_b200 *h, const float *src, size_t len, int is_iq)
+{
+	if (!h) return SONDE_ERR_ARG;
+	if (!src || len == 0) return fail(h, SONDE_ERR_ARG, "null input or zero length");
+	if (len > (size_t)h->cfg.max_chunk_len) return fail(h, SONDE_ERR_TOOLONG, "len > max_chunk_len");
+	CK(cudaSetDevice(h->device));
+	const size_t esz = is_iq ? 2 * sizeof(float) : sizeof(float);
+	const size_t need = (size_t)h->cfg.n_channels * h->cfg.max_chunk_len * 2 * sizeof(float);
+	if (!h->d_in) {
+		CK(cudaMalloc(&h->d_in, need));
+		h->d_in_bytes = need;
+	}
+	/* the stream orders this copy after the previous call's kernels, so one staging buffer is enough */
+	CK(cudaMemcpyAsync(h->d_in, src, (size_t)h->cfg.n_channels * len * esz, cudaMemcpyHostToDevice, h->stream));
+	return run_chunk(h, h->d_in, len, len, is_iq);
+}
+
+int sonde_b200_process_iq(sonde_b200 *h, const float *iq, size_t len) { return process_host(h, iq, len, 1); }
+int sonde_b200_process_fm(sonde_b200 *h, const float *fm, size_t len) { return process_host(h, fm, len, 0); }
+
+int sonde_b200_max_frames(const sonde_b200 *h) { return h ? h->max_frames : SONDE_ERR_ARG; }
+int sonde_b200_bits_stride(const sonde_b200 *h) { return h ? h->bits_stride : SONDE_ERR_ARG; }
+int sonde_b200_soft_stride(const sonde_b200 *h) { return h ? h->soft_stride : SONDE_ERR_ARG; }
+long sonde_b200_launch_count(const sonde_b200 *h) { return h ? h->launches : 0; }
+
+int sonde_b200_sync(sonde_b200 *h)
+{
+	if (!h) return SONDE_ERR_ARG;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->stream));
+	return SONDE_OK;
+}
+
+int sonde_b200_fetch_counts(sonde_b200 *h, int32_t *frames, int32_t *ok)
+{
+	if (!h) return SONDE_ERR_ARG;
+	CK(cudaSetDevice(h->device));
+	const int C = h->cfg.n_channels;
+	CK(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)C * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	for (int c = 0; c < C; c++) {
+		if (frames) frames[c] = h->h_counts[2 * c];
+		if (ok) ok[c] = h->h_counts[2 * c + 1];
+	}
+	return SONDE_OK;
+}
+
+int sonde_b200_fetch(sonde_b200 *h, sonde_frame_rec *recs, int32_t *counts)
+{
+	if (!h || !recs || !counts) return SONDE_ERR_ARG;
+	int rc = sonde_b200_fetch_counts(h, counts, nullptr);
+	if (rc) return rc;
+	const int C = h->cfg.n_channels;
+	for (int c = 0; c < C; c++)
+		if (counts[c] > h->max_frames) return fail(h, SONDE_ERR_STATE, "frame record overflow");
+	CK(cudaMemcpyAsync(recs, h->d_recs, (size_t)C * h->max_frames * sizeof(sonde_frame_rec),
+	                   cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	return SONDE_OK;
+}
+
+int sonde_b200_fetch_bits(sonde_b200 *h, uint8_t *bits, int32_t *nbits)
+{
+	if (!h || !bits || !nbits) return SONDE_ERR_ARG;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->stream));
+	const int C = h->cfg.n_channels;
+	std::vector<demod_state> st(C);
+	std::vector<uint8_t> ring((size_t)C * h->ring_bytes);
+	CK(cudaMemcpy(st.data(), h->d_demod, st.size() * sizeof(demod_state), cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(ring.data(), h->d_ring, ring.size(), cudaMemcpyDeviceToHost));
+	memset(bits, 0, (size_t)C * h->bits_stride);
+	for (int c = 0; c < C; c++) {
+		/* the bits of the last call are the last nsoft positions of the stream */
+		const uint64_t end = st[c].nbits, n = (uint64_t)st[c].nsoft, start = end - n;
+		if (n > (uint64_t)(h->bits_stride - 1) * 8) return fail(h, SONDE_ERR_STATE, "bit tap overflow");
+		const uint8_t *r = ring.data() + (size_t)c * h->ring_bytes;
+		uint8_t *o = bits + (size_t)c * h->bits_stride;
+		for (uint64_t i = 0; i < n; i++) {
+			const uint64_t p = start + i;
+			const int b = (r[(p >> 3) & (h->ring_bytes - 1)] >> (7 - (p & 7))) & 1;
+			o[i >> 3] |= (uint8_t)(b << (7 - (i & 7)));
+		}
+		nbits[c] = (int32_t)n;
+	}
+	return SONDE_OK;
+}
+
+int sonde_b200_fetch_soft(sonde_b200 *h, float *soft, int32_t *nsoft)
+{
+	if (!h || !soft || !nsoft) return SONDE_ERR_ARG;
+	if (!h->d_soft) return fail(h, SONDE_ERR_STATE, "created without keep_soft");
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->stream));
+	const int C = h->cfg.n_channels;
+	std::vector<demod_state> st(C);
+	CK(cudaMemcpy(st.data(), h->d_demod, st.size() * sizeof(demod_state), cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(soft, h->d_soft, (size_t)C * h->soft_stride * sizeof(float), cudaMemcpyDeviceToHost));
+	for (int c = 0; c < C; c++) nsoft[c] = st[c].nsoft;
+	return SONDE_OK;
+}
+
+int sonde_b200_fetch_state(sonde_b200 *h, float *state /*[C][8]*/)
+{
+	if (!h || !state) return SONDE_ERR_ARG;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->stream));
+	const int C = h->cfg.n_channels;
+	std::vector<demod_state> st(C);
+	CK(cudaMemcpy(st.data(), h->d_demod, st.size() * sizeof(demod_state), cudaMemcpyDeviceToHost));
+	for (int c = 0; c < C; c++) {
+		float *o = state + 8 * c;
+		o[0] = st[c].agc_bias; o[1] = st[c].agc_avg; o[2] = st[c].t_phase; o[3] = st[c].t_freq;
+		o[4] = st[c].t_prev; o[5] = (float)st[c].t_state; o[6] = st[c].disc_prev; o[7] = 0;
+	}
+	return SONDE_OK;
+}
+
+int sonde_b200_last_kernel_ms(sonde_b200 *h, float *demod_ms, float *frame_ms)
+{
+	if (!h) return SONDE_ERR_ARG;
+	if (!h->have_timing) return fail(h, SONDE_ERR_STATE, "no process call yet");
+	CK(cudaSetDevice(h->device));
+	CK(cudaEventSynchronize(h->ev[2]));
+	float a = 0, b = 0;
+	CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+	CK(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+	if (demod_ms) *demod_ms = a;
+	if (frame_ms) *frame_ms = b;
+	return SONDE_OK;
+}
+
+int sonde_b200_modem_info(int type, int samplerate, float *taps, int taps_cap, float *consts)
+{
+	sonde_modem m;
+	if (sonde_modem_init(&m, type, samplerate)) return SONDE_ERR_ARG;
+	const int n = m.num_phases * SONDE_FIR_TAPS;
+	for (int i = 0; taps && i < n && i < taps_cap; i++) taps[i] = m.taps[i];
+	if (consts) {
+		consts[0] = m.freq0; consts[1] = m.alpha; consts[2] = m.beta; consts[3] = m.max_fdev;
+		consts[4] = (float)m.num_phases; consts[5] = (float)m.boxcar_len; consts[6] = m.f_mark; consts[7] = m.f_space;
+	}
+	return n;
+}
+
+void *sonde_b200_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+
+void sonde_b200_host_free(void *p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+void *sonde_b200_stream(sonde_b200 *h) { return h ? (void *)h->stream : nullptr; }
+
+}  /* extern "C" */

@@ -1,0 +1,54 @@
+"""Helpers for the -m gpu parity tests: drive the C ABI over a [C][n] batch in chunks."""
+import numpy as np
+
+from sdrpp_radiosonde_b200 import capi
+
+
+def rec_key(r, raw_bytes):
+    """Comparable view of one frame record (GPU structured-array row or ctypes FrameRec)."""
+    if isinstance(r, np.void):
+        n = max(int(r["data_len"]), 132)
+        return (int(r["chunk"]), int(r["sync_offset"]), int(r["inverted"]), int(r["status"]), int(r["ok"]),
+                int(r["aux"]), bytes(r["data"][:n]), bytes(r["raw"][:raw_bytes]))
+    n = max(int(r.data_len), 132)
+    return (int(r.chunk), int(r.sync_offset), int(r.inverted), int(r.status), int(r.ok), int(r.aux),
+            bytes(r.data[:n]), bytes(r.raw[:raw_bytes]))
+
+
+def run_gpu(types, batch, chunk, kind="fm", keep_soft=False, want_bits=False):
+    """Feed batch[C][n] through the GPU path in buffers of `chunk` samples.
+
+    Returns dict(frames=[list of record rows per channel], bits=[...], soft=[...], state=...).
+    """
+    C, n = batch.shape
+    dec = capi.BatchDecoder(types, min(chunk, n), keep_soft=keep_soft)
+    frames = [[] for _ in range(C)]
+    bits = [[] for _ in range(C)]
+    soft = [[] for _ in range(C)]
+    try:
+        for pos in range(0, n, chunk):
+            part = np.ascontiguousarray(batch[:, pos:pos + chunk])
+            if kind == "fm":
+                dec.process_fm(part)
+            else:
+                dec.process_iq(part)
+            recs, counts = dec.fetch()
+            for c in range(C):
+                frames[c].extend(recs[c, :counts[c]].copy())
+            if want_bits:
+                for c, b in enumerate(dec.fetch_bits()):
+                    bits[c].append(b)
+            if keep_soft:
+                for c, s in enumerate(dec.fetch_soft()):
+                    soft[c].append(s)
+        state = dec.fetch_state()
+        launches = dec.launch_count
+    finally:
+        dec.close()
+    return {
+        "frames": frames,
+        "bits": [np.concatenate(b) if b else np.zeros(0, np.uint8) for b in bits],
+        "soft": [np.concatenate(s) if s else np.zeros(0, np.float32) for s in soft],
+        "state": state,
+        "launches": launches,
+    }

@@ -1,0 +1,94 @@
+"""-m gpu: the CUDA path (through the C ABI) against the UNMODIFIED reference (oracle/_ref) and the
+C restatement (oracle/), on the same seeded synthetic signals.  Bit-exact on everything."""
+import numpy as np
+import pytest
+
+from sdrpp_radiosonde_b200 import synth
+from tests import reflib
+from tests.gpu_util import rec_key, run_gpu
+
+pytestmark = pytest.mark.gpu
+
+GFSK_TYPES = [synth.RS41, synth.DFM09, synth.M10, synth.IMS100, synth.MRZN1]
+BAUD = {t: synth.MODEMS[t].baud for t in range(7)}
+
+
+def checkers():
+    out = []
+    if reflib.have_ref():
+        out.append(reflib.RefLib())
+    if reflib.have_oracle():
+        out.append(reflib.OracleLib())
+    assert out, "neither oracle/_ref nor oracle/_build is built"
+    return out
+
+
+def make_fm_batch(stype, n_ch, n, **kw):
+    rows = []
+    for c in range(n_ch):
+        spec = synth.default_spec(stype, c)
+        for k, v in kw.items():
+            setattr(spec, k, v)
+        rows.append(synth.make_fm(spec, n))
+    return np.stack(rows)
+
+
+@pytest.mark.parametrize("stype", GFSK_TYPES)
+@pytest.mark.parametrize("chunk", [1024, 48000, 777])
+def test_frames_match_reference_fm(stype, chunk):
+    n_ch, n = 3, 48000 * 3
+    kw = {"bit_errors": 20} if stype == synth.RS41 else {}
+    batch = make_fm_batch(stype, n_ch, n, **kw)
+    got = run_gpu([stype] * n_ch, batch, chunk, kind="fm")
+    raw_bytes = (synth.MODEMS[stype].frame_bits + 7) // 8
+    for chk in checkers():
+        for c in range(n_ch):
+            want = chk.frames_run(stype, batch[c], chunk)
+            assert len(got["frames"][c]) == len(want), (chk.prefix, c, len(got["frames"][c]), len(want))
+            for i, (g, w) in enumerate(zip(got["frames"][c], want)):
+                assert rec_key(g, raw_bytes) == rec_key(w, raw_bytes), (chk.prefix, stype, c, i)
+            assert sum(int(w.ok) for w in want) > 0, "signal did not decode at all"
+
+
+@pytest.mark.parametrize("stype", GFSK_TYPES)
+@pytest.mark.parametrize("chunk", [1024, 48000])
+def test_bits_soft_and_state_bit_exact(stype, chunk):
+    n_ch, n = 2, 48000 * 2
+    batch = make_fm_batch(stype, n_ch, n)
+    got = run_gpu([stype] * n_ch, batch, chunk, kind="fm", keep_soft=True, want_bits=True)
+    for chk in checkers():
+        for c in range(n_ch):
+            bits = chk.demod_bits(stype, batch[c], chunk)
+            assert np.array_equal(got["bits"][c], bits), (chk.prefix, stype, c)
+            soft, state = chk.gfsk_soft(BAUD[stype], batch[c], chunk)
+            # north_star: soft symbols within 1e-5 relative -> required here: bit-identical
+            assert np.array_equal(got["soft"][c].view(np.uint32), soft.view(np.uint32)), (chk.prefix, stype, c)
+            assert np.array_equal(got["state"][c, :6].view(np.uint32), state[:6].view(np.uint32))
+
+
+def test_mixed_batch_and_ragged_groups():
+    """Channel grouping: mixed types in one handle, group sizes that do not fill a CTA."""
+    types = [synth.RS41, synth.M10, synth.DFM09, synth.RS41, synth.MRZN1, synth.M10, synth.IMS100,
+             synth.DFM09, synth.RS41, synth.RS41, synth.RS41]
+    n = 48000 * 2
+    batch = np.stack([synth.make_fm(synth.default_spec(t, c), n) for c, t in enumerate(types)])
+    got = run_gpu(types, batch, 4096, kind="fm")
+    chk = checkers()[0]
+    for c, t in enumerate(types):
+        want = chk.frames_run(t, batch[c], 4096)
+        raw_bytes = (synth.MODEMS[t].frame_bits + 7) // 8
+        assert [rec_key(g, raw_bytes) for g in got["frames"][c]] == [rec_key(w, raw_bytes) for w in want], (c, t)
+
+
+def test_zero_samples_bypass_agc():
+    """Exact-zero samples bypass the AGC without touching its state (agc.c:23)."""
+    n = 48000
+    fm = synth.make_fm(synth.default_spec(synth.RS41, 0), n)
+    fm[1000:1300] = 0.0
+    fm[5000] = 0.0
+    fm[-1] = 0.0
+    got = run_gpu([synth.RS41], fm[None, :], 4096, kind="fm", keep_soft=True, want_bits=True)
+    for chk in checkers():
+        soft, state = chk.gfsk_soft(4800, fm, 4096)
+        assert np.array_equal(got["soft"][0].view(np.uint32), soft.view(np.uint32))
+        assert np.array_equal(got["state"][0, :6].view(np.uint32), state[:6].view(np.uint32))
