@@ -45,7 +45,7 @@ extern "C" {
 #define SONDE_API
 #endif
 
-/* Sonde (decoder) types: the seven decoders of the reference (SD/include/*.h). */
+/* Sonde (decoder) types: the seven decoders of the reference (the headers under SD/include/). */
 enum sonde_type {
 	SONDE_RS41   = 0,   /* Vaisala RS41-SG          SD/sonde/rs41/   */
 	SONDE_DFM09  = 1,   /* GRAW DFM06/09/17         SD/sonde/dfm09/  */

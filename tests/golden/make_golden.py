@@ -76,6 +76,33 @@ def main():
     with open(os.path.join(HERE, "fec_known_answers.json"), "w") as f:
         json.dump(ka, f, indent=0)
 
+    # demodulator constants as the unmodified reference derives them (gfsk_init)
+    tabs = {}
+    for stype in range(5):
+        baud = synth.MODEMS[stype].baud
+        tabs[synth.TYPE_NAMES[stype]] = {
+            "baud": baud,
+            "taps_u32": [int(v) for v in ref.gfsk_taps(baud).view(np.uint32)],
+            "timing_u32": [int(v) for v in ref.gfsk_timing(baud).view(np.uint32)],
+        }
+    with open(os.path.join(HERE, "modem_tables.json"), "w") as f:
+        json.dump(tabs, f)
+
+    # soft symbols / loop state of the reference's own primitives on a seeded RS41 + M10 signal
+    soft = {}
+    for stype in (synth.RS41, synth.M10, synth.DFM09):
+        fm = synth.make_fm(synth.default_spec(stype, 7), 24000)
+        s, st = ref.gfsk_soft(synth.MODEMS[stype].baud, fm, 1024)
+        bits = ref.demod_bits(stype, fm, 1024)
+        soft[synth.TYPE_NAMES[stype]] = {
+            "n": 24000, "chunk": 1024, "channel": 7,
+            "fm_crc32": int(np.uint32(__import__("zlib").crc32(fm.tobytes()))),
+            "soft_u32": [int(v) for v in s.view(np.uint32)],
+            "state_u32": [int(v) for v in st[:6].view(np.uint32)],
+            "bits_hex": np.packbits(bits).tobytes().hex(), "nbits": int(bits.size)}
+    with open(os.path.join(HERE, "soft_symbols.json"), "w") as f:
+        json.dump(soft, f)
+
     # frame bytes decoded by the unmodified reference from seeded synthetic signals
     for stype in range(7):
         name = synth.TYPE_NAMES[stype]
