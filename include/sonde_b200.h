@@ -112,7 +112,7 @@ typedef struct {
 	float   fm_gain;          /* discriminator gain (1/deviation); 0 -> 2/pi, i.e.
 	                             dsp::demod::FM(samplerate=bw, bandwidth=bw/2)  src/main.cpp:57 */
 	int32_t keep_soft;        /* !=0: keep soft symbols for sonde_b200_fetch_soft()  */
-	int32_t reserved;
+	int32_t reserved;         /* bit 0: use the phase-by-phase demod kernel (cross-check only) */
 } sonde_b200_config;
 
 SONDE_API int  sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg);
@@ -134,6 +134,9 @@ SONDE_API int  sonde_b200_fetch(sonde_b200 *h, sonde_frame_rec *recs, int32_t *c
 
 /* Only the per-channel counters of the last call (cheap D2H): frames[C], ok[C]. Synchronises. */
 SONDE_API int  sonde_b200_fetch_counts(sonde_b200 *h, int32_t *frames, int32_t *ok);
+
+/* Running totals since create, per channel: framer windows, windows passing the gate, demodulated bits. */
+SONDE_API int  sonde_b200_fetch_totals(sonde_b200 *h, int64_t *frames, int64_t *ok, int64_t *bits);
 
 /* Parity taps for the last process call.
  *  bits : demodulated hard bits, MSB first, bits[C][bits_stride_bytes]; nbits[C]

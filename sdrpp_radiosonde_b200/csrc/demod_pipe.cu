@@ -1,0 +1,496 @@
+/*
+ * demod_pipe.cu — K1 (production): IQ / FM samples -> hard bits, as a warp-specialised
+ * software pipeline inside each CTA.
+ *
+ * One CTA owns PIPE_G = 8 channels of one sonde type and streams the chunk through tiles of
+ * PIPE_T = 256 samples.  Eleven warps, four roles, tiles handed over through mbarrier-guarded
+ * shared-memory rings, so that the three serial recurrences of the reference chain run
+ * concurrently with each other and with the data-parallel work:
+ *
+ *   PW  warps 0-7   S1 load + FM discriminator (tile k+1, inputs prefetched one tile earlier)
+ *                   S3 gain apply  a = s * (5 / avg)                       (tile k)
+ *                   S4 49-tap FIR at every position / polyphase branch     (tile k)
+ *   A1  warp 8      AGC bias recurrence      s = x - bias ; bias = .99 bias + .01 s   (agc.c:24-25)
+ *   A2  warp 9      AGC level recurrence     v = avg ; avg = .999 avg + .001 |s|      (agc.c:27-28)
+ *   TM  warp 10     Gardner NCO + retime + slicer, event driven: each lane (= channel) jumps from
+ *                   timing hit to timing hit and only *selects* precomputed FIR outputs
+ *                                                                         (timing.c:28-76, gfsk.c:75-125)
+ *
+ *        HBM --S1--> x[3] --A1--> s[2] --A2--> v[2] --S3--> a[2] --S4--> y[2] --TM--> bit ring (HBM)
+ *
+ * Lanes of A1/A2/TM are channels, so a serial step costs one warp instruction for all 8
+ * channels; the per-sample critical paths are 3 dependent fp32 ops (A1), 2 (A2) and one add
+ * per NCO slot plus ~20 ops per symbol (TM).  Everything is the reference's fp32 operation
+ * order (strict_math.cuh), so soft symbols stay bit-identical.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_state.h"
+#include "strict_math.cuh"
+
+static __constant__ sonde_modem c_modem[SONDE_NTYPES_];
+
+extern "C" cudaError_t sonde_upload_modems_pipe(const sonde_modem *m)
+{
+	return cudaMemcpyToSymbol(c_modem, m, sizeof(sonde_modem) * SONDE_NTYPES_);
+}
+
+namespace {
+
+constexpr int G = 8;                     /* channels per CTA                       */
+constexpr int T = 256;                   /* samples per tile                       */
+constexpr int NPW = 8;                   /* parallel-work warps                    */
+constexpr int NPWT = NPW * 32;           /* = T : one sample column per PW thread  */
+constexpr int W_A1 = NPW, W_A2 = NPW + 1, W_TM = NPW + 2;
+constexpr int NTHREADS = (NPW + 3) * 32;
+constexpr int RS = T + 4;                /* row stride: 16 B aligned, lanes (= rows) hit distinct banks */
+constexpr int AS = SONDE_FIR_HIST + T + 4;
+constexpr int R = 8;                     /* FIR outputs per thread                 */
+constexpr int NX = 3, NS2 = 2;           /* ring depths                            */
+constexpr unsigned FULL = 0xffffffffu;
+
+static_assert(G == NPW && T == NPWT && T / R == 32, "thread <-> work mappings below rely on this");
+
+template <int P>
+struct smem_t {
+	float x[NX][G][RS];                  /* discriminator output / FM input          */
+	float s[NS2][G][RS];                 /* bias-removed samples                     */
+	float v[NS2][G][RS];                 /* moving_avg before each sample's update   */
+	float a[NS2][G][AS];                 /* AGC output, [0,48) = previous tile tail  */
+	float y[NS2][P][G][RS];              /* FIR output per polyphase branch          */
+	float ph[G][RS];                     /* S1 scratch: phases, [g][0] = previous    */
+	float carry[2][G];                   /* last phase of the previous tile          */
+	float taps[P * SONDE_FIR_TAPS];
+	int   zflag[NX];                     /* tile contains exact-zero samples         */
+	unsigned long long xfull[NX], sfull[NS2], sfree[NS2], vfull[NS2], vfree[NS2], yfull[NS2], yfree[NS2];
+};
+
+/* ---- mbarrier helpers (CTA scope) --------------------------------------------------------- */
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *b, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"W_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra D_%=;\n"
+		"bra W_%=;\n"
+		"D_%=:\n"
+		"}\n" ::"r"(s32(b)), "r"(parity) : "memory");
+}
+/* all lanes of a warp finished their writes -> one arrival */
+__device__ __forceinline__ void warp_arrive(unsigned long long *b, int lane)
+{
+	__syncwarp();
+	if (lane == 0) mbar_arrive(b);
+}
+__device__ __forceinline__ void pw_barrier()
+{
+	asm volatile("bar.sync 1, %0;" ::"n"(NPWT) : "memory");
+}
+
+/* ---- TM helpers ----------------------------------------------------------------------------- */
+struct tm_regs {
+	float prev, phase, freq, interm, target;     /* target = (float)state : 1 = mid-symbol, 2 = symbol */
+	uint32_t acc;
+	int cnt, nsoft;
+	uint64_t nbits;
+};
+
+/* advance the NCO slot by slot until phase >= target (timing.c:32-38) or the tile's slots run out.
+ * On a hit `s` is the index one past the hit slot. */
+__device__ __forceinline__ bool nco_advance(float &phase, const float freq, const float target, int &s, const int ns)
+{
+	while (s + 4 <= ns) {
+		const float p1 = fadd(phase, freq), p2 = fadd(p1, freq), p3 = fadd(p2, freq), p4 = fadd(p3, freq);
+		const bool h1 = p1 >= target, h2 = p2 >= target, h3 = p3 >= target, h4 = p4 >= target;
+		if (h1 | h2 | h3 | h4) {
+			const int k = h1 ? 1 : h2 ? 2 : h3 ? 3 : 4;
+			phase = h1 ? p1 : h2 ? p2 : h3 ? p3 : p4;
+			s += k;
+			return true;
+		}
+		phase = p4;
+		s += 4;
+	}
+	while (s < ns) {
+		phase = fadd(phase, freq);
+		s++;
+		if (phase >= target) return true;
+	}
+	return false;
+}
+
+/* retime() + slicer at a symbol hit (timing.c:45-76, gfsk.c:99-115) */
+__device__ __forceinline__ void symbol_hit(tm_regs &t, const float yv, const float center, const float alpha,
+                                           const float beta, const float max_fdev, uint8_t *ring,
+                                           const uint32_t ring_mask, float *soft, const int soft_cap)
+{
+	const float err = (fmul(yv, t.prev) < 0.0f) ? fmul(fsub(yv, t.prev), t.interm) : 0.0f;
+	t.prev = yv;
+	float fd = fsub(t.freq, center);
+	const float ea = fmul(err, alpha);
+	const float lo = (2.0f < ea) ? 2.0f : ea;
+	const float cl = (-2.0f > lo) ? -2.0f : lo;
+	t.phase = fsub(t.phase, fsub(2.0f, cl));
+	fd = fadd(fd, fmul(err, beta));
+	const float fl = (max_fdev < fd) ? max_fdev : fd;
+	fd = (-max_fdev > fl) ? -max_fdev : fl;
+	t.freq = fadd(center, fd);
+	t.target = 1.0f;
+
+	t.acc = (t.acc << 1) | (yv > 0.0f ? 1u : 0u);
+	t.cnt++;
+	if (soft && t.nsoft < soft_cap) soft[t.nsoft] = yv;
+	t.nsoft++;
+	if (t.cnt == 8) {
+		ring[(uint32_t)(t.nbits >> 3) & ring_mask] = (uint8_t)t.acc;
+		t.acc = 0;
+		t.cnt = 0;
+	}
+	t.nbits++;
+}
+
+/* filter_get(phase) of slot index sl: sample sl / P, polyphase branch P-1-(sl % P) (filter.c:54) */
+template <int P>
+__device__ __forceinline__ float y_at(const float (*y)[G][RS], const int g, const int sl)
+{
+	return (P == 1) ? y[0][g][sl] : y[P - 1 - (sl % P)][g][sl / P];
+}
+
+/* ---- S4: FIR at R consecutive positions, reference summation order (filter.c:59-61) ---------- */
+template <int P>
+__device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS], const float *taps, int g, int seg)
+{
+	float w[R + SONDE_FIR_HIST];
+	const float4 *src = reinterpret_cast<const float4 *>(arow + seg * R);
+#pragma unroll
+	for (int k = 0; k < (R + SONDE_FIR_HIST) / 4; k++) {
+		const float4 q = src[k];
+		w[4 * k + 0] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+	}
+#pragma unroll
+	for (int br = 0; br < P; br++) {
+		float acc[R];
+#pragma unroll
+		for (int r = 0; r < R; r++) acc[r] = 0.0f;
+#pragma unroll
+		for (int i = 0; i < SONDE_FIR_TAPS; i++) {
+			const float c = taps[br * SONDE_FIR_TAPS + i];
+#pragma unroll
+			for (int r = 0; r < R; r++) acc[r] = fadd(acc[r], fmul(w[r + i], c));
+		}
+		float4 *dst = reinterpret_cast<float4 *>(&y[br][g][seg * R]);
+		dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+		dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+	}
+}
+
+template <int P, bool IQ>
+__global__ void __launch_bounds__(NTHREADS, 1)
+demod_pipe_kernel(const demod_params p, const int group_base)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	smem_t<P> &sm = *reinterpret_cast<smem_t<P> *>(smem_raw);
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int grp = group_base + blockIdx.x;
+	const sonde_modem &md = c_modem[p.group_type[grp]];
+	const int *chans = p.group_chan + (size_t)grp * G;
+	const int L = p.len;
+	const int ntiles = (L + T - 1) / T;
+
+	/* ---- prologue ------------------------------------------------------------------------- */
+	if (tid == 0) {
+		for (int i = 0; i < NX; i++) { mbar_init(&sm.xfull[i], NPW); sm.zflag[i] = 0; }
+		for (int i = 0; i < NS2; i++) {
+			mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sfree[i], 1 + NPW);
+			mbar_init(&sm.vfull[i], 1); mbar_init(&sm.vfree[i], NPW);
+			mbar_init(&sm.yfull[i], NPW); mbar_init(&sm.yfree[i], 1);
+		}
+	}
+	for (int i = tid; i < P * SONDE_FIR_TAPS; i += NTHREADS) sm.taps[i] = md.taps[i];
+	for (int i = tid; i < G * SONDE_FIR_HIST; i += NTHREADS) {
+		const int g = i / SONDE_FIR_HIST, k = i % SONDE_FIR_HIST;
+		const int ch = chans[g];
+		/* tile 0 reads its head from "slot 1's tail" */
+		sm.a[1][g][T + k] = (ch >= 0) ? p.st[ch].hist[k] : 0.0f;
+	}
+	if (tid < G) sm.carry[0][tid] = (chans[tid] >= 0) ? p.st[chans[tid]].disc_prev : 0.0f;
+	__syncthreads();
+
+	if (warp < NPW) {
+		/* =============================== PW: S1 / S3 / S4 =================================== */
+		const int t = tid;                       /* sample column owned in S1 / S3              */
+		int ch_of[G];
+#pragma unroll
+		for (int g = 0; g < G; g++) ch_of[g] = chans[g];
+
+		float2 q[G];                             /* prefetched raw input of the next S1 tile    */
+		auto prefetch = [&](int tile) {
+			const int i = tile * T + t;
+#pragma unroll
+			for (int g = 0; g < G; g++) {
+				q[g] = make_float2(0.0f, 0.0f);
+				if (tile < ntiles && i < L && ch_of[g] >= 0) {
+					if (IQ) q[g] = __ldg(static_cast<const float2 *>(p.in) + (size_t)ch_of[g] * p.row_stride + i);
+					else    q[g].x = __ldg(static_cast<const float *>(p.in) + (size_t)ch_of[g] * p.row_stride + i);
+				}
+			}
+		};
+		/* S1 of `tile` from the registers loaded by prefetch(tile); issues the loads of tile+1 */
+		auto stage1 = [&](int tile) {
+			const int slot = tile % NX;
+			const int n = min(T, L - tile * T);
+			float cur[G];
+			if (t == 0) sm.zflag[slot] = 0;
+#pragma unroll
+			for (int g = 0; g < G; g++) {
+				if (IQ) {
+					const float phv = (t < n) ? det_phase(q[g].x, q[g].y) : 0.0f;
+					sm.ph[g][t + 1] = phv;
+					if (t == n - 1) sm.carry[(tile + 1) & 1][g] = phv;
+				} else {
+					cur[g] = q[g].x;
+				}
+			}
+			if (IQ && t < G) sm.ph[t][0] = sm.carry[tile & 1][t];
+			prefetch(tile + 1);
+			pw_barrier();
+			bool zero = false;
+#pragma unroll
+			for (int g = 0; g < G; g++) {
+				const float xv = IQ ? disc_step(sm.ph[g][t + 1], sm.ph[g][t], p.fm_gain) : cur[g];
+				sm.x[slot][g][t] = xv;
+				zero |= (t < n && ch_of[g] >= 0 && xv == 0.0f);
+			}
+			if (zero) atomicOr(&sm.zflag[slot], 1);
+			warp_arrive(&sm.xfull[slot], lane);
+		};
+
+		prefetch(0);
+		stage1(0);
+
+		for (int k = 0; k < ntiles; k++) {
+			const int n = min(T, L - k * T);
+			const int xs = k % NX, ss = k % NS2;
+			const uint32_t par = (k / NS2) & 1;
+
+			/* ---- S1(k+1) ---- */
+			if (k + 1 < ntiles) stage1(k + 1);
+
+			/* ---- S3(k): a = s * (5 / avg_before)  (agc.c:27,31); zero samples pass as 0 ---- */
+			mbar_wait(&sm.vfull[ss], par);            /* implies sfull[ss] (A2 consumed it first) */
+			const bool zslow = sm.zflag[xs] != 0;
+#pragma unroll
+			for (int g = 0; g < G; g++) {
+				float o = 0.0f;
+				if (t < n && ch_of[g] >= 0 && !(zslow && sm.x[xs][g][t] == 0.0f))
+					o = fmul(sm.s[ss][g][t], fdiv(5.0f, sm.v[ss][g][t]));
+				sm.a[ss][g][SONDE_FIR_HIST + t] = o;
+			}
+			/* head = tail of the previous tile */
+			for (int i = t; i < G * SONDE_FIR_HIST; i += NPWT) {
+				const int g = i / SONDE_FIR_HIST, j = i % SONDE_FIR_HIST;
+				sm.a[ss][g][j] = sm.a[ss ^ 1][g][T + j];
+			}
+			warp_arrive(&sm.sfree[ss], lane);
+			if (lane == 0) mbar_arrive(&sm.vfree[ss]);
+			pw_barrier();
+
+			/* ---- S4(k) ---- */
+			mbar_wait(&sm.yfree[ss], par ^ 1);
+			fir_segment<P>(sm.a[ss][warp], sm.y[ss], sm.taps, warp, lane);
+			warp_arrive(&sm.yfull[ss], lane);
+		}
+
+		/* save the filter memory (last 48 inputs) and the discriminator phase */
+		pw_barrier();
+		{
+			const int ls = (ntiles - 1) % NS2;
+			const int nl = L - (ntiles - 1) * T;
+			for (int i = t; i < G * SONDE_FIR_HIST; i += NPWT) {
+				const int g = i / SONDE_FIR_HIST, j = i % SONDE_FIR_HIST;
+				if (ch_of[g] >= 0) p.st[ch_of[g]].hist[j] = sm.a[ls][g][nl + j];
+			}
+			if (IQ && t < G && chans[t] >= 0) p.st[chans[t]].disc_prev = sm.carry[ntiles & 1][t];
+		}
+	} else if (warp == W_A1) {
+		/* =============================== A1: bias recurrence ================================ */
+		const int g = lane & (G - 1);
+		const bool own = lane < G && chans[g] >= 0;
+		float bias = own ? p.st[chans[g]].agc_bias : 0.0f;
+		const float k1 = fsub(1.0f, 0.01f), k0 = 0.01f;
+		for (int k = 0; k < ntiles; k++) {
+			const int n = min(T, L - k * T);
+			const int xs = k % NX, ss = k % NS2;
+			const uint32_t par = (k / NS2) & 1;
+			mbar_wait(&sm.xfull[xs], (k / NX) & 1);
+			mbar_wait(&sm.sfree[ss], par ^ 1);
+			const float *__restrict__ x = sm.x[xs][g];
+			float *__restrict__ s = sm.s[ss][g];
+			if (lane < G) {
+				if (!sm.zflag[xs]) {
+					int i = 0;
+					float4 xv = *reinterpret_cast<const float4 *>(x);
+					for (; i + 4 <= n; i += 4) {
+						const float4 nx = *reinterpret_cast<const float4 *>(x + i + 4);   /* row has 4 floats of slack */
+						float4 o;
+						o.x = fsub(xv.x, bias); bias = fadd(fmul(bias, k1), fmul(o.x, k0));
+						o.y = fsub(xv.y, bias); bias = fadd(fmul(bias, k1), fmul(o.y, k0));
+						o.z = fsub(xv.z, bias); bias = fadd(fmul(bias, k1), fmul(o.z, k0));
+						o.w = fsub(xv.w, bias); bias = fadd(fmul(bias, k1), fmul(o.w, k0));
+						*reinterpret_cast<float4 *>(s + i) = o;
+						xv = nx;
+					}
+					for (; i < n; i++) {
+						const float o = fsub(x[i], bias);
+						bias = fadd(fmul(bias, k1), fmul(o, k0));
+						s[i] = o;
+					}
+				} else {
+					for (int i = 0; i < n; i++) {
+						const float xi = x[i];
+						if (xi == 0.0f) { s[i] = 0.0f; continue; }        /* agc.c:23 */
+						const float o = fsub(xi, bias);
+						bias = fadd(fmul(bias, k1), fmul(o, k0));
+						s[i] = o;
+					}
+				}
+			}
+			warp_arrive(&sm.sfull[ss], lane);
+		}
+		if (own) p.st[chans[g]].agc_bias = bias;
+	} else if (warp == W_A2) {
+		/* =============================== A2: level recurrence =============================== */
+		const int g = lane & (G - 1);
+		const bool own = lane < G && chans[g] >= 0;
+		float avg = own ? p.st[chans[g]].agc_avg : 5.0f;
+		const float k1 = fsub(1.0f, 0.001f), k0 = 0.001f;
+		for (int k = 0; k < ntiles; k++) {
+			const int n = min(T, L - k * T);
+			const int xs = k % NX, ss = k % NS2;
+			const uint32_t par = (k / NS2) & 1;
+			mbar_wait(&sm.sfull[ss], par);
+			mbar_wait(&sm.vfree[ss], par ^ 1);
+			const float *__restrict__ s = sm.s[ss][g];
+			const float *__restrict__ x = sm.x[xs][g];
+			float *__restrict__ v = sm.v[ss][g];
+			if (lane < G) {
+				if (!sm.zflag[xs]) {
+					int i = 0;
+					float4 sv = *reinterpret_cast<const float4 *>(s);
+					for (; i + 4 <= n; i += 4) {
+						const float4 nx = *reinterpret_cast<const float4 *>(s + i + 4);
+						float4 o;
+						o.x = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.x), k0));
+						o.y = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.y), k0));
+						o.z = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.z), k0));
+						o.w = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.w), k0));
+						*reinterpret_cast<float4 *>(v + i) = o;
+						sv = nx;
+					}
+					for (; i < n; i++) {
+						v[i] = avg;
+						avg = fadd(fmul(avg, k1), fmul(fabsf(s[i]), k0));
+					}
+				} else {
+					for (int i = 0; i < n; i++) {
+						v[i] = avg;
+						if (x[i] == 0.0f) continue;
+						avg = fadd(fmul(avg, k1), fmul(fabsf(s[i]), k0));
+					}
+				}
+			}
+			warp_arrive(&sm.vfull[ss], lane);
+			if (lane == 0) mbar_arrive(&sm.sfree[ss]);
+		}
+		if (own) p.st[chans[g]].agc_avg = avg;
+	} else {
+		/* =============================== TM: timing + slicer ================================ */
+		const int g = lane & (G - 1);
+		const bool own = lane < G && chans[g] >= 0;
+		const int ch = own ? chans[g] : 0;
+		tm_regs tr = {};
+		const float center = md.freq0, alpha = md.alpha, beta = md.beta, max_fdev = md.max_fdev;
+		uint8_t *ring = p.ring + (size_t)ch * p.ring_bytes;
+		float *soft = (own && p.soft) ? p.soft + (size_t)ch * p.soft_stride : nullptr;
+		const uint32_t ring_mask = p.ring_bytes - 1;
+		if (own) {
+			const demod_state &st = p.st[ch];
+			tr.prev = st.t_prev; tr.phase = st.t_phase; tr.freq = st.t_freq;
+			tr.target = (float)st.t_state;
+			tr.interm = 0.0f;                               /* gfsk.c:73 */
+			tr.acc = st.bit_acc; tr.cnt = st.bit_cnt; tr.nbits = st.nbits; tr.nsoft = 0;
+		}
+		for (int k = 0; k < ntiles; k++) {
+			const int n = min(T, L - k * T);
+			const int ss = k % NS2;
+			mbar_wait(&sm.yfull[ss], (k / NS2) & 1);
+			const float (*y)[G][RS] = sm.y[ss];
+			const int ns = own ? n * P : 0;
+			int s = 0;
+			/* lanes that ended the previous tile between the mid-symbol and the symbol instant first
+			 * finish that symbol, so that every lane enters the main loop waiting for a mid-symbol hit */
+			if (tr.target == 2.0f) {
+				if (nco_advance(tr.phase, tr.freq, 2.0f, s, ns))
+					symbol_hit(tr, y_at<P>(y, g, s - 1), center, alpha, beta, max_fdev, ring, ring_mask, soft, p.soft_stride);
+			}
+			for (;;) {
+				bool live = false;
+				if (tr.target == 1.0f && nco_advance(tr.phase, tr.freq, 1.0f, s, ns)) {
+					tr.interm = y_at<P>(y, g, s - 1);
+					tr.target = 2.0f;
+					if (nco_advance(tr.phase, tr.freq, 2.0f, s, ns)) {
+						symbol_hit(tr, y_at<P>(y, g, s - 1), center, alpha, beta, max_fdev, ring, ring_mask, soft,
+						           p.soft_stride);
+						live = true;
+					}
+				}
+				if (!__any_sync(FULL, live)) break;
+			}
+			warp_arrive(&sm.yfree[ss], lane);
+		}
+		if (own) {
+			demod_state &st = p.st[ch];
+			st.t_prev = tr.prev; st.t_phase = tr.phase; st.t_freq = tr.freq; st.t_state = (int)tr.target;
+			st.bit_acc = tr.acc; st.bit_cnt = tr.cnt; st.nbits = tr.nbits; st.nsoft = tr.nsoft;
+			if (tr.cnt) ring[(uint32_t)(tr.nbits >> 3) & ring_mask] = (uint8_t)(tr.acc << (8 - tr.cnt));
+		}
+	}
+}
+
+template <int P, bool IQ>
+cudaError_t launch(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
+{
+	static bool attr_done = false;
+	if (!attr_done) {
+		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                     (int)sizeof(smem_t<P>));
+		if (e != cudaSuccess) return e;
+		attr_done = true;
+	}
+	demod_pipe_kernel<P, IQ><<<n_groups, NTHREADS, sizeof(smem_t<P>), stream>>>(*p, group_base);
+	return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" cudaError_t sonde_launch_demod_pipe(const demod_params *p, int group_base, int n_groups, int phases,
+                                               cudaStream_t stream)
+{
+	if (n_groups <= 0) return cudaSuccess;
+	if (phases == 1) return p->is_iq ? launch<1, true>(p, group_base, n_groups, stream) : launch<1, false>(p, group_base, n_groups, stream);
+	return p->is_iq ? launch<2, true>(p, group_base, n_groups, stream) : launch<2, false>(p, group_base, n_groups, stream);
+}

@@ -22,6 +22,9 @@ extern "C" cudaError_t sonde_upload_modems(const sonde_modem *m);
 extern "C" cudaError_t sonde_upload_modems_frame(const sonde_modem *m);
 extern "C" cudaError_t sonde_launch_demod_gfsk(const demod_params *p, int group_base, int n_groups, int phases,
                                                cudaStream_t stream);
+extern "C" cudaError_t sonde_upload_modems_pipe(const sonde_modem *m);
+extern "C" cudaError_t sonde_launch_demod_pipe(const demod_params *p, int group_base, int n_groups, int phases,
+                                              cudaStream_t stream);
 extern "C" cudaError_t sonde_launch_demod_afsk(const demod_params *p, int group_base, int n_groups,
                                                cudaStream_t stream);
 extern "C" cudaError_t sonde_launch_frames(const frame_params *p, cudaStream_t stream);
@@ -137,6 +140,7 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	if (cudaSetDevice(h->device) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_frame(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (sonde_upload_modems_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	for (auto &e : h->ev)
 		if (cudaEventCreate(&e) != cudaSuccess) return bail(SONDE_ERR_CUDA);
@@ -260,8 +264,11 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	dp.soft_stride = h->soft_stride;
 
 	CK(cudaEventRecord(h->ev[0], h->stream));
-	if (h->groups_p1) { CK(sonde_launch_demod_gfsk(&dp, 0, h->groups_p1, 1, h->stream)); h->launches++; }
-	if (h->groups_p2) { CK(sonde_launch_demod_gfsk(&dp, h->groups_p1, h->groups_p2, 2, h->stream)); h->launches++; }
+	/* production kernel: the warp-specialised pipeline; reserved bit 0 selects the phase-by-phase
+	 * kernel of demod.cu (kept as an independent cross-check for the tests) */
+	auto demod = (h->cfg.reserved & 1) ? sonde_launch_demod_gfsk : sonde_launch_demod_pipe;
+	if (h->groups_p1) { CK(demod(&dp, 0, h->groups_p1, 1, h->stream)); h->launches++; }
+	if (h->groups_p2) { CK(demod(&dp, h->groups_p1, h->groups_p2, 2, h->stream)); h->launches++; }
 	if (h->groups_afsk) {
 		CK(sonde_launch_demod_afsk(&dp, h->groups_p1 + h->groups_p2, h->groups_afsk, h->stream));
 		h->launches++;
@@ -341,6 +348,24 @@ int sonde_b200_fetch_counts(sonde_b200 *h, int32_t *frames, int32_t *ok)
 	for (int c = 0; c < C; c++) {
 		if (frames) frames[c] = h->h_counts[2 * c];
 		if (ok) ok[c] = h->h_counts[2 * c + 1];
+	}
+	return SONDE_OK;
+}
+
+int sonde_b200_fetch_totals(sonde_b200 *h, int64_t *frames, int64_t *ok, int64_t *bits)
+{
+	if (!h) return SONDE_ERR_ARG;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->stream));
+	const int C = h->cfg.n_channels;
+	std::vector<framer_state> fs(C);
+	std::vector<demod_state> ds(C);
+	CK(cudaMemcpy(fs.data(), h->d_framer, fs.size() * sizeof(framer_state), cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(ds.data(), h->d_demod, ds.size() * sizeof(demod_state), cudaMemcpyDeviceToHost));
+	for (int c = 0; c < C; c++) {
+		if (frames) frames[c] = fs[c].frames_total;
+		if (ok) ok[c] = fs[c].ok_total;
+		if (bits) bits[c] = (int64_t)ds[c].nbits;
 	}
 	return SONDE_OK;
 }

@@ -191,6 +191,23 @@ class OracleLib(_FrameRunner):
         self.lib = ctypes.CDLL(path)
 
 
+def _frames_run_iq(self, stype, iq, chunk, samplerate=48000, gain=0.0, max_recs=None):
+    iq = np.ascontiguousarray(iq, dtype=np.complex64)
+    if max_recs is None:
+        max_recs = iq.size // 400 + 64
+    recs = (FrameRec * max_recs)()
+    fn = self.lib.orc_frames_run_iq
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float,
+                   ctypes.POINTER(FrameRec), ctypes.c_int]
+    n = fn(stype, samplerate, iq.ctypes.data, iq.size, chunk, gain, recs, max_recs)
+    assert 0 <= n <= max_recs, n
+    return [recs[i] for i in range(n)]
+
+
+OracleLib.frames_run_iq = _frames_run_iq
+
+
 def have_ref():
     return os.path.exists(REF_SO)
 
