@@ -42,8 +42,15 @@ constexpr int G = 8;                     /* channels per CTA                    
 constexpr int T = 256;                   /* samples per tile                       */
 constexpr int NPW = 8;                   /* parallel-work warps                    */
 constexpr int NPWT = NPW * 32;           /* = T : one sample column per PW thread  */
-constexpr int W_A1 = NPW, W_A2 = NPW + 1, W_TM = NPW + 2;
 constexpr int NTHREADS = (NPW + 3) * 32;
+/* Warp roles, chosen so that the four schedulers (warp id % 4) carry similar issue load:
+ *   SMSP0: PW PW PW | SMSP1: PW PW PW | SMSP2: A1 A2 PW | SMSP3: TM PW          */
+constexpr int W_A1 = 2, W_A2 = 6, W_TM = 3;
+__device__ __forceinline__ int pw_index(int warp)
+{
+	/* warps 0,1,4,5,7,8,9,10 -> 0..7 */
+	return warp < 2 ? warp : warp < 6 ? warp - 2 : warp - 3;
+}
 constexpr int RS = T + 4;                /* row stride: 16 B aligned, lanes (= rows) hit distinct banks */
 constexpr int AS = SONDE_FIR_HIST + T + 4;
 constexpr int R = 8;                     /* FIR outputs per thread                 */
@@ -108,34 +115,11 @@ struct tm_regs {
 	uint64_t nbits;
 };
 
-/* advance the NCO slot by slot until phase >= target (timing.c:32-38) or the tile's slots run out.
- * On a hit `s` is the index one past the hit slot. */
-__device__ __forceinline__ bool nco_advance(float &phase, const float freq, const float target, int &s, const int ns)
-{
-	while (s + 4 <= ns) {
-		const float p1 = fadd(phase, freq), p2 = fadd(p1, freq), p3 = fadd(p2, freq), p4 = fadd(p3, freq);
-		const bool h1 = p1 >= target, h2 = p2 >= target, h3 = p3 >= target, h4 = p4 >= target;
-		if (h1 | h2 | h3 | h4) {
-			const int k = h1 ? 1 : h2 ? 2 : h3 ? 3 : 4;
-			phase = h1 ? p1 : h2 ? p2 : h3 ? p3 : p4;
-			s += k;
-			return true;
-		}
-		phase = p4;
-		s += 4;
-	}
-	while (s < ns) {
-		phase = fadd(phase, freq);
-		s++;
-		if (phase >= target) return true;
-	}
-	return false;
-}
-
 /* retime() + slicer at a symbol hit (timing.c:45-76, gfsk.c:99-115) */
 __device__ __forceinline__ void symbol_hit(tm_regs &t, const float yv, const float center, const float alpha,
                                            const float beta, const float max_fdev, uint8_t *ring,
-                                           const uint32_t ring_mask, float *soft, const int soft_cap)
+                                           const uint32_t ring_mask, float *soft, const int soft_cap,
+                                           const bool writer)
 {
 	const float err = (fmul(yv, t.prev) < 0.0f) ? fmul(fsub(yv, t.prev), t.interm) : 0.0f;
 	t.prev = yv;
@@ -155,7 +139,7 @@ __device__ __forceinline__ void symbol_hit(tm_regs &t, const float yv, const flo
 	if (soft && t.nsoft < soft_cap) soft[t.nsoft] = yv;
 	t.nsoft++;
 	if (t.cnt == 8) {
-		ring[(uint32_t)(t.nbits >> 3) & ring_mask] = (uint8_t)t.acc;
+		if (writer) ring[(uint32_t)(t.nbits >> 3) & ring_mask] = (uint8_t)t.acc;
 		t.acc = 0;
 		t.cnt = 0;
 	}
@@ -197,7 +181,7 @@ __device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS]
 	}
 }
 
-template <int P, bool IQ>
+template <int P, int N, bool IQ>
 __global__ void __launch_bounds__(NTHREADS, 1)
 demod_pipe_kernel(const demod_params p, const int group_base)
 {
@@ -230,9 +214,10 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	if (tid < G) sm.carry[0][tid] = (chans[tid] >= 0) ? p.st[chans[tid]].disc_prev : 0.0f;
 	__syncthreads();
 
-	if (warp < NPW) {
+	if (warp != W_A1 && warp != W_A2 && warp != W_TM) {
 		/* =============================== PW: S1 / S3 / S4 =================================== */
-		const int t = tid;                       /* sample column owned in S1 / S3              */
+		const int pw = pw_index(warp);           /* 0..7 : FIR channel row owned in S4          */
+		const int t = pw * 32 + lane;            /* sample column owned in S1 / S3              */
 		int ch_of[G];
 #pragma unroll
 		for (int g = 0; g < G; g++) ch_of[g] = chans[g];
@@ -311,7 +296,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 
 			/* ---- S4(k) ---- */
 			mbar_wait(&sm.yfree[ss], par ^ 1);
-			fir_segment<P>(sm.a[ss][warp], sm.y[ss], sm.taps, warp, lane);
+			fir_segment<P>(sm.a[ss][pw], sm.y[ss], sm.taps, pw, lane);
 			warp_arrive(&sm.yfull[ss], lane);
 		}
 
@@ -418,14 +403,23 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 		}
 		if (own) p.st[chans[g]].agc_avg = avg;
 	} else {
-		/* =============================== TM: timing + slicer ================================ */
-		const int g = lane & (G - 1);
-		const bool own = lane < G && chans[g] >= 0;
+		/* =============================== TM: timing + slicer ================================
+		 * lane = 4 * channel + helper.  The four helper lanes of a channel carry identical state and
+		 * run one straight-line "round" together:
+		 *   1. the NCO chain p_k = p_{k-1} + freq for the next N slots (the reference's adds, in order)
+		 *   2. each helper tests the slots k = 4j + h + 1 against the mid-symbol (>= 1) and symbol (>= 2)
+		 *      thresholds; warp votes assemble per-channel hit masks (timing.c:35)
+		 *   3. first mid hit -> interm, first later symbol hit -> retime + slice (timing.c:45-76);
+		 *      the round consumes the slots up to that symbol (or all N)
+		 * No data-dependent branches, so the 8 channels never serialise. */
+		const int g = lane >> 2, h = lane & 3;
+		const bool own = chans[g] >= 0;
 		const int ch = own ? chans[g] : 0;
 		tm_regs tr = {};
 		const float center = md.freq0, alpha = md.alpha, beta = md.beta, max_fdev = md.max_fdev;
 		uint8_t *ring = p.ring + (size_t)ch * p.ring_bytes;
-		float *soft = (own && p.soft) ? p.soft + (size_t)ch * p.soft_stride : nullptr;
+		float *soft = (own && h == 0 && p.soft) ? p.soft + (size_t)ch * p.soft_stride : nullptr;
+		const bool writer = own && h == 0;
 		const uint32_t ring_mask = p.ring_bytes - 1;
 		if (own) {
 			const demod_state &st = p.st[ch];
@@ -441,28 +435,54 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			const float (*y)[G][RS] = sm.y[ss];
 			const int ns = own ? n * P : 0;
 			int s = 0;
-			/* lanes that ended the previous tile between the mid-symbol and the symbol instant first
-			 * finish that symbol, so that every lane enters the main loop waiting for a mid-symbol hit */
-			if (tr.target == 2.0f) {
-				if (nco_advance(tr.phase, tr.freq, 2.0f, s, ns))
-					symbol_hit(tr, y_at<P>(y, g, s - 1), center, alpha, beta, max_fdev, ring, ring_mask, soft, p.soft_stride);
-			}
-			for (;;) {
-				bool live = false;
-				if (tr.target == 1.0f && nco_advance(tr.phase, tr.freq, 1.0f, s, ns)) {
-					tr.interm = y_at<P>(y, g, s - 1);
-					tr.target = 2.0f;
-					if (nco_advance(tr.phase, tr.freq, 2.0f, s, ns)) {
-						symbol_hit(tr, y_at<P>(y, g, s - 1), center, alpha, beta, max_fdev, ring, ring_mask, soft,
-						           p.soft_stride);
-						live = true;
-					}
+			while (__any_sync(FULL, s < ns)) {
+				const int lim = min(N, ns - s);                 /* valid slots of this round */
+				float pk[N + 1];
+				pk[0] = tr.phase;
+#pragma unroll
+				for (int i = 1; i <= N; i++) pk[i] = fadd(pk[i - 1], tr.freq);
+				float cand[N / 4];
+				uint32_t m1 = 0, m2 = 0;
+#pragma unroll
+				for (int j = 0; j < N / 4; j++) {
+					const float lo = (h & 1) ? pk[4 * j + 2] : pk[4 * j + 1];
+					const float hi = (h & 1) ? pk[4 * j + 4] : pk[4 * j + 3];
+					cand[j] = (h & 2) ? hi : lo;
+					const uint32_t b1 = __ballot_sync(FULL, cand[j] >= 1.0f);
+					const uint32_t b2 = __ballot_sync(FULL, cand[j] >= 2.0f);
+					m1 |= ((b1 >> (4 * g)) & 0xFu) << (4 * j);
+					m2 |= ((b2 >> (4 * g)) & 0xFu) << (4 * j);
 				}
-				if (!__any_sync(FULL, live)) break;
+				const uint32_t valid = (1u << lim) - 1u;         /* lim <= N < 32 */
+				m1 &= valid;
+				m2 &= valid;
+				int k1 = 0;
+				if (tr.target == 1.0f) {
+					k1 = __ffs(m1);                              /* 1-based slot of the mid-symbol hit, 0 = none */
+					if (!k1) m2 = 0;
+				}
+				m2 &= 0xffffffffu << k1;                        /* the symbol hit comes strictly after it */
+				const int k2 = __ffs(m2);
+				if (k1) {
+					tr.interm = y_at<P>(y, g, s + k1 - 1);
+					tr.target = 2.0f;
+				}
+				const int kk = k2 ? k2 : lim;                    /* slots consumed */
+				const int ki = max(kk, 1) - 1;
+				float mine = cand[0];
+#pragma unroll
+				for (int j = 1; j < N / 4; j++) mine = ((ki >> 2) == j) ? cand[j] : mine;
+				const float pv = __shfl_sync(FULL, mine, (lane & ~3) | (ki & 3));
+				if (kk > 0) tr.phase = pv;
+				if (k2) {
+					const float yv = y_at<P>(y, g, s + k2 - 1);
+					symbol_hit(tr, yv, center, alpha, beta, max_fdev, ring, ring_mask, soft, p.soft_stride, writer);
+				}
+				s += kk;
 			}
 			warp_arrive(&sm.yfree[ss], lane);
 		}
-		if (own) {
+		if (writer) {
 			demod_state &st = p.st[ch];
 			st.t_prev = tr.prev; st.t_phase = tr.phase; st.t_freq = tr.freq; st.t_state = (int)tr.target;
 			st.bit_acc = tr.acc; st.bit_cnt = tr.cnt; st.nbits = tr.nbits; st.nsoft = tr.nsoft;
@@ -471,26 +491,33 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	}
 }
 
-template <int P, bool IQ>
+template <int P, int N, bool IQ>
 cudaError_t launch(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
 	static bool attr_done = false;
 	if (!attr_done) {
-		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, N, IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                     (int)sizeof(smem_t<P>));
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
-	demod_pipe_kernel<P, IQ><<<n_groups, NTHREADS, sizeof(smem_t<P>), stream>>>(*p, group_base);
+	demod_pipe_kernel<P, N, IQ><<<n_groups, NTHREADS, sizeof(smem_t<P>), stream>>>(*p, group_base);
 	return cudaGetLastError();
 }
 
 }  // namespace
 
-extern "C" cudaError_t sonde_launch_demod_pipe(const demod_params *p, int group_base, int n_groups, int phases,
+/* variant 0: 1 polyphase branch, <= 10 NCO slots per symbol (RS41)        -> 12-slot rounds
+ * variant 1: 1 branch, ~20 slots per symbol (DFM, iMS-100, MRZ-N1)         -> 24-slot rounds
+ * variant 2: 2 branches, 10 slots per symbol (M10/M20)                     -> 12-slot rounds */
+extern "C" cudaError_t sonde_launch_demod_pipe(const demod_params *p, int group_base, int n_groups, int variant,
                                                cudaStream_t stream)
 {
 	if (n_groups <= 0) return cudaSuccess;
-	if (phases == 1) return p->is_iq ? launch<1, true>(p, group_base, n_groups, stream) : launch<1, false>(p, group_base, n_groups, stream);
-	return p->is_iq ? launch<2, true>(p, group_base, n_groups, stream) : launch<2, false>(p, group_base, n_groups, stream);
+	switch (variant) {
+	case 0:  return p->is_iq ? launch<1, 12, true>(p, group_base, n_groups, stream) : launch<1, 12, false>(p, group_base, n_groups, stream);
+	case 1:  return p->is_iq ? launch<1, 24, true>(p, group_base, n_groups, stream) : launch<1, 24, false>(p, group_base, n_groups, stream);
+	case 2:  return p->is_iq ? launch<2, 12, true>(p, group_base, n_groups, stream) : launch<2, 12, false>(p, group_base, n_groups, stream);
+	default: return cudaErrorInvalidValue;
+	}
 }

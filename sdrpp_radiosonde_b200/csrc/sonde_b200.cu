@@ -38,7 +38,7 @@ struct sonde_b200 {
 	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 
 	/* CTA groups, sorted: GFSK 1-phase | GFSK 2-phase | AFSK */
-	int n_groups = 0, groups_p1 = 0, groups_p2 = 0, groups_afsk = 0;
+	int n_groups = 0, groups_v[4] = {0, 0, 0, 0};   /* per kernel variant, see sonde_launch_demod_pipe */
 	int32_t *d_group_chan = nullptr, *d_group_type = nullptr, *d_types = nullptr;
 
 	demod_state *d_demod = nullptr;
@@ -163,9 +163,11 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 		}
 		return added;
 	};
-	h->groups_p1 = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 1; });
-	h->groups_p2 = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 2; });
-	h->groups_afsk = add_groups([](const sonde_modem &m) { return m.baud && m.afsk; });
+	/* NCO slots per symbol = 2 / freq0 */
+	h->groups_v[0] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 1 && m.freq0 >= 0.19f; });
+	h->groups_v[1] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 1 && m.freq0 < 0.19f; });
+	h->groups_v[2] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 2; });
+	h->groups_v[3] = add_groups([](const sonde_modem &m) { return m.baud && m.afsk; });
 	h->n_groups = (int)gtype.size();
 
 	/* ---- sizes ----------------------------------------------------------------------------- */
@@ -202,7 +204,7 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	CKB(cudaMemset(h->d_framer, 0, (size_t)C * sizeof(framer_state)));
 	CKB(cudaMemset(h->d_counts, 0, (size_t)C * 2 * sizeof(int32_t)));
 	if (cfg->keep_soft) CKB(cudaMalloc(&h->d_soft, (size_t)C * h->soft_stride * sizeof(float)));
-	if (h->groups_afsk) {
+	if (h->groups_v[3]) {
 		CKB(cudaMalloc(&h->d_afsk, (size_t)C * sizeof(afsk_state)));
 		CKB(cudaMemset(h->d_afsk, 0, (size_t)C * sizeof(afsk_state)));
 	}
@@ -266,11 +268,17 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	CK(cudaEventRecord(h->ev[0], h->stream));
 	/* production kernel: the warp-specialised pipeline; reserved bit 0 selects the phase-by-phase
 	 * kernel of demod.cu (kept as an independent cross-check for the tests) */
-	auto demod = (h->cfg.reserved & 1) ? sonde_launch_demod_gfsk : sonde_launch_demod_pipe;
-	if (h->groups_p1) { CK(demod(&dp, 0, h->groups_p1, 1, h->stream)); h->launches++; }
-	if (h->groups_p2) { CK(demod(&dp, h->groups_p1, h->groups_p2, 2, h->stream)); h->launches++; }
-	if (h->groups_afsk) {
-		CK(sonde_launch_demod_afsk(&dp, h->groups_p1 + h->groups_p2, h->groups_afsk, h->stream));
+	int base = 0;
+	for (int v = 0; v < 3; v++) {
+		if (h->groups_v[v]) {
+			if (h->cfg.reserved & 1) CK(sonde_launch_demod_gfsk(&dp, base, h->groups_v[v], v == 2 ? 2 : 1, h->stream));
+			else                     CK(sonde_launch_demod_pipe(&dp, base, h->groups_v[v], v, h->stream));
+			h->launches++;
+		}
+		base += h->groups_v[v];
+	}
+	if (h->groups_v[3]) {
+		CK(sonde_launch_demod_afsk(&dp, base, h->groups_v[3], h->stream));
 		h->launches++;
 	}
 	CK(cudaEventRecord(h->ev[1], h->stream));
