@@ -160,6 +160,11 @@ SONDE_API int  sonde_b200_modem_info(int type, int samplerate, float *taps, int 
 SONDE_API void *sonde_b200_host_alloc(size_t bytes);
 SONDE_API void  sonde_b200_host_free(void *p);
 
+/* Diagnostics: the first call switches on the pipeline kernel's per-CTA stall counters; later calls copy them
+ * out: out[groups][16] cycles = [role*4 + {wait for input, wait for output slot, total}], roles 0..3 = parallel
+ * warps, AGC bias lane, AGC level lane, timing lane.  Returns the number of CTA groups. */
+SONDE_API int  sonde_b200_debug_stalls(sonde_b200 *h, long long *out, int cap_groups);
+
 /* The CUDA stream (cudaStream_t) all work of this handle is enqueued on. */
 SONDE_API void *sonde_b200_stream(sonde_b200 *h);
 

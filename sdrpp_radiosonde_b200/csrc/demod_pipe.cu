@@ -68,8 +68,9 @@ struct smem_t {
 	float y[NS2][P][G][RS];              /* FIR output per polyphase branch          */
 	float ph[G][RS];                     /* S1 scratch: phases, [g][0] = previous    */
 	float carry[2][G];                   /* last phase of the previous tile          */
-	float taps[P * SONDE_FIR_TAPS];
+	float2 taps[P * SONDE_FIR_TAPS];     /* each tap duplicated for the packed fp32x2 FIR */
 	int   zflag[NX];                     /* tile contains exact-zero samples         */
+	unsigned long long negzero2;         /* (-0.0f, -0.0f), read at run time so that the packed product stays an FFMA2 */
 	unsigned long long xfull[NX], sfull[NS2], sfree[NS2], vfull[NS2], vfree[NS2], yfull[NS2], yfree[NS2];
 };
 
@@ -96,6 +97,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity
 		"D_%=:\n"
 		"}\n" ::"r"(s32(b)), "r"(parity) : "memory");
 }
+/* wait that charges the stalled cycles to a diagnostics counter */
+__device__ __forceinline__ void mbar_wait_t(unsigned long long *b, uint32_t parity, long long &acc, bool on)
+{
+	if (!on) { mbar_wait(b, parity); return; }
+	const long long t0 = clock64();
+	mbar_wait(b, parity);
+	acc += clock64() - t0;
+}
 /* all lanes of a warp finished their writes -> one arrival */
 __device__ __forceinline__ void warp_arrive(unsigned long long *b, int lane)
 {
@@ -110,12 +119,20 @@ __device__ __forceinline__ void pw_barrier()
 /* ---- TM helpers ----------------------------------------------------------------------------- */
 struct tm_regs {
 	float prev, phase, freq, interm, target;     /* target = (float)state : 1 = mid-symbol, 2 = symbol */
-	uint32_t acc;
-	int cnt, nsoft;
-	uint64_t nbits;
+	uint32_t acc;                                /* bits of the byte being assembled                   */
+	uint32_t nb;                                 /* bits demodulated so far, low 32 bits of the stream position */
+	int nsoft;
 };
 
-/* retime() + slicer at a symbol hit (timing.c:45-76, gfsk.c:99-115) */
+__device__ __forceinline__ float rcp_approx(float x)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
+/* retime() + slicer at a symbol hit (timing.c:45-76, gfsk.c:99-115).  `ring` already points at the
+ * channel's ring; byte index = (stream bit position >> 3) & mask, position's low bits are in t.nb. */
 __device__ __forceinline__ void symbol_hit(tm_regs &t, const float yv, const float center, const float alpha,
                                            const float beta, const float max_fdev, uint8_t *ring,
                                            const uint32_t ring_mask, float *soft, const int soft_cap,
@@ -135,15 +152,10 @@ __device__ __forceinline__ void symbol_hit(tm_regs &t, const float yv, const flo
 	t.target = 1.0f;
 
 	t.acc = (t.acc << 1) | (yv > 0.0f ? 1u : 0u);
-	t.cnt++;
 	if (soft && t.nsoft < soft_cap) soft[t.nsoft] = yv;
 	t.nsoft++;
-	if (t.cnt == 8) {
-		if (writer) ring[(uint32_t)(t.nbits >> 3) & ring_mask] = (uint8_t)t.acc;
-		t.acc = 0;
-		t.cnt = 0;
-	}
-	t.nbits++;
+	if ((t.nb & 7u) == 7u && writer) ring[(t.nb >> 3) & ring_mask] = (uint8_t)t.acc;
+	t.nb++;
 }
 
 /* filter_get(phase) of slot index sl: sample sl / P, polyphase branch P-1-(sl % P) (filter.c:54) */
@@ -153,9 +165,31 @@ __device__ __forceinline__ float y_at(const float (*y)[G][RS], const int g, cons
 	return (P == 1) ? y[0][g][sl] : y[P - 1 - (sl % P)][g][sl / P];
 }
 
-/* ---- S4: FIR at R consecutive positions, reference summation order (filter.c:59-61) ---------- */
+/* ---- S4: FIR at R consecutive positions, reference summation order (filter.c:59-61) ----------
+ * Two neighbouring outputs share one packed fp32x2 multiply and one packed add (sm_100 FMUL2/FADD2,
+ * round-to-nearest per lane, never fused), which halves the issue slots of the dominant loop. */
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+	unsigned long long r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+	return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
+{
+	unsigned long long r;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+
 template <int P>
-__device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS], const float *taps, int g, int seg)
+__device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS], const float2 *taps2,
+                                            const unsigned long long negzero2, int g, int seg)
 {
 	float w[R + SONDE_FIR_HIST];
 	const float4 *src = reinterpret_cast<const float4 *>(arow + seg * R);
@@ -166,18 +200,22 @@ __device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS]
 	}
 #pragma unroll
 	for (int br = 0; br < P; br++) {
-		float acc[R];
+		unsigned long long acc[R / 2];
 #pragma unroll
-		for (int r = 0; r < R; r++) acc[r] = 0.0f;
+		for (int r = 0; r < R / 2; r++) acc[r] = 0ull;                 /* (+0, +0) */
 #pragma unroll
 		for (int i = 0; i < SONDE_FIR_TAPS; i++) {
-			const float c = taps[br * SONDE_FIR_TAPS + i];
+			const unsigned long long c = reinterpret_cast<const unsigned long long *>(taps2)[br * SONDE_FIR_TAPS + i];
 #pragma unroll
-			for (int r = 0; r < R; r++) acc[r] = fadd(acc[r], fmul(w[r + i], c));
+			for (int r = 0; r < R / 2; r++) {
+				/* a*c + (-0) == fl(a*c): the product rounded once, then the reference's add */
+				const unsigned long long prod = fma2(pack2(w[2 * r + i], w[2 * r + i + 1]), c, negzero2);
+				acc[r] = add2(acc[r], prod);
+			}
 		}
-		float4 *dst = reinterpret_cast<float4 *>(&y[br][g][seg * R]);
-		dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-		dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+		unsigned long long *dst = reinterpret_cast<unsigned long long *>(&y[br][g][seg * R]);
+#pragma unroll
+		for (int r = 0; r < R / 2; r++) dst[r] = acc[r];
 	}
 }
 
@@ -194,9 +232,14 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	const int *chans = p.group_chan + (size_t)grp * G;
 	const int L = p.len;
 	const int ntiles = (L + T - 1) / T;
+	const bool prof_on = p.prof != nullptr;
+	long long wacc[2] = {0, 0};
+	long long n_rounds = 0, n_slow = 0;
+	const long long t_start = prof_on ? clock64() : 0;
 
 	/* ---- prologue ------------------------------------------------------------------------- */
 	if (tid == 0) {
+		sm.negzero2 = 0x8000000080000000ull;
 		for (int i = 0; i < NX; i++) { mbar_init(&sm.xfull[i], NPW); sm.zflag[i] = 0; }
 		for (int i = 0; i < NS2; i++) {
 			mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sfree[i], 1 + NPW);
@@ -204,7 +247,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			mbar_init(&sm.yfull[i], NPW); mbar_init(&sm.yfree[i], 1);
 		}
 	}
-	for (int i = tid; i < P * SONDE_FIR_TAPS; i += NTHREADS) sm.taps[i] = md.taps[i];
+	for (int i = tid; i < P * SONDE_FIR_TAPS; i += NTHREADS) sm.taps[i] = make_float2(md.taps[i], md.taps[i]);
 	for (int i = tid; i < G * SONDE_FIR_HIST; i += NTHREADS) {
 		const int g = i / SONDE_FIR_HIST, k = i % SONDE_FIR_HIST;
 		const int ch = chans[g];
@@ -222,6 +265,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 #pragma unroll
 		for (int g = 0; g < G; g++) ch_of[g] = chans[g];
 
+		const unsigned long long negzero2 = *reinterpret_cast<volatile unsigned long long *>(&sm.negzero2);
 		float2 q[G];                             /* prefetched raw input of the next S1 tile    */
 		auto prefetch = [&](int tile) {
 			const int i = tile * T + t;
@@ -276,7 +320,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			if (k + 1 < ntiles) stage1(k + 1);
 
 			/* ---- S3(k): a = s * (5 / avg_before)  (agc.c:27,31); zero samples pass as 0 ---- */
-			mbar_wait(&sm.vfull[ss], par);            /* implies sfull[ss] (A2 consumed it first) */
+			mbar_wait_t(&sm.vfull[ss], par, wacc[0], prof_on);            /* implies sfull[ss] (A2 consumed it first) */
 			const bool zslow = sm.zflag[xs] != 0;
 #pragma unroll
 			for (int g = 0; g < G; g++) {
@@ -295,8 +339,8 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			pw_barrier();
 
 			/* ---- S4(k) ---- */
-			mbar_wait(&sm.yfree[ss], par ^ 1);
-			fir_segment<P>(sm.a[ss][pw], sm.y[ss], sm.taps, pw, lane);
+			mbar_wait_t(&sm.yfree[ss], par ^ 1, wacc[1], prof_on);
+			fir_segment<P>(sm.a[ss][pw], sm.y[ss], sm.taps, negzero2, pw, lane);
 			warp_arrive(&sm.yfull[ss], lane);
 		}
 
@@ -321,8 +365,8 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			const int n = min(T, L - k * T);
 			const int xs = k % NX, ss = k % NS2;
 			const uint32_t par = (k / NS2) & 1;
-			mbar_wait(&sm.xfull[xs], (k / NX) & 1);
-			mbar_wait(&sm.sfree[ss], par ^ 1);
+			mbar_wait_t(&sm.xfull[xs], (k / NX) & 1, wacc[0], prof_on);
+			mbar_wait_t(&sm.sfree[ss], par ^ 1, wacc[1], prof_on);
 			const float *__restrict__ x = sm.x[xs][g];
 			float *__restrict__ s = sm.s[ss][g];
 			if (lane < G) {
@@ -367,8 +411,8 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			const int n = min(T, L - k * T);
 			const int xs = k % NX, ss = k % NS2;
 			const uint32_t par = (k / NS2) & 1;
-			mbar_wait(&sm.sfull[ss], par);
-			mbar_wait(&sm.vfree[ss], par ^ 1);
+			mbar_wait_t(&sm.sfull[ss], par, wacc[0], prof_on);
+			mbar_wait_t(&sm.vfree[ss], par ^ 1, wacc[1], prof_on);
 			const float *__restrict__ s = sm.s[ss][g];
 			const float *__restrict__ x = sm.x[xs][g];
 			float *__restrict__ v = sm.v[ss][g];
@@ -404,89 +448,133 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 		if (own) p.st[chans[g]].agc_avg = avg;
 	} else {
 		/* =============================== TM: timing + slicer ================================
-		 * lane = 4 * channel + helper.  The four helper lanes of a channel carry identical state and
-		 * run one straight-line "round" together:
-		 *   1. the NCO chain p_k = p_{k-1} + freq for the next N slots (the reference's adds, in order)
-		 *   2. each helper tests the slots k = 4j + h + 1 against the mid-symbol (>= 1) and symbol (>= 2)
-		 *      thresholds; warp votes assemble per-channel hit masks (timing.c:35)
-		 *   3. first mid hit -> interm, first later symbol hit -> retime + slice (timing.c:45-76);
-		 *      the round consumes the slots up to that symbol (or all N)
-		 * No data-dependent branches, so the 8 channels never serialise. */
-		const int g = lane >> 2, h = lane & 3;
-		const bool own = chans[g] >= 0;
+		 * lane = channel.  Per "round" a lane advances its NCO by up to N slots, i.e. to its next symbol
+		 * instant (timing.c:28-43), then retimes and slices (timing.c:45-76, gfsk.c:99-115).
+		 *
+		 * The reference finds the hit slots by comparing after every add.  Here the slot numbers are
+		 * PREDICTED arithmetically (c = ceil((threshold - phase) / freq)), the reference's chain of adds
+		 * is then run for exactly that many slots as predicated FADDs (same operations, same order, so
+		 * the phase value is the reference's), and the prediction is VERIFIED on the chain values
+		 * (p[c-1] < threshold <= p[c]; the chain is monotone because freq > 0).  The critical path per
+		 * symbol is therefore the add chain itself.  If any lane's check fails (rounding put a slot on
+		 * the other side of a threshold, or a pathological state), the round is redone for the warp with
+		 * the literal slot-by-slot loop, so the result is exact in every case. */
+		const int g = lane & (G - 1);
+		const bool own = lane < G && chans[g] >= 0;
 		const int ch = own ? chans[g] : 0;
 		tm_regs tr = {};
 		const float center = md.freq0, alpha = md.alpha, beta = md.beta, max_fdev = md.max_fdev;
 		uint8_t *ring = p.ring + (size_t)ch * p.ring_bytes;
-		float *soft = (own && h == 0 && p.soft) ? p.soft + (size_t)ch * p.soft_stride : nullptr;
-		const bool writer = own && h == 0;
+		float *soft = (own && p.soft) ? p.soft + (size_t)ch * p.soft_stride : nullptr;
+		/* the ring is a power of two and far smaller than 2^32 bits, so the low 32 bits of the
+		 * stream position address it */
 		const uint32_t ring_mask = p.ring_bytes - 1;
+		uint64_t nbits0 = 0;
 		if (own) {
 			const demod_state &st = p.st[ch];
 			tr.prev = st.t_prev; tr.phase = st.t_phase; tr.freq = st.t_freq;
 			tr.target = (float)st.t_state;
 			tr.interm = 0.0f;                               /* gfsk.c:73 */
-			tr.acc = st.bit_acc; tr.cnt = st.bit_cnt; tr.nbits = st.nbits; tr.nsoft = 0;
+			tr.acc = st.bit_acc; nbits0 = st.nbits; tr.nb = (uint32_t)nbits0; tr.nsoft = 0;
+		} else {
+			tr.freq = center; tr.target = 1.0f;
 		}
+		float rf = rcp_approx(tr.freq);                      /* only steers the prediction */
+		/* A predicted mid-symbol slot is trusted only when (1 - phase)/freq is at least DELTA away from
+		 * an integer.  |phase| < 4, so each of the <= N adds of the chain rounds by <= 2^-23 and the chain
+		 * deviates from phase + k*freq by < N * 1.2e-7, i.e. N * 1.2e-7 / freq slots; the approximate
+		 * quotient adds < 4 * 2^-23 * (4 / freq) slots.  DELTA is 8x that sum. */
+		const float DELTA = 8.0f * ((float)(N + 16) * 1.2e-7f) / center;
 		for (int k = 0; k < ntiles; k++) {
 			const int n = min(T, L - k * T);
 			const int ss = k % NS2;
-			mbar_wait(&sm.yfull[ss], (k / NS2) & 1);
+			mbar_wait_t(&sm.yfull[ss], (k / NS2) & 1, wacc[0], prof_on);
 			const float (*y)[G][RS] = sm.y[ss];
 			const int ns = own ? n * P : 0;
 			int s = 0;
 			while (__any_sync(FULL, s < ns)) {
-				const int lim = min(N, ns - s);                 /* valid slots of this round */
-				float pk[N + 1];
-				pk[0] = tr.phase;
+				const int lim = min(N, ns - s);                 /* slots this round may consume */
+				const float p0 = tr.phase, f = tr.freq;
+				const bool want_mid = tr.target == 1.0f;
+				/* predicted slots (1-based) of the mid-symbol and symbol hits */
+				const float x1 = fmul(fsub(1.0f, p0), rf), x2 = fmul(fsub(2.0f, p0), rf);
+				const float x1c = ceilf(x1);
+				const float m1 = x1c - x1;
+				const bool mid_ok = !want_mid || x1 <= 0.0f || (m1 > DELTA && m1 < 1.0f - DELTA);
+				const int c1 = want_mid ? max(1, (int)x1c) : 0;
+				const int c2 = max(c1 + 1, __float2int_ru(x2));
+				const bool mid_in = want_mid && c1 <= lim;
+				const bool sym_in = c2 <= lim;
+				const int K = sym_in ? c2 : lim;                 /* slots consumed */
+				const float y_mid = mid_in ? y_at<P>(y, g, s + c1 - 1) : 0.0f;
+				const float y_sym = sym_in ? y_at<P>(y, g, s + c2 - 1) : 0.0f;
+				/* the reference's adds for slots 1 .. K-1, then slot K */
+				float pa = p0;
 #pragma unroll
-				for (int i = 1; i <= N; i++) pk[i] = fadd(pk[i - 1], tr.freq);
-				float cand[N / 4];
-				uint32_t m1 = 0, m2 = 0;
-#pragma unroll
-				for (int j = 0; j < N / 4; j++) {
-					const float lo = (h & 1) ? pk[4 * j + 2] : pk[4 * j + 1];
-					const float hi = (h & 1) ? pk[4 * j + 4] : pk[4 * j + 3];
-					cand[j] = (h & 2) ? hi : lo;
-					const uint32_t b1 = __ballot_sync(FULL, cand[j] >= 1.0f);
-					const uint32_t b2 = __ballot_sync(FULL, cand[j] >= 2.0f);
-					m1 |= ((b1 >> (4 * g)) & 0xFu) << (4 * j);
-					m2 |= ((b2 >> (4 * g)) & 0xFu) << (4 * j);
+				for (int i = 1; i < N; i++)
+					asm("{\n.reg .pred q;\nsetp.lt.s32 q, %2, %3;\n@q add.rn.f32 %0, %0, %1;\n}"
+					    : "+f"(pa) : "f"(f), "r"(i), "r"(K));
+				const float pl = (K > 0) ? fadd(pa, f) : p0;
+				/* verify the symbol prediction on the chain values (monotone chain: freq > 0) */
+				const bool hit_ok = (c2 - 1 == c1 || pa < 2.0f) && pl >= 2.0f;
+				const bool none_ok = (want_mid && !mid_in) ? (K == 0 || pl < 1.0f)    /* not even the mid-symbol hit */
+				                                           : (lim <= c1 || pl < 2.0f);
+				const bool ok = lim == 0 || (mid_ok && (sym_in ? hit_ok : none_ok));   /* idle lanes never veto */
+				if (prof_on) n_rounds++;
+				if (__all_sync(FULL, ok)) {
+					if (mid_in) { tr.interm = y_mid; tr.target = 2.0f; }
+					tr.phase = pl;
+					if (sym_in) {
+						symbol_hit(tr, y_sym, center, alpha, beta, max_fdev, ring, ring_mask, soft, p.soft_stride, own);
+						rf = rcp_approx(tr.freq);
+					}
+					s += K;
+				} else {
+					/* exact slot-by-slot replay of this round (timing.c:28-43) */
+					if (prof_on) n_slow++;
+					float ph = p0;
+					int used = lim;
+					bool sym = false;
+					for (int i = 1; i <= lim; i++) {
+						ph = fadd(ph, f);
+						if (ph >= tr.target) {
+							if (tr.target == 1.0f) {
+								tr.interm = y_at<P>(y, g, s + i - 1);
+								tr.target = 2.0f;
+							} else {
+								used = i;
+								sym = true;
+								break;
+							}
+						}
+					}
+					tr.phase = ph;
+					if (sym) {
+						symbol_hit(tr, y_at<P>(y, g, s + used - 1), center, alpha, beta, max_fdev, ring, ring_mask, soft,
+						           p.soft_stride, own);
+						rf = rcp_approx(tr.freq);
+					}
+					s += used;
 				}
-				const uint32_t valid = (1u << lim) - 1u;         /* lim <= N < 32 */
-				m1 &= valid;
-				m2 &= valid;
-				int k1 = 0;
-				if (tr.target == 1.0f) {
-					k1 = __ffs(m1);                              /* 1-based slot of the mid-symbol hit, 0 = none */
-					if (!k1) m2 = 0;
-				}
-				m2 &= 0xffffffffu << k1;                        /* the symbol hit comes strictly after it */
-				const int k2 = __ffs(m2);
-				if (k1) {
-					tr.interm = y_at<P>(y, g, s + k1 - 1);
-					tr.target = 2.0f;
-				}
-				const int kk = k2 ? k2 : lim;                    /* slots consumed */
-				const int ki = max(kk, 1) - 1;
-				float mine = cand[0];
-#pragma unroll
-				for (int j = 1; j < N / 4; j++) mine = ((ki >> 2) == j) ? cand[j] : mine;
-				const float pv = __shfl_sync(FULL, mine, (lane & ~3) | (ki & 3));
-				if (kk > 0) tr.phase = pv;
-				if (k2) {
-					const float yv = y_at<P>(y, g, s + k2 - 1);
-					symbol_hit(tr, yv, center, alpha, beta, max_fdev, ring, ring_mask, soft, p.soft_stride, writer);
-				}
-				s += kk;
 			}
 			warp_arrive(&sm.yfree[ss], lane);
 		}
-		if (writer) {
+		if (own) {
 			demod_state &st = p.st[ch];
+			const uint64_t nbits = nbits0 + (uint64_t)(tr.nb - (uint32_t)nbits0);
+			const int cnt = (int)(tr.nb & 7u);
 			st.t_prev = tr.prev; st.t_phase = tr.phase; st.t_freq = tr.freq; st.t_state = (int)tr.target;
-			st.bit_acc = tr.acc; st.bit_cnt = tr.cnt; st.nbits = tr.nbits; st.nsoft = tr.nsoft;
-			if (tr.cnt) ring[(uint32_t)(tr.nbits >> 3) & ring_mask] = (uint8_t)(tr.acc << (8 - tr.cnt));
+			st.bit_acc = tr.acc & ((1u << cnt) - 1u); st.bit_cnt = cnt; st.nbits = nbits; st.nsoft = tr.nsoft;
+			if (cnt) ring[(uint32_t)(nbits >> 3) & ring_mask] = (uint8_t)(tr.acc << (8 - cnt));
+		}
+	}
+	if (prof_on && lane == 0) {
+		/* per CTA: [role*4 + {wait0, wait1, total}] ; roles: 0 = PW (warp 0), 1 = A1, 2 = A2, 3 = TM */
+		const int role = warp == W_A1 ? 1 : warp == W_A2 ? 2 : warp == W_TM ? 3 : (warp == 0 ? 0 : -1);
+		if (role >= 0) {
+			long long *o = p.prof + (size_t)blockIdx.x * 16 + role * 4;
+			o[0] = wacc[0]; o[1] = wacc[1]; o[2] = clock64() - t_start;
+			o[3] = (n_rounds << 32) | n_slow;
 		}
 	}
 }

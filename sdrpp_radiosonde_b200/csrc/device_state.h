@@ -80,6 +80,7 @@ struct demod_params {
 	uint32_t      ring_bytes;     /* power of two                                     */
 	float        *soft;           /* [C][soft_stride] or NULL                         */
 	int32_t       soft_stride;
+	long long    *prof;           /* optional [n_groups][16] cycle counters (diagnostics) */
 };
 
 struct frame_params {

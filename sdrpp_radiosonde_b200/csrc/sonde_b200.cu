@@ -53,6 +53,7 @@ struct sonde_b200 {
 	void *d_in = nullptr;            /* staging for the host-buffer entry points */
 	size_t d_in_bytes = 0;
 	int32_t *h_counts = nullptr;     /* pinned */
+	long long *d_prof = nullptr;     /* diagnostics: per-CTA stall counters of the pipeline kernel */
 
 	int chunk_index = 0;
 	uint64_t bits_before_last = 0;
@@ -232,6 +233,7 @@ void sonde_b200_destroy(sonde_b200 *h)
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_group_chan); cudaFree(h->d_group_type); cudaFree(h->d_types);
 	cudaFree(h->d_demod); cudaFree(h->d_afsk); cudaFree(h->d_framer); cudaFree(h->d_ring);
+	cudaFree(h->d_prof);
 	cudaFree(h->d_recs); cudaFree(h->d_counts); cudaFree(h->d_soft); cudaFree(h->d_in);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	for (auto &e : h->ev)
@@ -264,6 +266,7 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	dp.ring_bytes = h->ring_bytes;
 	dp.soft = h->d_soft;
 	dp.soft_stride = h->soft_stride;
+	dp.prof = h->d_prof;
 
 	CK(cudaEventRecord(h->ev[0], h->stream));
 	/* production kernel: the warp-specialised pipeline; reserved bit 0 selects the phase-by-phase
@@ -485,6 +488,23 @@ void *sonde_b200_host_alloc(size_t bytes)
 void sonde_b200_host_free(void *p)
 {
 	if (p) cudaFreeHost(p);
+}
+
+/* Diagnostics: enable (and read back) the pipeline kernel's per-CTA stall counters.
+ * out[n_groups][16] cycles: [role*4 + {wait on input, wait on output slot, total}], roles PW, A1, A2, TM. */
+int sonde_b200_debug_stalls(sonde_b200 *h, long long *out, int cap_groups)
+{
+	if (!h) return SONDE_ERR_ARG;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->stream));
+	if (!h->d_prof) {
+		CK(cudaMalloc(&h->d_prof, (size_t)h->n_groups * 16 * sizeof(long long)));
+		CK(cudaMemset(h->d_prof, 0, (size_t)h->n_groups * 16 * sizeof(long long)));
+		return h->n_groups;
+	}
+	const int n = h->n_groups < cap_groups ? h->n_groups : cap_groups;
+	if (out) CK(cudaMemcpy(out, h->d_prof, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+	return n;
 }
 
 void *sonde_b200_stream(sonde_b200 *h) { return h ? (void *)h->stream : nullptr; }
