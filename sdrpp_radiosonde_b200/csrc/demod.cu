@@ -55,6 +55,8 @@ struct smem_t {
 	float y[SONDE_MAX_PHASES][G][RS];   /* S4 out: FIR output per polyphase branch       */
 	float ph[G][RS];               /* S1 scratch: phases, ph[g][0] = previous sample      */
 	float taps[SONDE_MAX_PHASES * SONDE_FIR_TAPS];
+	float2 mhist[G][SONDE_AFSK_MAXLEN];   /* AFSK boxcar histories (afsk.c:117-124) */
+	float2 shist[G][SONDE_AFSK_MAXLEN];
 };
 
 /* ---- S2: the two AGC recurrences for one channel over n samples ---------------------- */
@@ -76,6 +78,62 @@ __device__ __forceinline__ void agc_chains(const float *x, float *s, float *v, i
 		s[i] = si;
 		v[i] = avg;
 		avg = fadd(fmul(avg, kg1), fmul(fabsf(si), kg0));
+	}
+}
+
+/* ---- AFSK front end for one channel over n samples (afsk.c:104-141) ---------------------------
+ * s = agc(x) / len * 2 ; mix with the mark and space NCOs ; running boxcar sums over one symbol ;
+ * filter input = |mark_sum| - |space_sum|.  The reference calls glibc cexpf/cabsf/fmod per sample:
+ *   - fmod(p + f, 2 pi) in double and cabsf == (float)sqrt((double)re*re + (double)im*im) are
+ *     reproduced exactly (both are exactly-rounded double operations);
+ *   - sin/cos are evaluated in double and rounded to float, which equals glibc's sinf/cosf except
+ *     where glibc's own result is not the correctly rounded one (< 1 ulp apart).  The boxcar sums
+ *     integrate such differences, so AFSK soft symbols are NOT claimed bit-exact;
+ *     frame bytes are what tests/test_gpu_parity.py checks for the two AFSK sondes. */
+struct afsk_regs {
+	float p_mark, p_space, mre, mim, sre, sim;
+	int idx;
+};
+
+__device__ __forceinline__ float agc_full(float x, float &bias, float &avg)        /* agc.c:19-34 */
+{
+	if (x == 0.0f) return 0.0f;
+	const float s = fsub(x, bias);
+	bias = fadd(fmul(bias, fsub(1.0f, 0.01f)), fmul(s, 0.01f));
+	const float gain = fdiv(5.0f, avg);
+	avg = fadd(fmul(avg, fsub(1.0f, 0.001f)), fmul(fabsf(s), 0.001f));
+	return fmul(s, gain);
+}
+
+__device__ __forceinline__ float cabs_exact(float re, float im)
+{
+	return (float)sqrt(__dadd_rn(__dmul_rn((double)re, (double)re), __dmul_rn((double)im, (double)im)));
+}
+
+__device__ void afsk_chain(const float *x, float *out, int n, float &bias, float &avg, afsk_regs &a,
+                           float2 *mh, float2 *sh, const int len, const float f_mark, const float f_space)
+{
+	const double two_pi = 2.0 * 3.14159265358979323846;
+	const float flen = (float)len;
+	for (int i = 0; i < n; i++) {
+		const float s = fmul(fdiv(agc_full(x[i], bias, avg), flen), 2.0f);
+		double sn, cs;
+		sincos((double)a.p_mark, &sn, &cs);
+		float2 o = make_float2(fmul(s, (float)cs), fmul(s, -(float)sn));
+		float2 h = mh[a.idx];
+		a.mre = fadd(a.mre, fsub(o.x, h.x));
+		a.mim = fadd(a.mim, fsub(o.y, h.y));
+		mh[a.idx] = o;
+		sincos((double)a.p_space, &sn, &cs);
+		o = make_float2(fmul(s, (float)cs), fmul(s, -(float)sn));
+		h = sh[a.idx];
+		a.sre = fadd(a.sre, fsub(o.x, h.x));
+		a.sim = fadd(a.sim, fsub(o.y, h.y));
+		sh[a.idx] = o;
+		out[i] = fsub(cabs_exact(a.mre, a.mim), cabs_exact(a.sre, a.sim));
+		a.idx = (a.idx + 1) % len;
+		a.p_mark = (float)fmod((double)fadd(a.p_mark, f_mark), two_pi);
+		a.p_space = (float)fmod((double)fadd(a.p_space, f_space), two_pi);
 	}
 }
 
@@ -169,7 +227,7 @@ __device__ __forceinline__ void fir_segment(smem_t &sm, int g, int seg)
 	}
 }
 
-template <int P>
+template <int P, bool AFSK>
 __global__ void __launch_bounds__(NT, 1)
 demod_gfsk_kernel(const demod_params p, const int group_base)
 {
@@ -201,6 +259,21 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 		my_ring = p.ring + (size_t)my_ch * p.ring_bytes;
 		if (p.soft) my_soft = p.soft + (size_t)my_ch * p.soft_stride;
 		sm.ph[tid][0] = st.disc_prev;
+	}
+	afsk_regs ar = {};
+	if (AFSK) {
+		if (my_ch >= 0) {
+			const afsk_state &as = p.ast[my_ch];
+			ar.p_mark = as.p_mark; ar.p_space = as.p_space;
+			ar.mre = as.mark_re; ar.mim = as.mark_im; ar.sre = as.space_re; ar.sim = as.space_im;
+			ar.idx = as.idx;
+		}
+		for (int i = tid; i < G * SONDE_AFSK_MAXLEN; i += NT) {
+			const int g = i / SONDE_AFSK_MAXLEN, k = i % SONDE_AFSK_MAXLEN;
+			const int ch = chans[g];
+			sm.mhist[g][k] = (ch >= 0) ? make_float2(p.ast[ch].mark_hist[2 * k], p.ast[ch].mark_hist[2 * k + 1]) : make_float2(0, 0);
+			sm.shist[g][k] = (ch >= 0) ? make_float2(p.ast[ch].space_hist[2 * k], p.ast[ch].space_hist[2 * k + 1]) : make_float2(0, 0);
+		}
 	}
 	/* FIR history */
 	for (int i = tid; i < G * SONDE_FIR_HIST; i += NT) {
@@ -259,6 +332,14 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 			any_zero = __syncthreads_or(zero);
 		}
 
+		if (AFSK) {
+			/* ---- S2'/S3': AGC + mixers + boxcar, serial per channel ------------------------ */
+			if (my_ch >= 0)
+				afsk_chain(sm.x[tid], &sm.a[tid][SONDE_FIR_HIST], n, bias, avg, ar, sm.mhist[tid], sm.shist[tid],
+				           md.boxcar_len, md.f_mark, md.f_space);
+			for (int i = tid; i < G * (T - n); i += NT) sm.a[i / (T - n)][SONDE_FIR_HIST + n + i % (T - n)] = 0.0f;
+			__syncthreads();
+		} else {
 		/* ---- S2: AGC recurrences ------------------------------------------------------ */
 		if (my_ch >= 0) {
 			if (any_zero) agc_chains<true>(sm.x[tid], sm.s[tid], sm.v[tid], n, bias, avg);
@@ -276,6 +357,7 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 			sm.a[g][SONDE_FIR_HIST + i] = o;
 		}
 		__syncthreads();
+		}
 
 		/* ---- S4: FIR everywhere -------------------------------------------------------- */
 		fir_segment<P>(sm, tid / 32, tid % 32);
@@ -316,38 +398,56 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 		const int ch = chans[g];
 		if (ch >= 0) p.st[ch].hist[k] = sm.a[g][k];
 	}
+	if (AFSK) {
+		if (my_ch >= 0) {
+			afsk_state &as = p.ast[my_ch];
+			as.p_mark = ar.p_mark; as.p_space = ar.p_space;
+			as.mark_re = ar.mre; as.mark_im = ar.mim; as.space_re = ar.sre; as.space_im = ar.sim;
+			as.idx = ar.idx;
+		}
+		__syncthreads();
+		for (int i = tid; i < G * SONDE_AFSK_MAXLEN; i += NT) {
+			const int g = i / SONDE_AFSK_MAXLEN, k = i % SONDE_AFSK_MAXLEN;
+			const int ch = chans[g];
+			if (ch >= 0) {
+				p.ast[ch].mark_hist[2 * k] = sm.mhist[g][k].x; p.ast[ch].mark_hist[2 * k + 1] = sm.mhist[g][k].y;
+				p.ast[ch].space_hist[2 * k] = sm.shist[g][k].x; p.ast[ch].space_hist[2 * k + 1] = sm.shist[g][k].y;
+			}
+		}
+	}
 }
 
 }  // namespace
 
 extern "C" size_t sonde_demod_smem_bytes(void) { return sizeof(smem_t); }
 
-/* Launches the GFSK demodulator over groups [group_base, group_base + n_groups) that share
- * the polyphase count `phases`. */
-extern "C" cudaError_t sonde_launch_demod_gfsk(const demod_params *p, int group_base, int n_groups,
-                                               int phases, cudaStream_t stream)
+/* Launches the phase-by-phase demodulator over groups [group_base, group_base + n_groups) that
+ * share the polyphase count `phases`. */
+template <int P, bool AFSK>
+static cudaError_t launch_legacy(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
 	static bool attr_done = false;
 	if (!attr_done) {
-		cudaError_t e = cudaFuncSetAttribute(demod_gfsk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		cudaError_t e = cudaFuncSetAttribute(demod_gfsk_kernel<P, AFSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                     (int)sizeof(smem_t));
-		if (e != cudaSuccess) return e;
-		e = cudaFuncSetAttribute(demod_gfsk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                         (int)sizeof(smem_t));
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
-	if (n_groups <= 0) return cudaSuccess;
-	if (phases == 1)
-		demod_gfsk_kernel<1><<<n_groups, NT, sizeof(smem_t), stream>>>(*p, group_base);
-	else
-		demod_gfsk_kernel<2><<<n_groups, NT, sizeof(smem_t), stream>>>(*p, group_base);
+	demod_gfsk_kernel<P, AFSK><<<n_groups, NT, sizeof(smem_t), stream>>>(*p, group_base);
 	return cudaGetLastError();
 }
 
-#ifndef SONDE_HAVE_AFSK
-extern "C" cudaError_t sonde_launch_demod_afsk(const demod_params *, int, int n_groups, cudaStream_t)
+extern "C" cudaError_t sonde_launch_demod_gfsk(const demod_params *p, int group_base, int n_groups,
+                                               int phases, cudaStream_t stream)
 {
-	return n_groups > 0 ? cudaErrorNotSupported : cudaSuccess;
+	if (n_groups <= 0) return cudaSuccess;
+	return phases == 1 ? launch_legacy<1, false>(p, group_base, n_groups, stream)
+	                   : launch_legacy<2, false>(p, group_base, n_groups, stream);
 }
-#endif
+
+/* AFSK sondes (iMet-1/4, SRS-C50): 1 polyphase branch at 48 kS/s. */
+extern "C" cudaError_t sonde_launch_demod_afsk(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
+{
+	if (n_groups <= 0) return cudaSuccess;
+	return launch_legacy<1, true>(p, group_base, n_groups, stream);
+}

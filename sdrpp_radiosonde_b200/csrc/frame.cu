@@ -734,6 +734,11 @@ frame_kernel(const frame_params p)
 		}
 		__syncwarp();
 
+		/* iMet-4's 60th byte spans frame bits 599..606: the 7 bits past the frame are whatever the framer
+		 * buffer holds there, i.e. the UNSHIFTED, un-inverted buffer byte 75 (imet4/frame.c:14, framer.c:94-104) */
+		if (type == SONDE_IMET4 && lane == 0) ws.raw[75] = (uint8_t)(win_bits64(ws.win, 600) >> 56);
+		__syncwarp();
+
 		/* post-framer pipeline */
 		int status = 0, ok = 0, aux = 0, adjust = 0;
 		switch (type) {

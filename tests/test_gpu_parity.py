@@ -125,3 +125,41 @@ def test_iq_path_matches_oracle(stype):
         want = orc.frames_run_iq(stype, batch[c], chunk)
         assert [rec_key(g, rb) for g in got["frames"][c]] == [rec_key(w, rb) for w in want], (stype, c)
         assert sum(int(w.ok) for w in want) > 0
+
+
+@pytest.mark.parametrize("stype", [synth.IMET4, synth.C50])
+@pytest.mark.parametrize("chunk", [1024, 48000])
+def test_afsk_frames_match_reference(stype, chunk):
+    """AFSK sondes (iMet-1/4 incl. framer_adjust, SRS-C50 incl. the 90-bit frame quirks): frame records are
+    bit-exact; soft symbols are reported, not asserted (libm-dependent)."""
+    n_ch, n = 3, 48000 * 3
+    batch = make_fm_batch(stype, n_ch, n)
+    got = run_gpu([stype] * n_ch, batch, chunk, kind="fm", want_bits=True)
+    raw_bytes = (synth.MODEMS[stype].frame_bits + 7) // 8
+    for chk in checkers():
+        for c in range(n_ch):
+            want = chk.frames_run(stype, batch[c], chunk)
+            bits = chk.demod_bits(stype, batch[c], chunk)
+            nb = min(bits.size, got["bits"][c].size)
+            mism = int(np.count_nonzero(bits[:nb] != got["bits"][c][:nb]))
+            print(f"{chk.prefix} type {stype} ch {c}: {len(want)} frames, demod bit mismatches {mism}/{nb}")
+            assert len(got["frames"][c]) == len(want), (chk.prefix, c, len(got["frames"][c]), len(want))
+            for i, (g, w) in enumerate(zip(got["frames"][c], want)):
+                assert rec_key(g, raw_bytes) == rec_key(w, raw_bytes), (chk.prefix, stype, c, i)
+            assert sum(int(w.ok) for w in want) > 0
+
+
+def test_all_seven_types_one_handle():
+    """Config-5 style batch: every decoder type in one handle (three GFSK kernel variants + AFSK)."""
+    types = [c % 7 for c in range(21)]
+    n = 48000 * 2
+    batch = np.stack([synth.make_fm(synth.default_spec(t, c), n) for c, t in enumerate(types)])
+    got = run_gpu(types, batch, 48000, kind="fm")
+    chk = checkers()[0]
+    total_ok = 0
+    for c, t in enumerate(types):
+        want = chk.frames_run(t, batch[c], 48000)
+        raw_bytes = (synth.MODEMS[t].frame_bits + 7) // 8
+        assert [rec_key(g, raw_bytes) for g in got["frames"][c]] == [rec_key(w, raw_bytes) for w in want], (c, t)
+        total_ok += sum(int(w.ok) for w in want)
+    assert total_ok > 50
