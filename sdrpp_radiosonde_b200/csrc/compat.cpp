@@ -1,0 +1,99 @@
+/*
+ * compat.cpp — the reference's seven xxx_decoder_init / xxx_decode / xxx_decoder_deinit entry points
+ * (SD/include/*.h shape) as a thin adapter over the batch C ABI with C = 1.
+ *
+ * Call protocol (SD/include/rs41.h:23-33, src/decode/decoder.hpp:61): the caller re-invokes xxx_decode
+ * with the same buffer until PROCEED.  The first call for a buffer runs the GPU path over the whole
+ * buffer and queues its frame records; each further call pops one (PARSED) and the call after the
+ * last one answers PROCEED and re-arms.
+ */
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/sonde_b200_compat.h"
+#include "../host/gpu_decoder.hpp"
+
+struct sonde_compat_decoder {
+	sonde_b200 *h = nullptr;
+	int type = 0, max_chunk = 0, max_frames = 0;
+	std::vector<sonde_frame_rec> recs;
+	int n_recs = 0, next = 0;
+	bool armed = false;              /* records of the current buffer are queued */
+	const sonde_frame_rec *last = nullptr;
+};
+
+namespace {
+
+sonde_compat_decoder *make(int type, int samplerate)
+{
+	sonde_compat_decoder *d = new (std::nothrow) sonde_compat_decoder();
+	if (!d) return nullptr;
+	const int32_t t = type;
+	sonde_b200_config cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.n_channels = 1;
+	cfg.samplerate = samplerate;
+	cfg.max_chunk_len = 1 << 20;
+	cfg.types = &t;
+	if (sonde_b200_create(&d->h, &cfg) != SONDE_OK) {
+		delete d;
+		return nullptr;
+	}
+	d->type = type;
+	d->max_chunk = cfg.max_chunk_len;
+	d->max_frames = sonde_b200_max_frames(d->h);
+	d->recs.resize(d->max_frames);
+	return d;
+}
+
+void destroy(sonde_compat_decoder *d)
+{
+	if (!d) return;
+	sonde_b200_destroy(d->h);
+	delete d;
+}
+
+ParserStatus step(sonde_compat_decoder *d, SondeData *dst, const float *src, size_t len)
+{
+	if (!d || !src) return PROCEED;
+	if (!d->armed) {
+		int32_t count = 0;
+		d->n_recs = d->next = 0;
+		if (len == 0 || len > (size_t)d->max_chunk) return PROCEED;
+		if (sonde_b200_process_fm(d->h, src, len) != SONDE_OK) return PROCEED;
+		if (sonde_b200_fetch(d->h, d->recs.data(), &count) != SONDE_OK) return PROCEED;
+		d->n_recs = count;
+		d->armed = true;
+	}
+	if (d->next < d->n_recs) {
+		d->last = &d->recs[d->next++];
+		if (dst) {
+			::SondeData tmp;
+			radiosonde::fragment_from_record(*d->last, &tmp);
+			memcpy(dst, &tmp, sizeof(tmp));
+		}
+		return PARSED;
+	}
+	d->armed = false;
+	return PROCEED;
+}
+
+}  // namespace
+
+#define SONDE_COMPAT_IMPL(X, T, TYPE)                                                                   \
+	extern "C" T *X##_decoder_init(int samplerate) { return make(TYPE, samplerate); }                   \
+	extern "C" void X##_decoder_deinit(T *d) { destroy(d); }                                            \
+	extern "C" ParserStatus X##_decode(T *d, SondeData *dst, const float *src, size_t len)              \
+	{                                                                                                   \
+		return step(d, dst, src, len);                                                                  \
+	}                                                                                                   \
+	extern "C" const sonde_frame_rec *X##_last_frame(const T *d) { return d ? d->last : nullptr; }
+
+SONDE_COMPAT_IMPL(rs41, RS41Decoder, SONDE_RS41)
+SONDE_COMPAT_IMPL(dfm09, DFM09Decoder, SONDE_DFM09)
+SONDE_COMPAT_IMPL(m10, M10Decoder, SONDE_M10)
+SONDE_COMPAT_IMPL(ims100, IMS100Decoder, SONDE_IMS100)
+SONDE_COMPAT_IMPL(mrzn1, MRZN1Decoder, SONDE_MRZN1)
+SONDE_COMPAT_IMPL(imet4, IMET4Decoder, SONDE_IMET4)
+SONDE_COMPAT_IMPL(c50, C50Decoder, SONDE_C50)

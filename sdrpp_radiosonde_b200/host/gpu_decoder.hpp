@@ -1,0 +1,222 @@
+/*
+ * gpu_decoder.hpp — the SDR++ decoder-block surface on top of the C ABI (include/sonde_b200.h).
+ *
+ *   radiosonde::GpuDecoder       : dsp::block     one channel, complex IQ in -> SondeFullData callback
+ *   radiosonde::GpuChannelBank   : dsp::block     C channels batched into one GPU call per buffer
+ *
+ * GpuDecoder replaces, behind src/main.cpp:57-68, the chain
+ *     dsp::demod::FM<float> -> dsp::multirate::RationalResampler<float> -> radiosonde::Decoder<...>
+ * (src/main.hpp:33-42, src/decode/decoder.hpp:22-129): it is fed by vfo->output
+ * (dsp::stream<dsp::complex_t> at the 48 kS/s channel rate) and fires the same
+ * void(*)(SondeFullData*, void*) callback on the block's worker thread.
+ *
+ * run() mirrors decoder.hpp:53-119: read() -> for every framer window of the buffer
+ * (== every PARSED return of the reference's xxx_decode loop) merge the fragment into the persistent
+ * SondeFullData and call back iff fragment.fields != 0 -> flush().
+ *
+ * Telemetry: frame -> SondeData conversion is SURVEY.md §8 row f-1 ("next"); fragment_from_record()
+ * below covers what the frame gate itself establishes (RS41 status subframe: sequence number and
+ * serial, CRC-checked as rs41.c:165-175 does; M10/M20, MRZ-N1: sequence counters).  Every record
+ * is additionally handed to an optional frame callback so a host parser can run on the exact bytes
+ * the reference's parser would see.
+ *
+ * There is no CPU fallback: init() throws std::runtime_error when the CUDA path is unavailable.
+ */
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sonde_b200.h"
+#include "dsp_standin.hpp"
+#include "sonde_data.hpp"
+
+namespace radiosonde {
+
+typedef void (*SondeCallback)(SondeFullData *data, void *ctx);
+typedef void (*FrameCallback)(int channel, const sonde_frame_rec *rec, void *ctx);
+
+inline uint16_t crc16_ccitt_false(const uint8_t *p, size_t n)
+{
+	uint16_t crc = 0xFFFF;
+	for (; n; n--) {
+		crc ^= (uint16_t)(*p++ << 8);
+		for (int i = 0; i < 8; i++) crc = (crc & 0x8000) ? (uint16_t)((crc << 1) ^ 0x1021) : (uint16_t)(crc << 1);
+	}
+	return crc;
+}
+
+/* What the frame bytes establish without the telemetry parsers. */
+inline void fragment_from_record(const sonde_frame_rec &r, SondeData *dst)
+{
+	memset(dst, 0, sizeof(*dst));
+	switch (r.type) {
+	case SONDE_RS41: {
+		/* subframe walk of rs41.c:157-175: {type, len, data[len], crc16 LE}; parsed even if RS failed */
+		const uint8_t *data = r.data + 57;
+		const int data_len = 263 + (r.data[56] == 0xF0 ? 198 : 0);
+		int off = 0;
+		const uint8_t *sf = data;
+		off += sf[1] + 4;
+		while (off < data_len && sf[1]) {
+			const uint16_t want = (uint16_t)(sf[2 + sf[1]] | sf[3 + sf[1]] << 8);
+			if (crc16_ccitt_false(sf + 2, sf[1]) == want && sf[0] == 0x79) {        /* RS41_SFTYPE_INFO */
+				dst->seq = sf[2] | sf[3] << 8;
+				memcpy(dst->serial, sf + 4, 8);
+				dst->serial[8] = 0;
+				dst->fields |= DATA_SEQ | DATA_SERIAL;
+			}
+			sf = data + off;
+			off += sf[1] + 4;
+		}
+		break;
+	}
+	case SONDE_M10:
+		if (r.ok && r.data[4] == 0x9F) { dst->seq = r.data[103]; dst->fields |= DATA_SEQ; }
+		break;
+	case SONDE_MRZN1:
+		if (r.ok) { dst->seq = r.data[4]; dst->fields |= DATA_SEQ; }
+		break;
+	default:
+		break;
+	}
+}
+
+inline float dewpoint(float temp, float rh)          /* Magnus formula, as src/decode/decoder.hpp:132-140 */
+{
+	const float t = (logf(rh / 100.0f) + (17.27f * temp / (237.3f + temp))) / 17.27f;
+	return 237.3f * t / (1 - t);
+}
+
+/* merge of decoder.hpp:64-110 */
+inline void merge_fragment(SondeFullData &d, const SondeData &f)
+{
+	if (f.fields & DATA_SEQ) d.seq = f.seq;
+	if (f.fields & DATA_POS) { d.lat = f.lat; d.lon = f.lon; d.alt = f.alt; }
+	if (f.fields & DATA_SPEED) { d.spd = f.speed; d.hdg = f.heading; d.climb = f.climb; }
+	if (f.fields & DATA_TIME) d.time = f.time;
+	if (f.fields & DATA_PTU) {
+		d.calib_percent = f.calib_percent;
+		d.calibrated = d.calib_percent >= 100.0f;
+		d.temp = f.temp; d.rh = f.rh; d.pressure = f.pressure;
+		d.dewpt = dewpoint(d.temp, d.rh);
+	}
+	if (f.fields & DATA_SERIAL) d.serial = f.serial;
+	if (f.fields & DATA_SHUTDOWN) d.burstkill = f.shutdown;
+	if (f.fields & DATA_OZONE) {
+		char buf[48];
+		snprintf(buf, sizeof(buf), "O3=%.2fmPa", f.o3_mpa);
+		d.auxData = buf;
+	}
+}
+
+/* C channels, one input stream each, one GPU call per buffer. */
+class GpuChannelBank : public dsp::block {
+public:
+	GpuChannelBank() {}
+	~GpuChannelBank() { deinit(); }
+
+	void init(const std::vector<dsp::stream<dsp::complex_t> *> &in, int samplerate, const std::vector<int> &types,
+	          SondeCallback cb, void *ctx, int max_chunk = dsp::STREAM_BUFFER_SIZE / 8, int device = 0)
+	{
+		if (in.empty() || in.size() != types.size()) throw std::invalid_argument("GpuChannelBank: bad channel list");
+		m_in = in;
+		m_cb = cb;
+		m_ctx = ctx;
+		m_types.assign(types.begin(), types.end());
+		sonde_b200_config cfg;
+		memset(&cfg, 0, sizeof(cfg));
+		cfg.n_channels = (int32_t)in.size();
+		cfg.samplerate = samplerate;
+		cfg.max_chunk_len = max_chunk;
+		cfg.device = device;
+		cfg.types = m_types.data();
+		const int rc = sonde_b200_create(&m_h, &cfg);
+		if (rc != SONDE_OK)
+			throw std::runtime_error(std::string("sonde_b200_create failed (") + std::to_string(rc) +
+			                         "): the CUDA path is required, there is no CPU fallback");
+		m_max_frames = sonde_b200_max_frames(m_h);
+		m_max_chunk = max_chunk;
+		m_recs.resize((size_t)in.size() * m_max_frames);
+		m_counts.resize(in.size());
+		m_data.resize(in.size());
+		m_stage = (float *)sonde_b200_host_alloc((size_t)in.size() * max_chunk * 2 * sizeof(float));
+		if (!m_stage) throw std::runtime_error("pinned staging allocation failed");
+		for (auto *s : m_in) dsp::block::registerInput(s);
+		dsp::block::_block_init = true;
+	}
+
+	void setFrameCallback(FrameCallback cb, void *ctx) { m_fcb = cb; m_fctx = ctx; }
+
+	void deinit()
+	{
+		if (!dsp::block::_block_init) return;
+		dsp::block::stop();
+		for (auto *s : m_in) dsp::block::unregisterInput(s);
+		dsp::block::_block_init = false;
+		if (m_stage) sonde_b200_host_free(m_stage);
+		m_stage = nullptr;
+		sonde_b200_destroy(m_h);
+		m_h = nullptr;
+	}
+
+	int run() override
+	{
+		const size_t C = m_in.size();
+		int count = -1;
+		for (size_t c = 0; c < C; c++) {
+			const int n = m_in[c]->read();
+			if (n < 0) return -1;
+			if (count < 0 || n < count) count = n;          /* channels are fed in lock step */
+		}
+		if (count > m_max_chunk) count = m_max_chunk;
+		for (size_t c = 0; c < C; c++)
+			memcpy(m_stage + c * (size_t)count * 2, m_in[c]->readBuf, (size_t)count * sizeof(dsp::complex_t));
+
+		if (count > 0) {
+			if (sonde_b200_process_iq(m_h, m_stage, (size_t)count) != SONDE_OK ||
+			    sonde_b200_fetch(m_h, m_recs.data(), m_counts.data()) != SONDE_OK)
+				throw std::runtime_error(std::string("sonde_b200: ") + sonde_b200_last_error(m_h));
+			for (size_t c = 0; c < C; c++) {
+				for (int k = 0; k < m_counts[c]; k++) {
+					const sonde_frame_rec &r = m_recs[c * m_max_frames + k];
+					if (m_fcb) m_fcb((int)c, &r, m_fctx);
+					SondeData fragment;
+					fragment_from_record(r, &fragment);
+					merge_fragment(m_data[c], fragment);
+					if (fragment.fields && m_cb) m_cb(&m_data[c], m_ctx);
+				}
+			}
+		}
+		for (auto *s : m_in) s->flush();
+		return 0;
+	}
+
+	sonde_b200 *handle() { return m_h; }
+
+private:
+	std::vector<dsp::stream<dsp::complex_t> *> m_in;
+	std::vector<int32_t> m_types;
+	SondeCallback m_cb = nullptr;
+	FrameCallback m_fcb = nullptr;
+	void *m_ctx = nullptr, *m_fctx = nullptr;
+	sonde_b200 *m_h = nullptr;
+	int m_max_frames = 0, m_max_chunk = 0;
+	std::vector<sonde_frame_rec> m_recs;
+	std::vector<int32_t> m_counts;
+	std::vector<SondeFullData> m_data;
+	float *m_stage = nullptr;
+};
+
+/* One channel: the drop-in for one plugin instance (src/main.hpp:33-42). */
+class GpuDecoder : public GpuChannelBank {
+public:
+	void init(dsp::stream<dsp::complex_t> *in, double samplerate, int type, SondeCallback cb, void *ctx)
+	{
+		GpuChannelBank::init({in}, (int)samplerate, {type}, cb, ctx);
+	}
+};
+
+}  // namespace radiosonde

@@ -163,3 +163,29 @@ def test_all_seven_types_one_handle():
         assert [rec_key(g, raw_bytes) for g in got["frames"][c]] == [rec_key(w, raw_bytes) for w in want], (c, t)
         total_ok += sum(int(w.ok) for w in want)
     assert total_ok > 50
+
+
+def test_auto_detect_all_seven_types():
+    """Config 5: AUTO channels run all seven chains until one yields a decodable frame (SD/decode.c:174-224);
+    every synthetic signal must lock to its own decoder, and the locked channel's records equal the reference's."""
+    from sdrpp_radiosonde_b200 import capi, shard
+    n, chunk = 48000 * 2, 48000
+    batch = np.stack([synth.make_fm(synth.default_spec(t, 40 + t), n) for t in range(7)])
+    plan = shard.AutoPlan([shard.AUTO] * 7)
+    dec = capi.BatchDecoder(plan.virtual_types, chunk)
+    frames = [[] for _ in plan.virtual_types]
+    for pos in range(0, n, chunk):
+        dec.process_fm(plan.expand(batch[:, pos:pos + chunk]))
+        recs, counts = dec.fetch()
+        ok = np.array([int(recs[v, :counts[v]]["ok"].sum()) for v in range(len(plan.virtual_types))])
+        for v in range(len(plan.virtual_types)):
+            frames[v].extend(recs[v, :counts[v]].copy())
+        plan.update(ok)
+    dec.close()
+    assert plan.locked == list(range(7)), plan.locked
+    chk = checkers()[0]
+    for t in range(7):
+        want = chk.frames_run(t, batch[t], chunk)
+        rb = (synth.MODEMS[t].frame_bits + 7) // 8
+        got = frames[plan.active_slot(t)]
+        assert [rec_key(g, rb) for g in got] == [rec_key(w, rb) for w in want], t
