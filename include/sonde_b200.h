@@ -118,7 +118,8 @@ typedef struct {
 SONDE_API int  sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg);
 SONDE_API void sonde_b200_destroy(sonde_b200 *h);
 
-/* Host-buffer entry points: H2D copy + kernels are enqueued; results are ready after fetch. */
+/* Host-buffer entry points: H2D copy + kernels are enqueued (asynchronously when the buffer is pinned, see
+ * sonde_b200_host_alloc; the buffer must then stay untouched until the call has been fetched or synced). */
 SONDE_API int  sonde_b200_process_iq(sonde_b200 *h, const float *iq /*[C][len][2]*/, size_t len);
 SONDE_API int  sonde_b200_process_fm(sonde_b200 *h, const float *fm /*[C][len]*/,    size_t len);
 
@@ -129,10 +130,15 @@ SONDE_API int  sonde_b200_process_fm_device(sonde_b200 *h, const void *d_fm, siz
 /* Capacity (records per channel per process call) of the fetch arrays. */
 SONDE_API int  sonde_b200_max_frames(const sonde_b200 *h);
 
-/* Copy the records of the last process call: recs[C][max_frames], counts[C].  Synchronises. */
+/* Copy the records of one process call: recs[C][max_frames], counts[C].  Blocks until that call is done.
+ * Results are double buffered: fetch() serves the OLDEST call not fetched yet among the last two issued, so
+ *     process(0); process(1); fetch() -> call 0; process(2); fetch() -> call 1; ...
+ * overlaps the host->device copy of call i+1 and the fetch of call i with the kernels in between, while the
+ * plain process(); fetch(); process(); fetch(); sequence keeps returning the call just made.  Results of calls
+ * older than the last two are dropped if they were never fetched. */
 SONDE_API int  sonde_b200_fetch(sonde_b200 *h, sonde_frame_rec *recs, int32_t *counts);
 
-/* Only the per-channel counters of the last call (cheap D2H): frames[C], ok[C]. Synchronises. */
+/* Only the per-channel counters (cheap D2H): frames[C], ok[C]; same call selection as fetch(). */
 SONDE_API int  sonde_b200_fetch_counts(sonde_b200 *h, int32_t *frames, int32_t *ok);
 
 /* Running totals since create, per channel: framer windows, windows passing the gate, demodulated bits. */

@@ -46,12 +46,16 @@ struct sonde_b200 {
 	framer_state *d_framer = nullptr;
 	uint8_t *d_ring = nullptr;
 	uint32_t ring_bytes = 0;
-	sonde_frame_rec *d_recs = nullptr;
-	int32_t *d_counts = nullptr;
+	/* results and host-input staging are double buffered by call parity so that the H2D copy of call
+	 * i+1 overlaps the kernels of call i and fetch() of call i can run while call i+1 computes */
+	sonde_frame_rec *d_recs[2] = {nullptr, nullptr};
+	int32_t *d_counts[2] = {nullptr, nullptr};
+	cudaStream_t cstream = nullptr, dstream = nullptr;        /* H2D copies, D2H fetches */
+	cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+	long n_issued = 0, n_fetched = 0;
 	float *d_soft = nullptr;
 	int max_frames = 0, soft_stride = 0, bits_stride = 0;
-	void *d_in = nullptr;            /* staging for the host-buffer entry points */
-	size_t d_in_bytes = 0;
+	void *d_in[2] = {nullptr, nullptr};   /* staging for the host-buffer entry points */
 	int32_t *h_counts = nullptr;     /* pinned */
 	long long *d_prof = nullptr;     /* diagnostics: per-CTA stall counters of the pipeline kernel */
 
@@ -143,8 +147,14 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	if (sonde_upload_modems_frame(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (cudaStreamCreateWithFlags(&h->dstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	for (auto &e : h->ev)
 		if (cudaEventCreate(&e) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	for (int b = 0; b < 2; b++)
+		if (cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming) != cudaSuccess)
+			return bail(SONDE_ERR_CUDA);
 
 	/* ---- channel groups: type-homogeneous CTAs, ordered by kernel variant ---------------- */
 	const int C = cfg->n_channels;
@@ -198,12 +208,14 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	CKB(cudaMalloc(&h->d_demod, (size_t)C * sizeof(demod_state)));
 	CKB(cudaMalloc(&h->d_framer, (size_t)C * sizeof(framer_state)));
 	CKB(cudaMalloc(&h->d_ring, (size_t)C * h->ring_bytes));
-	CKB(cudaMalloc(&h->d_recs, (size_t)C * h->max_frames * sizeof(sonde_frame_rec)));
-	CKB(cudaMalloc(&h->d_counts, (size_t)C * 2 * sizeof(int32_t)));
+	for (int b = 0; b < 2; b++) {
+		CKB(cudaMalloc(&h->d_recs[b], (size_t)C * h->max_frames * sizeof(sonde_frame_rec)));
+		CKB(cudaMalloc(&h->d_counts[b], (size_t)C * 2 * sizeof(int32_t)));
+		CKB(cudaMemset(h->d_counts[b], 0, (size_t)C * 2 * sizeof(int32_t)));
+	}
 	CKB(cudaMallocHost(&h->h_counts, (size_t)C * 2 * sizeof(int32_t)));
 	CKB(cudaMemset(h->d_ring, 0, (size_t)C * h->ring_bytes));
 	CKB(cudaMemset(h->d_framer, 0, (size_t)C * sizeof(framer_state)));
-	CKB(cudaMemset(h->d_counts, 0, (size_t)C * 2 * sizeof(int32_t)));
 	if (cfg->keep_soft) CKB(cudaMalloc(&h->d_soft, (size_t)C * h->soft_stride * sizeof(float)));
 	if (h->groups_v[3]) {
 		CKB(cudaMalloc(&h->d_afsk, (size_t)C * sizeof(afsk_state)));
@@ -234,7 +246,14 @@ void sonde_b200_destroy(sonde_b200 *h)
 	cudaFree(h->d_group_chan); cudaFree(h->d_group_type); cudaFree(h->d_types);
 	cudaFree(h->d_demod); cudaFree(h->d_afsk); cudaFree(h->d_framer); cudaFree(h->d_ring);
 	cudaFree(h->d_prof);
-	cudaFree(h->d_recs); cudaFree(h->d_counts); cudaFree(h->d_soft); cudaFree(h->d_in);
+	for (int b = 0; b < 2; b++) {
+		cudaFree(h->d_recs[b]); cudaFree(h->d_counts[b]); cudaFree(h->d_in[b]);
+		if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+		if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
+	}
+	cudaFree(h->d_soft);
+	if (h->cstream) cudaStreamDestroy(h->cstream);
+	if (h->dstream) cudaStreamDestroy(h->dstream);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	for (auto &e : h->ev)
 		if (e) cudaEventDestroy(e);
@@ -294,15 +313,18 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	fp.fst = h->d_framer;
 	fp.ring = h->d_ring;
 	fp.ring_bytes = h->ring_bytes;
-	fp.recs = h->d_recs;
+	const int par = (int)(h->n_issued & 1);
+	fp.recs = h->d_recs[par];
 	fp.max_frames = h->max_frames;
 	fp.chunk_index = h->chunk_index;
-	fp.counts = h->d_counts;
+	fp.counts = h->d_counts[par];
 	CK(sonde_launch_frames(&fp, h->stream));
 	h->launches++;
 	CK(cudaEventRecord(h->ev[2], h->stream));
+	CK(cudaEventRecord(h->ev_done[par], h->stream));
 	h->have_timing = true;
 	h->chunk_index++;
+	h->n_issued++;
 	return SONDE_OK;
 }
 
@@ -324,13 +346,15 @@ static int process_host(sonde_b200 *h, const float *src, size_t len, int is_iq)
 	CK(cudaSetDevice(h->device));
 	const size_t esz = is_iq ? 2 * sizeof(float) : sizeof(float);
 	const size_t need = (size_t)h->cfg.n_channels * h->cfg.max_chunk_len * 2 * sizeof(float);
-	if (!h->d_in) {
-		CK(cudaMalloc(&h->d_in, need));
-		h->d_in_bytes = need;
-	}
-	/* the stream orders this copy after the previous call's kernels, so one staging buffer is enough */
-	CK(cudaMemcpyAsync(h->d_in, src, (size_t)h->cfg.n_channels * len * esz, cudaMemcpyHostToDevice, h->stream));
-	return run_chunk(h, h->d_in, len, len, is_iq);
+	const int par = (int)(h->n_issued & 1);
+	if (!h->d_in[par]) CK(cudaMalloc(&h->d_in[par], need));
+	/* copy on the copy stream once the kernels that last read this staging buffer are done; the compute
+	 * stream then waits for the copy.  With pinned `src` the H2D of this call overlaps the previous call's kernels. */
+	if (h->n_issued >= 2) CK(cudaStreamWaitEvent(h->cstream, h->ev_done[par], 0));
+	CK(cudaMemcpyAsync(h->d_in[par], src, (size_t)h->cfg.n_channels * len * esz, cudaMemcpyHostToDevice, h->cstream));
+	CK(cudaEventRecord(h->ev_copied[par], h->cstream));
+	CK(cudaStreamWaitEvent(h->stream, h->ev_copied[par], 0));
+	return run_chunk(h, h->d_in[par], len, len, is_iq);
 }
 
 int sonde_b200_process_iq(sonde_b200 *h, const float *iq, size_t len) { return process_host(h, iq, len, 1); }
@@ -345,7 +369,34 @@ int sonde_b200_sync(sonde_b200 *h)
 {
 	if (!h) return SONDE_ERR_ARG;
 	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->cstream));
 	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaStreamSynchronize(h->dstream));
+	return SONDE_OK;
+}
+
+/* Which call do fetch()/fetch_counts() serve: the oldest one not fetched yet among the last two issued
+ * (results are double buffered; older unfetched results have been overwritten). */
+static int fetch_slot(sonde_b200 *h, long *call)
+{
+	if (h->n_issued == 0) return -1;
+	long c = h->n_fetched;
+	if (c < h->n_issued - 2) c = h->n_issued - 2;
+	if (c >= h->n_issued) c = h->n_issued - 1;          /* everything fetched already: serve the last call again */
+	*call = c;
+	return (int)(c & 1);
+}
+
+static int fetch_counts_of(sonde_b200 *h, int par, int32_t *frames, int32_t *ok)
+{
+	const int C = h->cfg.n_channels;
+	CK(cudaStreamWaitEvent(h->dstream, h->ev_done[par], 0));
+	CK(cudaMemcpyAsync(h->h_counts, h->d_counts[par], (size_t)C * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->dstream));
+	CK(cudaStreamSynchronize(h->dstream));
+	for (int c = 0; c < C; c++) {
+		if (frames) frames[c] = h->h_counts[2 * c];
+		if (ok) ok[c] = h->h_counts[2 * c + 1];
+	}
 	return SONDE_OK;
 }
 
@@ -353,14 +404,12 @@ int sonde_b200_fetch_counts(sonde_b200 *h, int32_t *frames, int32_t *ok)
 {
 	if (!h) return SONDE_ERR_ARG;
 	CK(cudaSetDevice(h->device));
-	const int C = h->cfg.n_channels;
-	CK(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)C * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-	CK(cudaStreamSynchronize(h->stream));
-	for (int c = 0; c < C; c++) {
-		if (frames) frames[c] = h->h_counts[2 * c];
-		if (ok) ok[c] = h->h_counts[2 * c + 1];
-	}
-	return SONDE_OK;
+	long call = 0;
+	const int par = fetch_slot(h, &call);
+	if (par < 0) return fail(h, SONDE_ERR_STATE, "no process call yet");
+	const int rc = fetch_counts_of(h, par, frames, ok);
+	if (rc == SONDE_OK && call >= h->n_fetched) h->n_fetched = call + 1;
+	return rc;
 }
 
 int sonde_b200_fetch_totals(sonde_b200 *h, int64_t *frames, int64_t *ok, int64_t *bits)
@@ -384,14 +433,19 @@ int sonde_b200_fetch_totals(sonde_b200 *h, int64_t *frames, int64_t *ok, int64_t
 int sonde_b200_fetch(sonde_b200 *h, sonde_frame_rec *recs, int32_t *counts)
 {
 	if (!h || !recs || !counts) return SONDE_ERR_ARG;
-	int rc = sonde_b200_fetch_counts(h, counts, nullptr);
+	CK(cudaSetDevice(h->device));
+	long call = 0;
+	const int par = fetch_slot(h, &call);
+	if (par < 0) return fail(h, SONDE_ERR_STATE, "no process call yet");
+	int rc = fetch_counts_of(h, par, counts, nullptr);
 	if (rc) return rc;
 	const int C = h->cfg.n_channels;
 	for (int c = 0; c < C; c++)
 		if (counts[c] > h->max_frames) return fail(h, SONDE_ERR_STATE, "frame record overflow");
-	CK(cudaMemcpyAsync(recs, h->d_recs, (size_t)C * h->max_frames * sizeof(sonde_frame_rec),
-	                   cudaMemcpyDeviceToHost, h->stream));
-	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaMemcpyAsync(recs, h->d_recs[par], (size_t)C * h->max_frames * sizeof(sonde_frame_rec),
+	                   cudaMemcpyDeviceToHost, h->dstream));
+	CK(cudaStreamSynchronize(h->dstream));
+	if (call >= h->n_fetched) h->n_fetched = call + 1;
 	return SONDE_OK;
 }
 

@@ -189,3 +189,28 @@ def test_auto_detect_all_seven_types():
         rb = (synth.MODEMS[t].frame_bits + 7) // 8
         got = frames[plan.active_slot(t)]
         assert [rec_key(g, rb) for g in got] == [rec_key(w, rb) for w in want], t
+
+
+def test_pipelined_fetch_equals_sequential():
+    """fetch() serves the oldest unfetched call of the last two, so process(i+1) may be issued before
+    fetch(i) (H2D / D2H overlap); the records must equal the strictly alternating sequence."""
+    from sdrpp_radiosonde_b200 import capi
+    types = [synth.RS41, synth.M10, synth.DFM09, synth.C50]
+    n, chunk = 48000 * 2, 6000
+    batch = np.stack([synth.make_iq(synth.default_spec(t, c), n) for c, t in enumerate(types)])
+    seq = run_gpu(types, batch, chunk, kind="iq")
+    dec = capi.BatchDecoder(types, chunk)
+    frames = [[] for _ in types]
+    chunks = [np.ascontiguousarray(batch[:, p:p + chunk]) for p in range(0, n, chunk)]
+    dec.process_iq(chunks[0])
+    for i in range(len(chunks)):
+        if i + 1 < len(chunks):
+            dec.process_iq(chunks[i + 1])
+        recs, counts = dec.fetch()
+        for c in range(len(types)):
+            assert all(int(r["chunk"]) == i for r in recs[c, :counts[c]])
+            frames[c].extend(recs[c, :counts[c]].copy())
+    dec.close()
+    for c, t in enumerate(types):
+        rb = (synth.MODEMS[t].frame_bits + 7) // 8
+        assert [rec_key(g, rb) for g in frames[c]] == [rec_key(g, rb) for g in seq["frames"][c]]
