@@ -131,12 +131,9 @@ __device__ __forceinline__ float rcp_approx(float x)
 	return r;
 }
 
-/* retime() + slicer at a symbol hit (timing.c:45-76, gfsk.c:99-115).  `ring` already points at the
- * channel's ring; byte index = (stream bit position >> 3) & mask, position's low bits are in t.nb. */
-__device__ __forceinline__ void symbol_hit(tm_regs &t, const float yv, const float center, const float alpha,
-                                           const float beta, const float max_fdev, uint8_t *ring,
-                                           const uint32_t ring_mask, float *soft, const int soft_cap,
-                                           const bool writer)
+/* retime() at a symbol hit (timing.c:45-76) */
+__device__ __forceinline__ void retime(tm_regs &t, const float yv, const float center, const float alpha,
+                                       const float beta, const float max_fdev)
 {
 	const float err = (fmul(yv, t.prev) < 0.0f) ? fmul(fsub(yv, t.prev), t.interm) : 0.0f;
 	t.prev = yv;
@@ -150,11 +147,20 @@ __device__ __forceinline__ void symbol_hit(tm_regs &t, const float yv, const flo
 	fd = (-max_fdev > fl) ? -max_fdev : fl;
 	t.freq = fadd(center, fd);
 	t.target = 1.0f;
+}
 
+/* slicer + bit packing (gfsk.c:107-115).  `ring` points at the channel's ring; byte index =
+ * (stream bit position >> 3) & mask, the position's low 32 bits are t.nb. */
+template <bool SOFT>
+__device__ __forceinline__ void emit_symbol(tm_regs &t, const float yv, uint8_t *ring, const uint32_t ring_mask,
+                                            float *soft, const int soft_cap)
+{
 	t.acc = (t.acc << 1) | (yv > 0.0f ? 1u : 0u);
-	if (soft && t.nsoft < soft_cap) soft[t.nsoft] = yv;
+	if (SOFT) {
+		if (t.nsoft < soft_cap) soft[t.nsoft] = yv;
+	}
 	t.nsoft++;
-	if ((t.nb & 7u) == 7u && writer) ring[(t.nb >> 3) & ring_mask] = (uint8_t)t.acc;
+	if ((t.nb & 7u) == 7u) ring[(t.nb >> 3) & ring_mask] = (uint8_t)t.acc;
 	t.nb++;
 }
 
@@ -219,7 +225,7 @@ __device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS]
 	}
 }
 
-template <int P, int N, bool IQ>
+template <int P, int N, bool IQ, bool SOFT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 demod_pipe_kernel(const demod_params p, const int group_base)
 {
@@ -492,7 +498,9 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			const float (*y)[G][RS] = sm.y[ss];
 			const int ns = own ? n * P : 0;
 			int s = 0;
-			while (__any_sync(FULL, s < ns)) {
+			/* Lanes run their rounds independently (no warp votes on the critical path); the few lanes that
+			 * need the replay or finish the tile earlier simply diverge and reconverge. */
+			while (s < ns) {
 				const int lim = min(N, ns - s);                 /* slots this round may consume */
 				const float p0 = tr.phase, f = tr.freq;
 				const bool want_mid = tr.target == 1.0f;
@@ -506,7 +514,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 				const bool mid_in = want_mid && c1 <= lim;
 				const bool sym_in = c2 <= lim;
 				const int K = sym_in ? c2 : lim;                 /* slots consumed */
-				const float y_mid = mid_in ? y_at<P>(y, g, s + c1 - 1) : 0.0f;
+				const float y_mid = mid_in ? y_at<P>(y, g, s + c1 - 1) : tr.interm;
 				const float y_sym = sym_in ? y_at<P>(y, g, s + c2 - 1) : 0.0f;
 				/* the reference's adds for slots 1 .. K-1, then slot K */
 				float pa = p0;
@@ -514,19 +522,30 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 				for (int i = 1; i < N; i++)
 					asm("{\n.reg .pred q;\nsetp.lt.s32 q, %2, %3;\n@q add.rn.f32 %0, %0, %1;\n}"
 					    : "+f"(pa) : "f"(f), "r"(i), "r"(K));
-				const float pl = (K > 0) ? fadd(pa, f) : p0;
+				const float pl = fadd(pa, f);                    /* lim >= 1 here, so K >= 1 */
+				/* speculative retime on the predicted symbol (timing.c:45-76); independent of the add chain
+				 * except for the final phase correction */
+				const float err = (fmul(y_sym, tr.prev) < 0.0f) ? fmul(fsub(y_sym, tr.prev), y_mid) : 0.0f;
+				const float ea = fmul(err, alpha);
+				const float lo = (2.0f < ea) ? 2.0f : ea;
+				const float cl = (-2.0f > lo) ? -2.0f : lo;
+				float fd = fadd(fsub(f, center), fmul(err, beta));
+				const float fl = (max_fdev < fd) ? max_fdev : fd;
+				fd = (-max_fdev > fl) ? -max_fdev : fl;
+				const float f_new = fadd(center, fd);
+				const float ph_new = fsub(pl, fsub(2.0f, cl));
 				/* verify the symbol prediction on the chain values (monotone chain: freq > 0) */
 				const bool hit_ok = (c2 - 1 == c1 || pa < 2.0f) && pl >= 2.0f;
-				const bool none_ok = (want_mid && !mid_in) ? (K == 0 || pl < 1.0f)    /* not even the mid-symbol hit */
+				const bool none_ok = (want_mid && !mid_in) ? (pl < 1.0f)              /* not even the mid-symbol hit */
 				                                           : (lim <= c1 || pl < 2.0f);
-				const bool ok = lim == 0 || (mid_ok && (sym_in ? hit_ok : none_ok));   /* idle lanes never veto */
-				if (prof_on) n_rounds++;
-				if (__all_sync(FULL, ok)) {
+				const bool ok = mid_ok && (sym_in ? hit_ok : none_ok);
+				if (ok) {
 					if (mid_in) { tr.interm = y_mid; tr.target = 2.0f; }
 					tr.phase = pl;
 					if (sym_in) {
-						symbol_hit(tr, y_sym, center, alpha, beta, max_fdev, ring, ring_mask, soft, p.soft_stride, own);
-						rf = rcp_approx(tr.freq);
+						tr.phase = ph_new; tr.freq = f_new; tr.prev = y_sym; tr.target = 1.0f;
+						rf = rcp_approx(f_new);
+						emit_symbol<SOFT>(tr, y_sym, ring, ring_mask, soft, p.soft_stride);
 					}
 					s += K;
 				} else {
@@ -550,13 +569,16 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 					}
 					tr.phase = ph;
 					if (sym) {
-						symbol_hit(tr, y_at<P>(y, g, s + used - 1), center, alpha, beta, max_fdev, ring, ring_mask, soft,
-						           p.soft_stride, own);
+						const float yv = y_at<P>(y, g, s + used - 1);
+						retime(tr, yv, center, alpha, beta, max_fdev);
 						rf = rcp_approx(tr.freq);
+						emit_symbol<SOFT>(tr, yv, ring, ring_mask, soft, p.soft_stride);
 					}
 					s += used;
 				}
+				if (prof_on) n_rounds++;
 			}
+			__syncwarp();
 			warp_arrive(&sm.yfree[ss], lane);
 		}
 		if (own) {
@@ -579,18 +601,25 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	}
 }
 
-template <int P, int N, bool IQ>
-cudaError_t launch(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
+template <int P, int N, bool IQ, bool SOFT>
+cudaError_t launch2(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
 	static bool attr_done = false;
 	if (!attr_done) {
-		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, N, IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, N, IQ, SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                     (int)sizeof(smem_t<P>));
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
-	demod_pipe_kernel<P, N, IQ><<<n_groups, NTHREADS, sizeof(smem_t<P>), stream>>>(*p, group_base);
+	demod_pipe_kernel<P, N, IQ, SOFT><<<n_groups, NTHREADS, sizeof(smem_t<P>), stream>>>(*p, group_base);
 	return cudaGetLastError();
+}
+
+template <int P, int N, bool IQ>
+cudaError_t launch(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
+{
+	return p->soft ? launch2<P, N, IQ, true>(p, group_base, n_groups, stream)
+	               : launch2<P, N, IQ, false>(p, group_base, n_groups, stream);
 }
 
 }  // namespace
