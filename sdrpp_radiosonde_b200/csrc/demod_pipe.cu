@@ -40,24 +40,31 @@ namespace {
 
 constexpr int G = 8;                     /* channels per CTA                       */
 constexpr int T = 256;                   /* samples per tile                       */
-constexpr int NPW = 8;                   /* parallel-work warps                    */
-constexpr int NPWT = NPW * 32;           /* = T : one sample column per PW thread  */
-constexpr int NTHREADS = (NPW + 3) * 32;
-/* Warp roles, chosen so that the four schedulers (warp id % 4) carry similar issue load:
- *   SMSP0: PW PW PW | SMSP1: PW PW PW | SMSP2: A1 A2 PW | SMSP3: TM PW          */
+constexpr int NPW = 16;                  /* parallel-work warps                    */
+constexpr int NPWT = NPW * 32;           /* PW threads                             */
+constexpr int CPT = G * T / NPWT;        /* channels per PW thread in S1 / S3 (one sample column each) */
+/* Warp roles by scheduler (warp id % 4).  The timing lane is latency-bound and loses issue slots to
+ * any PW warp on its scheduler, so it gets SMSP3 to itself (warps 7, 11, 15, 19 exit right away):
+ *   SMSP0: 6 PW | SMSP1: 6 PW | SMSP2: A1, A2, 4 PW | SMSP3: TM                                */
+constexpr int NWARPS = 23;
+constexpr int NTHREADS = NWARPS * 32;
 constexpr int W_A1 = 2, W_A2 = 6, W_TM = 3;
+__device__ __forceinline__ bool is_idle_warp(int warp) { return (warp & 3) == 3 && warp != W_TM; }
 __device__ __forceinline__ int pw_index(int warp)
 {
-	/* warps 0,1,4,5,7,8,9,10 -> 0..7 */
-	return warp < 2 ? warp : warp < 6 ? warp - 2 : warp - 3;
+	/* SMSP0 ids 0,4,..,20 -> 0..5 ; SMSP1 ids 1,5,..,21 -> 6..11 ; SMSP2 ids 10,14,18,22 -> 12..15 */
+	const int q = warp >> 2, r = warp & 3;
+	return r == 0 ? q : r == 1 ? 6 + q : 12 + (q - 2);
 }
 constexpr int RS = T + 4;                /* row stride: 16 B aligned, lanes (= rows) hit distinct banks */
 constexpr int AS = SONDE_FIR_HIST + T + 4;
-constexpr int R = 8;                     /* FIR outputs per thread                 */
+constexpr int R = G * T / NPWT;           /* FIR outputs per thread                 */
+constexpr int SEGS = T / R;              /* FIR segments per channel row           */
 constexpr int NX = 3, NS2 = 2;           /* ring depths                            */
 constexpr unsigned FULL = 0xffffffffu;
 
-static_assert(G == NPW && T == NPWT && T / R == 32, "thread <-> work mappings below rely on this");
+static_assert(NPWT % T == 0 && CPT * (NPWT / T) == G && R % 4 == 0 && SEGS % 32 == 0 && (SEGS / 32) * G == NPW,
+              "thread <-> work mappings below rely on this");
 
 template <int P>
 struct smem_t {
@@ -263,24 +270,29 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	if (tid < G) sm.carry[0][tid] = (chans[tid] >= 0) ? p.st[chans[tid]].disc_prev : 0.0f;
 	__syncthreads();
 
+	if (is_idle_warp(warp)) return;
 	if (warp != W_A1 && warp != W_A2 && warp != W_TM) {
 		/* =============================== PW: S1 / S3 / S4 =================================== */
-		const int pw = pw_index(warp);           /* 0..7 : FIR channel row owned in S4          */
-		const int t = pw * 32 + lane;            /* sample column owned in S1 / S3              */
-		int ch_of[G];
+		const int pw = pw_index(warp);           /* 0..NPW-1                                     */
+		const int pt = pw * 32 + lane;           /* PW thread index                              */
+		const int t = pt % T;                    /* sample column owned in S1 / S3               */
+		const int g0 = (pt / T) * CPT;           /* first of the CPT channels owned in S1 / S3   */
+		const int fir_g = pw % G;                /* channel row owned in S4                      */
+		const int fir_seg = (pw / G) * 32 + lane;/* segment of R outputs owned in S4             */
+		int ch_of[CPT];
 #pragma unroll
-		for (int g = 0; g < G; g++) ch_of[g] = chans[g];
+		for (int c = 0; c < CPT; c++) ch_of[c] = chans[g0 + c];
 
 		const unsigned long long negzero2 = *reinterpret_cast<volatile unsigned long long *>(&sm.negzero2);
-		float2 q[G];                             /* prefetched raw input of the next S1 tile    */
+		float2 q[CPT];                           /* prefetched raw input of the next S1 tile    */
 		auto prefetch = [&](int tile) {
 			const int i = tile * T + t;
 #pragma unroll
-			for (int g = 0; g < G; g++) {
-				q[g] = make_float2(0.0f, 0.0f);
-				if (tile < ntiles && i < L && ch_of[g] >= 0) {
-					if (IQ) q[g] = __ldg(static_cast<const float2 *>(p.in) + (size_t)ch_of[g] * p.row_stride + i);
-					else    q[g].x = __ldg(static_cast<const float *>(p.in) + (size_t)ch_of[g] * p.row_stride + i);
+			for (int c = 0; c < CPT; c++) {
+				q[c] = make_float2(0.0f, 0.0f);
+				if (tile < ntiles && i < L && ch_of[c] >= 0) {
+					if (IQ) q[c] = __ldg(static_cast<const float2 *>(p.in) + (size_t)ch_of[c] * p.row_stride + i);
+					else    q[c].x = __ldg(static_cast<const float *>(p.in) + (size_t)ch_of[c] * p.row_stride + i);
 				}
 			}
 		};
@@ -288,27 +300,29 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 		auto stage1 = [&](int tile) {
 			const int slot = tile % NX;
 			const int n = min(T, L - tile * T);
-			float cur[G];
-			if (t == 0) sm.zflag[slot] = 0;
+			float cur[CPT];
+			if (pt == 0) sm.zflag[slot] = 0;
 #pragma unroll
-			for (int g = 0; g < G; g++) {
+			for (int c = 0; c < CPT; c++) {
+				const int g = g0 + c;
 				if (IQ) {
-					const float phv = (t < n) ? det_phase(q[g].x, q[g].y) : 0.0f;
+					const float phv = (t < n) ? det_phase(q[c].x, q[c].y) : 0.0f;
 					sm.ph[g][t + 1] = phv;
 					if (t == n - 1) sm.carry[(tile + 1) & 1][g] = phv;
 				} else {
-					cur[g] = q[g].x;
+					cur[c] = q[c].x;
 				}
 			}
-			if (IQ && t < G) sm.ph[t][0] = sm.carry[tile & 1][t];
+			if (IQ && pt < G) sm.ph[pt][0] = sm.carry[tile & 1][pt];
 			prefetch(tile + 1);
 			pw_barrier();
 			bool zero = false;
 #pragma unroll
-			for (int g = 0; g < G; g++) {
-				const float xv = IQ ? disc_step(sm.ph[g][t + 1], sm.ph[g][t], p.fm_gain) : cur[g];
+			for (int c = 0; c < CPT; c++) {
+				const int g = g0 + c;
+				const float xv = IQ ? disc_step(sm.ph[g][t + 1], sm.ph[g][t], p.fm_gain) : cur[c];
 				sm.x[slot][g][t] = xv;
-				zero |= (t < n && ch_of[g] >= 0 && xv == 0.0f);
+				zero |= (t < n && ch_of[c] >= 0 && xv == 0.0f);
 			}
 			if (zero) atomicOr(&sm.zflag[slot], 1);
 			warp_arrive(&sm.xfull[slot], lane);
@@ -329,14 +343,15 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			mbar_wait_t(&sm.vfull[ss], par, wacc[0], prof_on);            /* implies sfull[ss] (A2 consumed it first) */
 			const bool zslow = sm.zflag[xs] != 0;
 #pragma unroll
-			for (int g = 0; g < G; g++) {
+			for (int c = 0; c < CPT; c++) {
+				const int g = g0 + c;
 				float o = 0.0f;
-				if (t < n && ch_of[g] >= 0 && !(zslow && sm.x[xs][g][t] == 0.0f))
+				if (t < n && ch_of[c] >= 0 && !(zslow && sm.x[xs][g][t] == 0.0f))
 					o = fmul(sm.s[ss][g][t], fdiv(5.0f, sm.v[ss][g][t]));
 				sm.a[ss][g][SONDE_FIR_HIST + t] = o;
 			}
 			/* head = tail of the previous tile */
-			for (int i = t; i < G * SONDE_FIR_HIST; i += NPWT) {
+			for (int i = pt; i < G * SONDE_FIR_HIST; i += NPWT) {
 				const int g = i / SONDE_FIR_HIST, j = i % SONDE_FIR_HIST;
 				sm.a[ss][g][j] = sm.a[ss ^ 1][g][T + j];
 			}
@@ -346,7 +361,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 
 			/* ---- S4(k) ---- */
 			mbar_wait_t(&sm.yfree[ss], par ^ 1, wacc[1], prof_on);
-			fir_segment<P>(sm.a[ss][pw], sm.y[ss], sm.taps, negzero2, pw, lane);
+			fir_segment<P>(sm.a[ss][fir_g], sm.y[ss], sm.taps, negzero2, fir_g, fir_seg);
 			warp_arrive(&sm.yfull[ss], lane);
 		}
 
@@ -355,11 +370,11 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 		{
 			const int ls = (ntiles - 1) % NS2;
 			const int nl = L - (ntiles - 1) * T;
-			for (int i = t; i < G * SONDE_FIR_HIST; i += NPWT) {
+			for (int i = pt; i < G * SONDE_FIR_HIST; i += NPWT) {
 				const int g = i / SONDE_FIR_HIST, j = i % SONDE_FIR_HIST;
-				if (ch_of[g] >= 0) p.st[ch_of[g]].hist[j] = sm.a[ls][g][nl + j];
+				if (chans[g] >= 0) p.st[chans[g]].hist[j] = sm.a[ls][g][nl + j];
 			}
-			if (IQ && t < G && chans[t] >= 0) p.st[chans[t]].disc_prev = sm.carry[ntiles & 1][t];
+			if (IQ && pt < G && chans[pt] >= 0) p.st[chans[pt]].disc_prev = sm.carry[ntiles & 1][pt];
 		}
 	} else if (warp == W_A1) {
 		/* =============================== A1: bias recurrence ================================ */
