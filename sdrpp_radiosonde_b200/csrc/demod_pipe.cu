@@ -43,19 +43,35 @@ constexpr int T = 256;                   /* samples per tile                    
 constexpr int NPW = 16;                  /* parallel-work warps                    */
 constexpr int NPWT = NPW * 32;           /* PW threads                             */
 constexpr int CPT = G * T / NPWT;        /* channels per PW thread in S1 / S3 (one sample column each) */
-/* Warp roles by scheduler (warp id % 4).  The timing lane is latency-bound and loses issue slots to
- * any PW warp on its scheduler, so it gets SMSP3 to itself (warps 7, 11, 15, 19 exit right away):
- *   SMSP0: 6 PW | SMSP1: 6 PW | SMSP2: A1, A2, 4 PW | SMSP3: TM                                */
-constexpr int NWARPS = 23;
-constexpr int NTHREADS = NWARPS * 32;
-constexpr int W_A1 = 2, W_A2 = 6, W_TM = 3;
-__device__ __forceinline__ bool is_idle_warp(int warp) { return (warp & 3) == 3 && warp != W_TM; }
-__device__ __forceinline__ int pw_index(int warp)
-{
-	/* SMSP0 ids 0,4,..,20 -> 0..5 ; SMSP1 ids 1,5,..,21 -> 6..11 ; SMSP2 ids 10,14,18,22 -> 12..15 */
-	const int q = warp >> 2, r = warp & 3;
-	return r == 0 ? q : r == 1 ? 6 + q : 12 + (q - 2);
-}
+/* Warp roles by scheduler (warp id % 4).  The serial lanes are latency-bound (IPC ~0.3) and lose issue slots
+ * to any PW warp on their scheduler.  Two placements, picked per kernel variant from measurements
+ * (tools/stalls.py):
+ *   layout 0 (timing lane is the critical stage: RS41, M10): TM alone on SMSP3
+ *        SMSP0: 6 PW | SMSP1: 6 PW | SMSP2: A1, A2, 4 PW | SMSP3: TM (+ 4 warps that exit at once)
+ *   layout 1 (AGC lanes are the critical stage: DFM, iMS-100, MRZ-N1): all three serial lanes on SMSP3
+ *        SMSP0: 6 PW | SMSP1: 5 PW | SMSP2: 5 PW | SMSP3: TM, A1, A2                                */
+template <int LAYOUT>
+struct roles;
+template <>
+struct roles<0> {
+	static constexpr int NWARPS = 23, W_TM = 3, W_A1 = 2, W_A2 = 6;
+	static __device__ __forceinline__ bool idle(int warp) { return (warp & 3) == 3 && warp != W_TM; }
+	static __device__ __forceinline__ int pw_index(int warp)
+	{
+		const int q = warp >> 2, r = warp & 3;        /* ids 0,4,..,20 -> 0..5 ; 1,5,..,21 -> 6..11 ; 10,14,18,22 -> 12..15 */
+		return r == 0 ? q : r == 1 ? 6 + q : 12 + (q - 2);
+	}
+};
+template <>
+struct roles<1> {
+	static constexpr int NWARPS = 21, W_TM = 3, W_A1 = 7, W_A2 = 11;
+	static __device__ __forceinline__ bool idle(int warp) { return (warp & 3) == 3 && warp > W_A2; }
+	static __device__ __forceinline__ int pw_index(int warp)
+	{
+		const int q = warp >> 2, r = warp & 3;        /* ids 0,4,..,20 -> 0..5 ; 1,5,..,17 -> 6..10 ; 2,6,..,18 -> 11..15 */
+		return r == 0 ? q : r == 1 ? 6 + q : 11 + q;
+	}
+};
 constexpr int RS = T + 4;                /* row stride: 16 B aligned, lanes (= rows) hit distinct banks */
 constexpr int AS = SONDE_FIR_HIST + T + 4;
 constexpr int R = G * T / NPWT;           /* FIR outputs per thread                 */
@@ -232,13 +248,16 @@ __device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS]
 	}
 }
 
-template <int P, int N, bool IQ, bool SOFT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int P, int N, bool IQ, bool SOFT, int LAYOUT>
+__global__ void __launch_bounds__(roles<LAYOUT>::NWARPS * 32, 1)
 demod_pipe_kernel(const demod_params p, const int group_base)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	smem_t<P> &sm = *reinterpret_cast<smem_t<P> *>(smem_raw);
 
+	using RL = roles<LAYOUT>;
+	constexpr int NTHREADS = RL::NWARPS * 32;
+	constexpr int W_A1 = RL::W_A1, W_A2 = RL::W_A2, W_TM = RL::W_TM;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int grp = group_base + blockIdx.x;
 	const sonde_modem &md = c_modem[p.group_type[grp]];
@@ -270,10 +289,10 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	if (tid < G) sm.carry[0][tid] = (chans[tid] >= 0) ? p.st[chans[tid]].disc_prev : 0.0f;
 	__syncthreads();
 
-	if (is_idle_warp(warp)) return;
+	if (RL::idle(warp)) return;
 	if (warp != W_A1 && warp != W_A2 && warp != W_TM) {
 		/* =============================== PW: S1 / S3 / S4 =================================== */
-		const int pw = pw_index(warp);           /* 0..NPW-1                                     */
+		const int pw = RL::pw_index(warp);           /* 0..NPW-1                                     */
 		const int pt = pw * 32 + lane;           /* PW thread index                              */
 		const int t = pt % T;                    /* sample column owned in S1 / S3               */
 		const int g0 = (pt / T) * CPT;           /* first of the CPT channels owned in S1 / S3   */
@@ -619,14 +638,15 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 template <int P, int N, bool IQ, bool SOFT>
 cudaError_t launch2(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
+	constexpr int LAYOUT = (N == 24) ? 1 : 0;
 	static bool attr_done = false;
 	if (!attr_done) {
-		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, N, IQ, SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                                     (int)sizeof(smem_t<P>));
+		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, N, IQ, SOFT, LAYOUT>,
+		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem_t<P>));
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
-	demod_pipe_kernel<P, N, IQ, SOFT><<<n_groups, NTHREADS, sizeof(smem_t<P>), stream>>>(*p, group_base);
+	demod_pipe_kernel<P, N, IQ, SOFT, LAYOUT><<<n_groups, roles<LAYOUT>::NWARPS * 32, sizeof(smem_t<P>), stream>>>(*p, group_base);
 	return cudaGetLastError();
 }
 
