@@ -174,6 +174,10 @@ SONDE_API int  sonde_b200_debug_stalls(sonde_b200 *h, long long *out, int cap_gr
 /* The CUDA stream (cudaStream_t) all work of this handle is enqueued on. */
 SONDE_API void *sonde_b200_stream(sonde_b200 *h);
 
+/* Device-side join: the stream returned by sonde_b200_stream() waits for the framer kernels of every call made
+ * so far (they run on an internal stream so that frame(i) overlaps demod(i+1)).  Does not block the host. */
+SONDE_API int  sonde_b200_join(sonde_b200 *h);
+
 /* Block until everything enqueued so far has finished. */
 SONDE_API int  sonde_b200_sync(sonde_b200 *h);
 

@@ -25,7 +25,7 @@ EXPORTS = [
     "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
     "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
     "sonde_b200_soft_stride", "sonde_b200_fetch_soft", "sonde_b200_fetch_state", "sonde_b200_modem_info",
-    "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_stream", "sonde_b200_sync",
+    "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
     "sonde_b200_last_kernel_ms", "sonde_b200_launch_count", "sonde_b200_last_error", "sonde_b200_version",
 ]
 
@@ -103,6 +103,7 @@ def load():
         "sonde_b200_stream": (vp, [vp]),
         "sonde_b200_debug_stalls": (ctypes.c_int, [vp, vp, ctypes.c_int]),
         "sonde_b200_sync": (ctypes.c_int, [vp]),
+        "sonde_b200_join": (ctypes.c_int, [vp]),
         "sonde_b200_last_kernel_ms": (ctypes.c_int, [vp, f32p, f32p]),
         "sonde_b200_launch_count": (ctypes.c_long, [vp]),
         "sonde_b200_last_error": (ctypes.c_char_p, [vp]),
@@ -269,6 +270,10 @@ class BatchDecoder:
         out = np.zeros((max(n, 1), 4, 4), dtype=np.int64)
         n = self.lib.sonde_b200_debug_stalls(self.h, out.ctypes.data, out.shape[0])
         return out[:n]
+
+    def join(self):
+        """Device-side: the handle's main stream waits for all framer kernels issued so far."""
+        self._ck(self.lib.sonde_b200_join(self.h))
 
     def sync(self):
         self._ck(self.lib.sonde_b200_sync(self.h))

@@ -389,6 +389,7 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 		st.agc_bias = bias; st.agc_avg = avg;
 		st.t_prev = tr.prev; st.t_phase = tr.phase; st.t_freq = tr.freq; st.t_state = tr.state;
 		st.bit_acc = tr.acc; st.bit_cnt = tr.cnt; st.nbits = tr.nbits; st.nsoft = tr.nsoft;
+		p.nbits_out[my_ch] = tr.nbits;
 		if (p.is_iq) st.disc_prev = sm.ph[tid][0];
 		if (tr.cnt)                                       /* left-aligned partial byte, gfsk.c:78 */
 			my_ring[(uint32_t)(tr.nbits >> 3) & ring_mask] = (uint8_t)(tr.acc << (8 - tr.cnt));

@@ -621,6 +621,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			const int cnt = (int)(tr.nb & 7u);
 			st.t_prev = tr.prev; st.t_phase = tr.phase; st.t_freq = tr.freq; st.t_state = (int)tr.target;
 			st.bit_acc = tr.acc & ((1u << cnt) - 1u); st.bit_cnt = cnt; st.nbits = nbits; st.nsoft = tr.nsoft;
+			p.nbits_out[ch] = nbits;
 			if (cnt) ring[(uint32_t)(nbits >> 3) & ring_mask] = (uint8_t)(tr.acc << (8 - cnt));
 		}
 	}

@@ -81,12 +81,14 @@ struct demod_params {
 	float        *soft;           /* [C][soft_stride] or NULL                         */
 	int32_t       soft_stride;
 	long long    *prof;           /* optional [n_groups][16] cycle counters (diagnostics) */
+	uint64_t     *nbits_out;      /* [C] stream length after this call (snapshot for the framer, which
+	                                 may run concurrently with the next call's demodulator)             */
 };
 
 struct frame_params {
 	int32_t        n_channels;
 	const int32_t *types;         /* [C]                                              */
-	const demod_state *dst;       /* [C] (nbits)                                      */
+	const uint64_t *nbits;        /* [C] demodulated stream length at the end of this call */
 	framer_state  *fst;           /* [C]                                              */
 	const uint8_t *ring;
 	uint32_t       ring_bytes;

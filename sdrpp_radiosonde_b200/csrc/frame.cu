@@ -23,6 +23,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "device_state.h"
 
@@ -135,30 +136,16 @@ struct gf {
 	}
 };
 
-__device__ void build_gf_tables(gf_tables &t, int tid, int nthreads)
+/* The log/antilog tables are built once on the host with the reference's recurrence (rs.c:78-87; note that
+ * logtable[1] ends up = n, not 0, because alpha[n] = 1 overwrites it — kept on purpose) and copied to
+ * shared memory by every CTA. */
+__device__ gf_tables g_gf;
+
+__device__ __forceinline__ void load_gf_tables(gf_tables &t, int tid, int nthreads)
 {
-	/* sequential recurrence, done by one thread per field (rs.c:78-87); note logtable[1]
-	 * ends up = n, not 0, because alpha[n] = 1 overwrites it — kept on purpose. */
-	if (tid == 0) {
-		uint32_t a = 1;
-		t.exp256[0] = 1; t.log256[0] = 0; t.log256[1] = 0;
-		for (int i = 1; i < 256; i++) {
-			a <<= 1;
-			if (a >= 256) a ^= 0x11D;
-			t.exp256[i] = (uint8_t)a;
-			t.log256[a] = (uint8_t)i;
-		}
-	}
-	if (tid == 32 % nthreads) {
-		uint32_t a = 1;
-		t.exp64[0] = 1; t.log64[0] = 0; t.log64[1] = 0;
-		for (int i = 1; i < 64; i++) {
-			a <<= 1;
-			if (a >= 64) a ^= 0x61;
-			t.exp64[i] = (uint8_t)a;
-			t.log64[a] = (uint8_t)i;
-		}
-	}
+	const uint32_t *src = reinterpret_cast<const uint32_t *>(&g_gf);
+	uint32_t *dst = reinterpret_cast<uint32_t *>(&t);
+	for (int i = tid; i < (int)(sizeof(gf_tables) / 4); i += nthreads) dst[i] = src[i];
 }
 
 /* ---- Reed-Solomon RS(255,231), warp-cooperative (rs.c:99-212, first_root 0, root_skip 1) -
@@ -169,13 +156,35 @@ __device__ int rs255_fix_warp(warp_smem &ws, const gf_tables &gt, int lane)
 	const gf<N> f = {gt.exp256, gt.log256};
 	uint8_t *data = ws.blk;
 
-	/* syndromes: lane j evaluates the block at zeroes[j] = alpha^j by Horner (rs.c:120-123,215-224) */
-	uint32_t syn = 0;
-	if (lane < TT) {
-		const uint32_t z = gt.exp256[lane];
-		for (int k = N - 1; k >= 0; k--) syn = f.mul(syn, z) ^ data[k];
-		ws.syn[lane] = (uint8_t)syn;
+	/* syndromes S_j = sum_i data[i] * alpha^(i*j), j = 0..23 (== the reference's Horner evaluation at
+	 * zeroes[j] = alpha^j, rs.c:120-123,215-224; GF arithmetic is exact, so the summation order is free).
+	 * Lane l takes symbols 8l .. 8l+7 and all 24 syndromes, then the lanes are XOR-reduced. */
+	uint32_t part[TT];
+#pragma unroll
+	for (int j = 0; j < TT; j++) part[j] = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		const int i = 8 * lane + k;
+		const uint32_t d = (i < N) ? data[i] : 0u;
+		const uint32_t ld = gt.log256[d];
+		uint32_t e = (ld >= N) ? ld - N : ld;    /* (log d + i*j) mod 255, stepped by i per syndrome; log 1 == 255 */
+		const uint32_t step = (i >= N) ? i - N : i;
+#pragma unroll
+		for (int j = 0; j < TT; j++) {
+			part[j] ^= d ? gt.exp256[e] : 0u;
+			e += step;
+			if (e >= N) e -= N;
+		}
 	}
+	uint32_t syn = 0;
+#pragma unroll
+	for (int j = 0; j < TT; j++) {
+		uint32_t v = part[j];
+#pragma unroll
+		for (int o = 16; o; o >>= 1) v ^= __shfl_xor_sync(FULL, v, o);
+		if (lane == j) syn = v;
+	}
+	if (lane < TT) ws.syn[lane] = (uint8_t)syn;
 	if (!__any_sync(FULL, syn != 0)) return 0;
 	__syncwarp();
 
@@ -636,7 +645,7 @@ frame_kernel(const frame_params p)
 {
 	__shared__ cta_smem sm;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	build_gf_tables(sm.gf, threadIdx.x, blockDim.x);
+	load_gf_tables(sm.gf, threadIdx.x, blockDim.x);
 	__syncthreads();
 
 	const int ch = blockIdx.x * WARPS_PER_CTA + wid;
@@ -651,7 +660,7 @@ frame_kernel(const frame_params p)
 	const int nq = 8 * (F / 8 + S / 8) - S;                   /* candidate offsets: correlator.c:36-63 */
 	const uint8_t *ring = p.ring + (size_t)ch * p.ring_bytes;
 	const uint32_t rmask = p.ring_bytes - 1;
-	const uint64_t B = p.dst[ch].nbits;
+	const uint64_t B = p.nbits[ch];
 
 	struct { uint64_t d_pos; int n_carry, zero_prefix, frames_total, ok_total, frames_last, ok_last; } fs;
 	{
@@ -823,6 +832,29 @@ frame_kernel(const frame_params p)
 }
 
 }  // namespace
+
+extern "C" cudaError_t sonde_upload_gf_tables(void)
+{
+	gf_tables t;
+	memset(&t, 0, sizeof(t));
+	unsigned a = 1;
+	t.exp256[0] = 1;
+	for (int i = 1; i < 256; i++) {
+		a <<= 1;
+		if (a >= 256) a ^= 0x11D;
+		t.exp256[i] = (uint8_t)a;
+		t.log256[a] = (uint8_t)i;
+	}
+	a = 1;
+	t.exp64[0] = 1;
+	for (int i = 1; i < 64; i++) {
+		a <<= 1;
+		if (a >= 64) a ^= 0x61;
+		t.exp64[i] = (uint8_t)a;
+		t.log64[a] = (uint8_t)i;
+	}
+	return cudaMemcpyToSymbol(g_gf, &t, sizeof(t));
+}
 
 extern "C" cudaError_t sonde_launch_frames(const frame_params *p, cudaStream_t stream)
 {

@@ -20,6 +20,7 @@
 
 extern "C" cudaError_t sonde_upload_modems(const sonde_modem *m);
 extern "C" cudaError_t sonde_upload_modems_frame(const sonde_modem *m);
+extern "C" cudaError_t sonde_upload_gf_tables(void);
 extern "C" cudaError_t sonde_launch_demod_gfsk(const demod_params *p, int group_base, int n_groups, int phases,
                                                cudaStream_t stream);
 extern "C" cudaError_t sonde_upload_modems_pipe(const sonde_modem *m);
@@ -51,6 +52,9 @@ struct sonde_b200 {
 	sonde_frame_rec *d_recs[2] = {nullptr, nullptr};
 	int32_t *d_counts[2] = {nullptr, nullptr};
 	cudaStream_t cstream = nullptr, dstream = nullptr;        /* H2D copies, D2H fetches */
+	cudaStream_t fstream = nullptr;                          /* framer kernels: frame(i) overlaps demod(i+1) */
+	cudaEvent_t ev_demod[2] = {nullptr, nullptr}, evf[2] = {nullptr, nullptr};
+	uint64_t *d_nbits[2] = {nullptr, nullptr};
 	cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 	long n_issued = 0, n_fetched = 0;
 	float *d_soft = nullptr;
@@ -146,9 +150,15 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	if (sonde_upload_modems(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_frame(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (sonde_upload_gf_tables() != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->dstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (cudaStreamCreateWithFlags(&h->fstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	for (int b = 0; b < 2; b++)
+		if (cudaEventCreateWithFlags(&h->ev_demod[b], cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreate(&h->evf[b]) != cudaSuccess)
+			return bail(SONDE_ERR_CUDA);
 	for (auto &e : h->ev)
 		if (cudaEventCreate(&e) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	for (int b = 0; b < 2; b++)
@@ -211,6 +221,8 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	for (int b = 0; b < 2; b++) {
 		CKB(cudaMalloc(&h->d_recs[b], (size_t)C * h->max_frames * sizeof(sonde_frame_rec)));
 		CKB(cudaMalloc(&h->d_counts[b], (size_t)C * 2 * sizeof(int32_t)));
+		CKB(cudaMalloc(&h->d_nbits[b], (size_t)C * sizeof(uint64_t)));
+		CKB(cudaMemset(h->d_nbits[b], 0, (size_t)C * sizeof(uint64_t)));
 		CKB(cudaMemset(h->d_counts[b], 0, (size_t)C * 2 * sizeof(int32_t)));
 	}
 	CKB(cudaMallocHost(&h->h_counts, (size_t)C * 2 * sizeof(int32_t)));
@@ -247,13 +259,16 @@ void sonde_b200_destroy(sonde_b200 *h)
 	cudaFree(h->d_demod); cudaFree(h->d_afsk); cudaFree(h->d_framer); cudaFree(h->d_ring);
 	cudaFree(h->d_prof);
 	for (int b = 0; b < 2; b++) {
-		cudaFree(h->d_recs[b]); cudaFree(h->d_counts[b]); cudaFree(h->d_in[b]);
+		cudaFree(h->d_recs[b]); cudaFree(h->d_counts[b]); cudaFree(h->d_in[b]); cudaFree(h->d_nbits[b]);
+		if (h->ev_demod[b]) cudaEventDestroy(h->ev_demod[b]);
+		if (h->evf[b]) cudaEventDestroy(h->evf[b]);
 		if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
 		if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
 	}
 	cudaFree(h->d_soft);
 	if (h->cstream) cudaStreamDestroy(h->cstream);
 	if (h->dstream) cudaStreamDestroy(h->dstream);
+	if (h->fstream) cudaStreamDestroy(h->fstream);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	for (auto &e : h->ev)
 		if (e) cudaEventDestroy(e);
@@ -287,6 +302,10 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	dp.soft_stride = h->soft_stride;
 	dp.prof = h->d_prof;
 
+	const int par = (int)(h->n_issued & 1);
+	dp.nbits_out = h->d_nbits[par];
+	/* the demodulator of call i+2 appends to ring positions the framer of call i may still be reading */
+	if (h->n_issued >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_done[par], 0));
 	CK(cudaEventRecord(h->ev[0], h->stream));
 	/* production kernel: the warp-specialised pipeline; reserved bit 0 selects the phase-by-phase
 	 * kernel of demod.cu (kept as an independent cross-check for the tests) */
@@ -304,24 +323,27 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 		h->launches++;
 	}
 	CK(cudaEventRecord(h->ev[1], h->stream));
+	CK(cudaEventRecord(h->ev_demod[par], h->stream));
 
+	/* the framer runs on its own stream: frame(i) overlaps demod(i+1); framer kernels stay in order */
 	frame_params fp;
 	memset(&fp, 0, sizeof(fp));
 	fp.n_channels = h->cfg.n_channels;
 	fp.types = h->d_types;
-	fp.dst = h->d_demod;
+	fp.nbits = h->d_nbits[par];
 	fp.fst = h->d_framer;
 	fp.ring = h->d_ring;
 	fp.ring_bytes = h->ring_bytes;
-	const int par = (int)(h->n_issued & 1);
 	fp.recs = h->d_recs[par];
 	fp.max_frames = h->max_frames;
 	fp.chunk_index = h->chunk_index;
 	fp.counts = h->d_counts[par];
-	CK(sonde_launch_frames(&fp, h->stream));
+	CK(cudaStreamWaitEvent(h->fstream, h->ev_demod[par], 0));
+	CK(cudaEventRecord(h->evf[0], h->fstream));
+	CK(sonde_launch_frames(&fp, h->fstream));
 	h->launches++;
-	CK(cudaEventRecord(h->ev[2], h->stream));
-	CK(cudaEventRecord(h->ev_done[par], h->stream));
+	CK(cudaEventRecord(h->evf[1], h->fstream));
+	CK(cudaEventRecord(h->ev_done[par], h->fstream));
 	h->have_timing = true;
 	h->chunk_index++;
 	h->n_issued++;
@@ -371,7 +393,19 @@ int sonde_b200_sync(sonde_b200 *h)
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->cstream));
 	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaStreamSynchronize(h->fstream));
 	CK(cudaStreamSynchronize(h->dstream));
+	return SONDE_OK;
+}
+
+/* Make the main stream wait (on the device, not the host) for every framer kernel enqueued so far, so that an
+ * event recorded on sonde_b200_stream() afterwards covers the whole work of the calls made up to now. */
+int sonde_b200_join(sonde_b200 *h)
+{
+	if (!h) return SONDE_ERR_ARG;
+	if (h->n_issued == 0) return SONDE_OK;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamWaitEvent(h->stream, h->ev_done[(h->n_issued - 1) & 1], 0));
 	return SONDE_OK;
 }
 
@@ -417,6 +451,7 @@ int sonde_b200_fetch_totals(sonde_b200 *h, int64_t *frames, int64_t *ok, int64_t
 	if (!h) return SONDE_ERR_ARG;
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaStreamSynchronize(h->fstream));
 	const int C = h->cfg.n_channels;
 	std::vector<framer_state> fs(C);
 	std::vector<demod_state> ds(C);
@@ -454,6 +489,7 @@ int sonde_b200_fetch_bits(sonde_b200 *h, uint8_t *bits, int32_t *nbits)
 	if (!h || !bits || !nbits) return SONDE_ERR_ARG;
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaStreamSynchronize(h->fstream));
 	const int C = h->cfg.n_channels;
 	std::vector<demod_state> st(C);
 	std::vector<uint8_t> ring((size_t)C * h->ring_bytes);
@@ -482,6 +518,7 @@ int sonde_b200_fetch_soft(sonde_b200 *h, float *soft, int32_t *nsoft)
 	if (!h->d_soft) return fail(h, SONDE_ERR_STATE, "created without keep_soft");
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaStreamSynchronize(h->fstream));
 	const int C = h->cfg.n_channels;
 	std::vector<demod_state> st(C);
 	CK(cudaMemcpy(st.data(), h->d_demod, st.size() * sizeof(demod_state), cudaMemcpyDeviceToHost));
@@ -495,6 +532,7 @@ int sonde_b200_fetch_state(sonde_b200 *h, float *state /*[C][8]*/)
 	if (!h || !state) return SONDE_ERR_ARG;
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaStreamSynchronize(h->fstream));
 	const int C = h->cfg.n_channels;
 	std::vector<demod_state> st(C);
 	CK(cudaMemcpy(st.data(), h->d_demod, st.size() * sizeof(demod_state), cudaMemcpyDeviceToHost));
@@ -511,10 +549,11 @@ int sonde_b200_last_kernel_ms(sonde_b200 *h, float *demod_ms, float *frame_ms)
 	if (!h) return SONDE_ERR_ARG;
 	if (!h->have_timing) return fail(h, SONDE_ERR_STATE, "no process call yet");
 	CK(cudaSetDevice(h->device));
-	CK(cudaEventSynchronize(h->ev[2]));
+	CK(cudaEventSynchronize(h->ev[1]));
+	CK(cudaEventSynchronize(h->evf[1]));
 	float a = 0, b = 0;
 	CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
-	CK(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+	CK(cudaEventElapsedTime(&b, h->evf[0], h->evf[1]));
 	if (demod_ms) *demod_ms = a;
 	if (frame_ms) *frame_ms = b;
 	return SONDE_OK;
