@@ -15,10 +15,10 @@
  * SondeFullData and call back iff fragment.fields != 0 -> flush().
  *
  * Telemetry: frame -> SondeData conversion is SURVEY.md §8 row f-1 ("next"); fragment_from_record()
- * below covers what the frame gate itself establishes (RS41 status subframe: sequence number and
- * serial, CRC-checked as rs41.c:165-175 does; M10/M20, MRZ-N1: sequence counters).  Every record
- * is additionally handed to an optional frame callback so a host parser can run on the exact bytes
- * the reference's parser would see.
+ * below covers RS41 sequence number, serial, GPS position / velocity and GPS time (CRC-checked subframes as
+ * rs41.c:165-175 does) and the M10 / MRZ-N1 sequence counters; PTU/XDATA and the other sondes' physical
+ * values are not converted yet.  Every record is additionally handed to an optional frame callback so a
+ * host parser can run on the exact bytes the reference's parser would see.
  *
  * There is no CPU fallback: init() throws std::runtime_error when the CUDA path is unavailable.
  */
@@ -48,13 +48,63 @@ inline uint16_t crc16_ccitt_false(const uint8_t *p, size_t n)
 	return crc;
 }
 
-/* What the frame bytes establish without the telemetry parsers. */
+/* ---- WGS-84 ECEF -> geodetic (Bowring's one-step method) and ENU velocity, as SD/gps/ecef.c:6-57.
+ * Mixed float/double like the reference (double constants, float libm calls) so the results agree to
+ * rounding. */
+namespace wgs84 {
+constexpr double A = 6378137.0, F = 1 / 298.257223563, B = A * (1 - F);
+constexpr double E2 = (A * A - B * B) / (A * A), EP2 = (A * A - B * B) / (B * B);
+constexpr double PI = 3.14159265358979323846;
+}  // namespace wgs84
+
+inline bool ecef_to_lla(float *lat, float *lon, float *alt, float x, float y, float z)
+{
+	const float lambda = atan2f(y, x);
+	const float p = sqrtf(x * x + y * y);
+	const float theta = atan2f((float)(z * wgs84::A), (float)(p * wgs84::B));
+	const float st = sinf(theta), ct = cosf(theta);
+	if (x == 0 || y == 0 || z == 0) {
+		*lat = *lon = *alt = NAN;
+		return false;
+	}
+	const float phi = atan2f((float)(z + wgs84::EP2 * wgs84::B * (st * st * st)),
+	                         (float)(p - wgs84::E2 * wgs84::A * (ct * ct * ct)));
+	const float sp = sinf(phi);
+	const float n = (float)(wgs84::A / sqrtf((float)(1 - wgs84::E2 * sp * sp)));
+	*lat = (float)(phi * 180 / wgs84::PI);
+	*lon = (float)(lambda * 180 / wgs84::PI);
+	*alt = p / cosf(phi) - n;
+	return true;
+}
+
+inline void ecef_velocity(float *speed, float *heading, float *climb, float lat, float lon, float dx, float dy, float dz)
+{
+	lat = (float)(lat * (wgs84::PI / 180));
+	lon = (float)(lon * (wgs84::PI / 180));
+	if (dx == 0 && dy == 0 && dz == 0) {
+		*speed = *heading = *climb = 0;
+		return;
+	}
+	*climb = dx * cosf(lat) * cosf(lon) + dy * cosf(lat) * sinf(lon) + dz * sinf(lat);
+	const float vn = -dx * sinf(lat) * cosf(lon) - dy * sinf(lat) * sinf(lon) + dz * cosf(lat);
+	const float ve = -dx * sinf(lon) + dy * cosf(lon);
+	*speed = sqrtf(vn * vn + ve * ve);
+	*heading = (float)(atan2f(ve, vn) * 180 / wgs84::PI);
+	if (*heading < 0) *heading += 360;
+}
+
+inline int32_t le32(const uint8_t *p) { return (int32_t)((uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24); }
+inline int16_t le16(const uint8_t *p) { return (int16_t)(p[0] | p[1] << 8); }
+
+/* Frame record -> SondeData fragment.  RS41: the subframe walk of rs41.c:157-175 ({type, len, data[len],
+ * crc16 LE}; CRC-valid subframes are parsed even if RS failed) with the status (rs41.c:219-236), GPS position
+ * (rs41.c:249-266, parser.c:193-226, gps/ecef.c) and GPS time (rs41.c:267-273, gps/time.c:8-11) subframes.
+ * PTU and XDATA need the 816-byte calibration state. */
 inline void fragment_from_record(const sonde_frame_rec &r, SondeData *dst)
 {
 	memset(dst, 0, sizeof(*dst));
 	switch (r.type) {
 	case SONDE_RS41: {
-		/* subframe walk of rs41.c:157-175: {type, len, data[len], crc16 LE}; parsed even if RS failed */
 		const uint8_t *data = r.data + 57;
 		const int data_len = 263 + (r.data[56] == 0xF0 ? 198 : 0);
 		int off = 0;
@@ -62,11 +112,33 @@ inline void fragment_from_record(const sonde_frame_rec &r, SondeData *dst)
 		off += sf[1] + 4;
 		while (off < data_len && sf[1]) {
 			const uint16_t want = (uint16_t)(sf[2 + sf[1]] | sf[3 + sf[1]] << 8);
-			if (crc16_ccitt_false(sf + 2, sf[1]) == want && sf[0] == 0x79) {        /* RS41_SFTYPE_INFO */
-				dst->seq = sf[2] | sf[3] << 8;
-				memcpy(dst->serial, sf + 4, 8);
-				dst->serial[8] = 0;
-				dst->fields |= DATA_SEQ | DATA_SERIAL;
+			if (crc16_ccitt_false(sf + 2, sf[1]) == want) {
+				const uint8_t *d = sf + 2;
+				switch (sf[0]) {
+				case 0x79:                                       /* RS41_SFTYPE_INFO */
+					dst->seq = d[0] | d[1] << 8;
+					memcpy(dst->serial, d + 2, 8);
+					dst->serial[8] = 0;
+					dst->fields |= DATA_SEQ | DATA_SERIAL;
+					break;
+				case 0x7B: {                                     /* RS41_SFTYPE_GPSPOS: ECEF cm, cm/s */
+					const float x = (float)(le32(d) / 100.0), y = (float)(le32(d + 4) / 100.0), z = (float)(le32(d + 8) / 100.0);
+					const float dx = (float)(le16(d + 12) / 100.0), dy = (float)(le16(d + 14) / 100.0), dz = (float)(le16(d + 16) / 100.0);
+					dst->fields |= DATA_POS | DATA_SPEED;
+					ecef_to_lla(&dst->lat, &dst->lon, &dst->alt, x, y, z);
+					ecef_velocity(&dst->speed, &dst->heading, &dst->climb, dst->lat, dst->lon, dx, dy, dz);
+					break;
+				}
+				case 0x7C: {                                     /* RS41_SFTYPE_GPSINFO: GPS week + ms of week */
+					const uint16_t week = (uint16_t)(d[0] | d[1] << 8);
+					const uint32_t ms = (uint32_t)le32(d + 2);
+					dst->time = (time_t)(ms / 1000UL) + (86400UL * 7) * week + 315964800UL;
+					dst->fields |= DATA_TIME;
+					break;
+				}
+				default:
+					break;
+				}
 			}
 			sf = data + off;
 			off += sf[1] + 4;

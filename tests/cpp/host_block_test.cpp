@@ -65,15 +65,19 @@ int main(int argc, char **argv)
 	if (!d) { printf("NOGPU compat\n"); return 3; }
 	int parsed = 0, with_fields = 0, seq = -1;
 	std::string serial;
-	SondeData out;
+	SondeData out, last_pos;
+	memset(&last_pos, 0, sizeof(last_pos));
 	for (size_t pos = 0; pos < n; pos += chunk) {
 		const size_t len = n - pos < chunk ? n - pos : chunk;
 		while (rs41_decode(d, &out, fm.data() + pos, len) != PROCEED) {
 			parsed++;
 			if (out.fields) { with_fields++; seq = out.seq; serial = out.serial; }
+			if ((out.fields & (DATA_POS | DATA_TIME)) == (DATA_POS | DATA_TIME)) last_pos = out;
 		}
 	}
 	printf("COMPAT parsed=%d with_fields=%d seq=%d serial=%s\n", parsed, with_fields, seq, serial.c_str());
+	printf("TELEM fields=%d lat=%.6f lon=%.6f alt=%.3f speed=%.4f heading=%.4f climb=%.4f time=%lld\n", last_pos.fields,
+	       last_pos.lat, last_pos.lon, last_pos.alt, last_pos.speed, last_pos.heading, last_pos.climb, (long long)last_pos.time);
 	rs41_decoder_deinit(d);
 	return 0;
 }

@@ -62,6 +62,14 @@ def test_host_block_and_compat_api_on_gpu(tmp_path):
     chk = reflib.RefLib() if reflib.have_ref() else reflib.OracleLib()
     want = chk.frames_run(synth.RS41, fm, chunk)
     assert int(cmp_["parsed"]) == len(want)
+    tel = dict(kv.split("=") for kv in out["TELEM"].split())
+    # 2021-03-17 04:16:03 UTC, 37.81514 S 145.01633 E, 7738 m
+    assert abs(float(tel["lat"]) + 37.81514) < 1e-4 and abs(float(tel["lon"]) - 145.01633) < 1e-4
+    assert abs(float(tel["alt"]) - 7738) < 2 and int(tel["time"]) == 1615954563
     if reflib.have_ref():
         sd, _ = reflib.RefLib().decode_run(synth.RS41, fm, chunk)
-        assert int(cmp_["with_fields"]) == sum(1 for s in sd if s.fields & 3)
+        assert int(cmp_["with_fields"]) == sum(1 for s in sd if s.fields)
+        ref = [s for s in sd if (s.fields & 0x14) == 0x14][-1]      # DATA_POS | DATA_TIME
+        for k in ("lat", "lon", "alt", "speed", "heading", "climb"):
+            assert abs(float(tel[k]) - getattr(ref, k)) <= 1e-5 * max(1.0, abs(getattr(ref, k))), k
+        assert int(tel["time"]) == ref.time
