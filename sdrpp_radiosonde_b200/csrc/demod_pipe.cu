@@ -47,15 +47,17 @@ constexpr int CPT = G * T / NPWT;        /* channels per PW thread in S1 / S3 (o
  * to any PW warp on their scheduler.  Two placements, picked per kernel variant from measurements
  * (tools/stalls.py):
  *   layout 0 (timing lane is the critical stage: RS41, M10): TM alone on SMSP3
- *        SMSP0: 6 PW | SMSP1: 6 PW | SMSP2: A1, A2, 4 PW | SMSP3: TM (+ 4 warps that exit at once)
+ *        SMSP0: 6 PW | SMSP1: 6 PW | SMSP2: A1, A2, 4 PW | SMSP3: TM, LD (+ 3 warps that exit at once)
  *   layout 1 (AGC lanes are the critical stage: DFM, iMS-100, MRZ-N1): all three serial lanes on SMSP3
- *        SMSP0: 6 PW | SMSP1: 5 PW | SMSP2: 5 PW | SMSP3: TM, A1, A2                                */
+ *        SMSP0: 6 PW | SMSP1: 5 PW | SMSP2: 5 PW | SMSP3: TM, A1, A2, LD
+ * LD is the TMA producer warp: one lane issues the bulk copies of the input tiles (it exits at once when the
+ * input rows are not 16-byte aligned and the PW threads load their samples themselves). */
 template <int LAYOUT>
 struct roles;
 template <>
 struct roles<0> {
-	static constexpr int NWARPS = 23, W_TM = 3, W_A1 = 2, W_A2 = 6;
-	static __device__ __forceinline__ bool idle(int warp) { return (warp & 3) == 3 && warp != W_TM; }
+	static constexpr int NWARPS = 23, W_TM = 3, W_A1 = 2, W_A2 = 6, W_LD = 7;
+	static __device__ __forceinline__ bool idle(int warp) { return (warp & 3) == 3 && warp != W_TM && warp != W_LD; }
 	static __device__ __forceinline__ int pw_index(int warp)
 	{
 		const int q = warp >> 2, r = warp & 3;        /* ids 0,4,..,20 -> 0..5 ; 1,5,..,21 -> 6..11 ; 10,14,18,22 -> 12..15 */
@@ -64,8 +66,8 @@ struct roles<0> {
 };
 template <>
 struct roles<1> {
-	static constexpr int NWARPS = 21, W_TM = 3, W_A1 = 7, W_A2 = 11;
-	static __device__ __forceinline__ bool idle(int warp) { return (warp & 3) == 3 && warp > W_A2; }
+	static constexpr int NWARPS = 21, W_TM = 3, W_A1 = 7, W_A2 = 11, W_LD = 15;
+	static __device__ __forceinline__ bool idle(int warp) { return (warp & 3) == 3 && warp > W_A2 && warp != W_LD; }
 	static __device__ __forceinline__ int pw_index(int warp)
 	{
 		const int q = warp >> 2, r = warp & 3;        /* ids 0,4,..,20 -> 0..5 ; 1,5,..,17 -> 6..10 ; 2,6,..,18 -> 11..15 */
@@ -89,11 +91,14 @@ struct smem_t {
 	float v[NS2][G][RS];                 /* moving_avg before each sample's update   */
 	float a[NS2][G][AS];                 /* AGC output, [0,48) = previous tile tail  */
 	float y[NS2][P][G][RS];              /* FIR output per polyphase branch          */
+	float2 raw[2][G][T];                 /* TMA landing zone: raw IQ (or FM in .x-packed form) of two tiles */
 	float ph[G][RS];                     /* S1 scratch: phases, [g][0] = previous    */
 	float carry[2][G];                   /* last phase of the previous tile          */
 	float2 taps[P * SONDE_FIR_TAPS];     /* each tap duplicated for the packed fp32x2 FIR */
 	int   zflag[NX];                     /* tile contains exact-zero samples         */
 	unsigned long long negzero2;         /* (-0.0f, -0.0f), read at run time so that the packed product stays an FFMA2 */
+	unsigned long long rawfull[2], rawfree[2];   /* complete_tx barriers of the bulk copies / slot released by PW */
+	int chan[G];
 	unsigned long long xfull[NX], sfull[NS2], sfree[NS2], vfull[NS2], vfree[NS2], yfull[NS2], yfree[NS2];
 };
 
@@ -127,6 +132,17 @@ __device__ __forceinline__ void mbar_wait_t(unsigned long long *b, uint32_t pari
 	const long long t0 = clock64();
 	mbar_wait(b, parity);
 	acc += clock64() - t0;
+}
+/* TMA: one elected thread starts a bulk global->shared copy whose completion is signalled on an mbarrier
+ * (cp.async.bulk, SASS UBLKCP).  Addresses and size must be multiples of 16 bytes. */
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *b)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(s32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(s32(b)) : "memory");
 }
 /* all lanes of a warp finished their writes -> one arrival */
 __device__ __forceinline__ void warp_arrive(unsigned long long *b, int lane)
@@ -248,7 +264,7 @@ __device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS]
 	}
 }
 
-template <int P, int N, bool IQ, bool SOFT, int LAYOUT>
+template <int P, int N, bool IQ, bool SOFT, int LAYOUT, bool TMA>
 __global__ void __launch_bounds__(roles<LAYOUT>::NWARPS * 32, 1)
 demod_pipe_kernel(const demod_params p, const int group_base)
 {
@@ -257,7 +273,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 
 	using RL = roles<LAYOUT>;
 	constexpr int NTHREADS = RL::NWARPS * 32;
-	constexpr int W_A1 = RL::W_A1, W_A2 = RL::W_A2, W_TM = RL::W_TM;
+	constexpr int W_A1 = RL::W_A1, W_A2 = RL::W_A2, W_TM = RL::W_TM, W_LD = RL::W_LD;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int grp = group_base + blockIdx.x;
 	const sonde_modem &md = c_modem[p.group_type[grp]];
@@ -272,6 +288,8 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	/* ---- prologue ------------------------------------------------------------------------- */
 	if (tid == 0) {
 		sm.negzero2 = 0x8000000080000000ull;
+		mbar_init(&sm.rawfull[0], 1); mbar_init(&sm.rawfull[1], 1);
+		mbar_init(&sm.rawfree[0], NPW); mbar_init(&sm.rawfree[1], NPW);
 		for (int i = 0; i < NX; i++) { mbar_init(&sm.xfull[i], NPW); sm.zflag[i] = 0; }
 		for (int i = 0; i < NS2; i++) {
 			mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sfree[i], 1 + NPW);
@@ -287,9 +305,34 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 		sm.a[1][g][T + k] = (ch >= 0) ? p.st[ch].hist[k] : 0.0f;
 	}
 	if (tid < G) sm.carry[0][tid] = (chans[tid] >= 0) ? p.st[chans[tid]].disc_prev : 0.0f;
+	if (tid < G) sm.chan[tid] = chans[tid];
 	__syncthreads();
 
 	if (RL::idle(warp)) return;
+	if (warp == W_LD) {
+		/* =============================== LD: TMA producer ===================================
+		 * 8 bulk copies per tile (one 2 KB row segment per channel) into sm.raw, two tiles ahead. */
+		if (TMA && lane == 0) {
+			constexpr uint32_t ESZ = IQ ? 8u : 4u;
+			for (int tile = 0; tile < ntiles; tile++) {
+				const int slot = tile & 1;
+				if (tile >= 2) mbar_wait(&sm.rawfree[slot], ((tile >> 1) - 1) & 1);
+				const int n = min(T, L - tile * T);
+				const uint32_t bytes = (uint32_t)n * ESZ;
+				uint32_t total = 0;
+#pragma unroll
+				for (int g = 0; g < G; g++) total += (sm.chan[g] >= 0) ? bytes : 0u;
+				mbar_expect_tx(&sm.rawfull[slot], total);
+#pragma unroll
+				for (int g = 0; g < G; g++)
+					if (sm.chan[g] >= 0)
+						tma_load_1d(&sm.raw[slot][g][0],
+						            static_cast<const char *>(p.in) + ((size_t)sm.chan[g] * p.row_stride + (size_t)tile * T) * ESZ,
+						            bytes, &sm.rawfull[slot]);
+			}
+		}
+		return;
+	}
 	if (warp != W_A1 && warp != W_A2 && warp != W_TM) {
 		/* =============================== PW: S1 / S3 / S4 =================================== */
 		const int pw = RL::pw_index(warp);           /* 0..NPW-1                                     */
@@ -303,24 +346,42 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 		for (int c = 0; c < CPT; c++) ch_of[c] = chans[g0 + c];
 
 		const unsigned long long negzero2 = *reinterpret_cast<volatile unsigned long long *>(&sm.negzero2);
-		float2 q[CPT];                           /* prefetched raw input of the next S1 tile    */
+		/* Input staging.  When the rows are 16-byte aligned (p.use_tma, decided on the host) one elected thread
+		 * streams each tile with 8 bulk copies (one 2 KB row segment per channel) into sm.raw two tiles ahead
+		 * and the PW threads read their samples from shared memory; otherwise every thread prefetches its
+		 * own samples into registers one tile ahead with coalesced loads. */
+		constexpr bool tma = TMA;
+		float2 q[CPT];                           /* register prefetch (non-TMA path)             */
 		auto prefetch = [&](int tile) {
+			if (tma || tile >= ntiles) return;
 			const int i = tile * T + t;
 #pragma unroll
 			for (int c = 0; c < CPT; c++) {
 				q[c] = make_float2(0.0f, 0.0f);
-				if (tile < ntiles && i < L && ch_of[c] >= 0) {
+				if (i < L && ch_of[c] >= 0) {
 					if (IQ) q[c] = __ldg(static_cast<const float2 *>(p.in) + (size_t)ch_of[c] * p.row_stride + i);
 					else    q[c].x = __ldg(static_cast<const float *>(p.in) + (size_t)ch_of[c] * p.row_stride + i);
 				}
 			}
 		};
-		/* S1 of `tile` from the registers loaded by prefetch(tile); issues the loads of tile+1 */
+		/* S1 of `tile`; starts the loads of a later tile */
 		auto stage1 = [&](int tile) {
 			const int slot = tile % NX;
 			const int n = min(T, L - tile * T);
 			float cur[CPT];
 			if (pt == 0) sm.zflag[slot] = 0;
+			if (tma) {
+				mbar_wait_t(&sm.rawfull[tile & 1], (tile >> 1) & 1, wacc[1], prof_on);
+#pragma unroll
+				for (int c = 0; c < CPT; c++) {
+					q[c] = make_float2(0.0f, 0.0f);
+					if (t < n && ch_of[c] >= 0) {
+						if (IQ) q[c] = sm.raw[tile & 1][g0 + c][t];
+						else    q[c].x = reinterpret_cast<const float *>(&sm.raw[tile & 1][g0 + c][0])[t];
+					}
+				}
+				warp_arrive(&sm.rawfree[tile & 1], lane);      /* values are in registers: the slot may be refilled */
+			}
 #pragma unroll
 			for (int c = 0; c < CPT; c++) {
 				const int g = g0 + c;
@@ -333,7 +394,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 				}
 			}
 			if (IQ && pt < G) sm.ph[pt][0] = sm.carry[tile & 1][pt];
-			prefetch(tile + 1);
+			if (!tma) prefetch(tile + 1);
 			pw_barrier();
 			bool zero = false;
 #pragma unroll
@@ -636,26 +697,29 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	}
 }
 
-template <int P, int N, bool IQ, bool SOFT>
+template <int P, int N, bool IQ, bool SOFT, bool TMA>
 cudaError_t launch2(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
 	constexpr int LAYOUT = (N == 24) ? 1 : 0;
 	static bool attr_done = false;
 	if (!attr_done) {
-		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, N, IQ, SOFT, LAYOUT>,
+		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, N, IQ, SOFT, LAYOUT, TMA>,
 		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem_t<P>));
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
-	demod_pipe_kernel<P, N, IQ, SOFT, LAYOUT><<<n_groups, roles<LAYOUT>::NWARPS * 32, sizeof(smem_t<P>), stream>>>(*p, group_base);
+	demod_pipe_kernel<P, N, IQ, SOFT, LAYOUT, TMA><<<n_groups, roles<LAYOUT>::NWARPS * 32, sizeof(smem_t<P>), stream>>>(*p, group_base);
 	return cudaGetLastError();
 }
 
 template <int P, int N, bool IQ>
 cudaError_t launch(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
-	return p->soft ? launch2<P, N, IQ, true>(p, group_base, n_groups, stream)
-	               : launch2<P, N, IQ, false>(p, group_base, n_groups, stream);
+	if (p->use_tma)
+		return p->soft ? launch2<P, N, IQ, true, true>(p, group_base, n_groups, stream)
+		               : launch2<P, N, IQ, false, true>(p, group_base, n_groups, stream);
+	return p->soft ? launch2<P, N, IQ, true, false>(p, group_base, n_groups, stream)
+	               : launch2<P, N, IQ, false, false>(p, group_base, n_groups, stream);
 }
 
 }  // namespace

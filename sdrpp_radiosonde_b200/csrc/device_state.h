@@ -70,6 +70,7 @@ struct demod_params {
 	size_t        row_stride;     /* in samples                                       */
 	int32_t       len;            /* samples per channel this call                    */
 	int32_t       is_iq;
+	int32_t       use_tma;        /* rows 16-byte aligned: stage tiles with cp.async.bulk */
 	float         fm_gain;
 	int32_t       n_groups;
 	const int32_t *group_chan;    /* [n_groups][DEMOD_G] channel ids, -1 = empty      */

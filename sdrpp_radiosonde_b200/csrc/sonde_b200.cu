@@ -290,6 +290,12 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	dp.row_stride = row_stride;
 	dp.len = (int32_t)len;
 	dp.is_iq = is_iq;
+	{
+		/* bulk (TMA) copies need 16-byte aligned row segments: base, row pitch and the last tile's length */
+		const size_t esz = is_iq ? 8 : 4;
+		dp.use_tma = ((uintptr_t)d_in % 16 == 0) && ((row_stride * esz) % 16 == 0) && ((len * esz) % 16 == 0) &&
+		             !(h->cfg.reserved & 2);
+	}
 	dp.fm_gain = h->cfg.fm_gain;
 	dp.n_groups = h->n_groups;
 	dp.group_chan = h->d_group_chan;

@@ -7,7 +7,7 @@ stype = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 C, L = 256, 48000
 iq = bench.gen_batch(stype, 0, C, L, 16)
 d = torch.from_numpy(iq).cuda()
-dec = capi.BatchDecoder(np.full(C, stype, np.int32), L)
+dec = capi.BatchDecoder(np.full(C, stype, np.int32), L, no_tma=(len(sys.argv) > 2 and sys.argv[2] == 'notma'))
 dec.process_iq_device(d.data_ptr(), L); dec.sync()
 dec.debug_stalls()
 dec.process_iq_device(d.data_ptr(), L); dec.sync()
