@@ -25,6 +25,8 @@ extern "C" {
 /* same signatures as the ref_* entry points of oracle/ref_harness.c */
 int  orc_frames_run(int type, int samplerate, const float *fm, size_t n, size_t chunk,
                     sonde_frame_rec *recs, int max_recs);
+int  orc_frames_run_ragged(int type, int samplerate, const float *fm, size_t n, const size_t *chunks, int n_chunks,
+                           sonde_frame_rec *recs, int max_recs);
 long orc_demod_bits(int type, int samplerate, const float *fm, size_t n, size_t chunk,
                     uint8_t *bits, size_t bits_cap_bytes);
 long orc_gfsk_soft(int samplerate, int baud, const float *fm, size_t n, size_t chunk,

@@ -208,6 +208,24 @@ def _frames_run_iq(self, stype, iq, chunk, samplerate=48000, gain=0.0, max_recs=
 OracleLib.frames_run_iq = _frames_run_iq
 
 
+def _frames_run_ragged(self, stype, fm, chunks, samplerate=48000, max_recs=None):
+    fm = np.ascontiguousarray(fm, dtype=np.float32)
+    if max_recs is None:
+        max_recs = fm.size // 80 + 64
+    recs = (FrameRec * max_recs)()
+    arr = (ctypes.c_size_t * len(chunks))(*chunks)
+    fn = self.lib.orc_frames_run_ragged
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_size_t,
+                   ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.POINTER(FrameRec), ctypes.c_int]
+    n = fn(stype, samplerate, _fptr(fm), fm.size, arr, len(chunks), recs, max_recs)
+    assert 0 <= n <= max_recs, n
+    return [recs[i] for i in range(n)]
+
+
+OracleLib.frames_run_ragged = _frames_run_ragged
+
+
 def have_ref():
     return os.path.exists(REF_SO)
 

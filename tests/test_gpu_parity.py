@@ -1,5 +1,7 @@
 """-m gpu: the CUDA path (through the C ABI) against the UNMODIFIED reference (oracle/_ref) and the
 C restatement (oracle/), on the same seeded synthetic signals.  Bit-exact on everything."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -214,3 +216,52 @@ def test_pipelined_fetch_equals_sequential():
     for c, t in enumerate(types):
         rb = (synth.MODEMS[t].frame_bits + 7) // 8
         assert [rec_key(g, rb) for g in frames[c]] == [rec_key(g, rb) for g in seq["frames"][c]]
+
+
+def test_ragged_and_tiny_buffers():
+    """Buffers of 1, 2, 7, 48, 49, 255, 256, 257 ... samples in an irregular sequence (an SDR++ stream does not
+    deliver fixed sizes): every call is one reference buffer, `interm` restarts at each (gfsk.c:73)."""
+    if not reflib.have_oracle():
+        pytest.skip("oracle not built")
+    from sdrpp_radiosonde_b200 import capi
+    orc = reflib.OracleLib()
+    seq = [1, 2, 7, 48, 49, 255, 256, 257, 1000, 3, 4097, 511, 1, 1, 12000, 5, 769]
+    types = [synth.RS41, synth.M10, synth.DFM09, synth.C50, synth.IMET4]
+    n = 48000 * 2
+    batch = np.stack([synth.make_fm(synth.default_spec(t, 20 + c), n) for c, t in enumerate(types)])
+    dec = capi.BatchDecoder(types, max(seq))
+    frames = [[] for _ in types]
+    pos = ci = 0
+    while pos < n:
+        ln = min(seq[ci % len(seq)], n - pos)
+        dec.process_fm(np.ascontiguousarray(batch[:, pos:pos + ln]))
+        recs, counts = dec.fetch()
+        for c in range(len(types)):
+            frames[c].extend(recs[c, :counts[c]].copy())
+        pos += ln
+        ci += 1
+    dec.close()
+    for c, t in enumerate(types):
+        want = orc.frames_run_ragged(t, batch[c], seq)
+        rb = (synth.MODEMS[t].frame_bits + 7) // 8
+        assert [rec_key(g, rb) for g in frames[c]] == [rec_key(w, rb) for w in want], (c, t)
+        assert sum(int(w.ok) for w in want) > 0
+
+
+def test_argument_errors_on_device():
+    from sdrpp_radiosonde_b200 import capi
+    dec = capi.BatchDecoder([synth.RS41, synth.DFM09], 1024)
+    with pytest.raises(capi.SondeError) as e:
+        dec.process_fm(np.zeros((2, 2048), np.float32))
+    assert e.value.code == capi.ERR_TOOLONG
+    assert dec.lib.sonde_b200_process_fm(dec.h, None, 16) == capi.ERR_ARG
+    assert dec.lib.sonde_b200_process_fm(dec.h, np.zeros(4, np.float32).ctypes.data, 0) == capi.ERR_ARG
+    frames, ok = np.zeros(2, np.int32), np.zeros(2, np.int32)
+    assert dec.lib.sonde_b200_fetch_counts(dec.h, frames.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                           ok.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))) == capi.ERR_STATE
+    # all-zero input (a muted channel): nothing decodes, nothing breaks, AGC state untouched (agc.c:23)
+    dec.process_fm(np.zeros((2, 1024), np.float32))
+    recs, counts = dec.fetch()
+    st = dec.fetch_state()
+    assert st[0, 0] == 0.0 and st[0, 1] == 5.0
+    dec.close()
