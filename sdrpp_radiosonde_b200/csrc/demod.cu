@@ -55,8 +55,14 @@ struct smem_t {
 	float y[SONDE_MAX_PHASES][G][RS];   /* S4 out: FIR output per polyphase branch       */
 	float ph[G][RS];               /* S1 scratch: phases, ph[g][0] = previous sample      */
 	float taps[SONDE_MAX_PHASES * SONDE_FIR_TAPS];
-	float2 mhist[G][SONDE_AFSK_MAXLEN];   /* AFSK boxcar histories (afsk.c:117-124) */
-	float2 shist[G][SONDE_AFSK_MAXLEN];
+};
+
+/* extra shared memory of the AFSK variant */
+constexpr int OS2 = SONDE_AFSK_MAXLEN + T + 2;   /* row stride (float2) of the mixer outputs: `len` history + tile */
+struct afsk_smem_t {
+	float  pn[2][G][RS];           /* NCO phase used for each sample, [0] mark, [1] space        */
+	float2 om[G][OS2], os[G][OS2]; /* mixer outputs; [0, len) = the previous `len` outputs       */
+	float2 msum[G][RS], ssum[G][RS];   /* running boxcar sums after each sample                  */
 };
 
 /* ---- S2: the two AGC recurrences for one channel over n samples ---------------------- */
@@ -81,60 +87,29 @@ __device__ __forceinline__ void agc_chains(const float *x, float *s, float *v, i
 	}
 }
 
-/* ---- AFSK front end for one channel over n samples (afsk.c:104-141) ---------------------------
+/* ---- AFSK front end (afsk.c:104-141) -------------------------------------------------------
  * s = agc(x) / len * 2 ; mix with the mark and space NCOs ; running boxcar sums over one symbol ;
- * filter input = |mark_sum| - |space_sum|.  The reference calls glibc cexpf/cabsf/fmod per sample:
- *   - fmod(p + f, 2 pi) in double and cabsf == (float)sqrt((double)re*re + (double)im*im) are
- *     reproduced exactly (both are exactly-rounded double operations);
+ * filter input = |mark_sum| - |space_sum|.  Only three things are serial in time: the AGC recurrences
+ * (shared with GFSK), the two NCO phases p = fmod(p + f, 2 pi) — data independent — and the running
+ * sums sum += out[n] - out[n - len].  They run on a few lanes; the expensive parts (sincos, sqrt) are
+ * evaluated for all samples of the tile in parallel.
+ * The reference calls glibc cexpf/cabsf/fmod per sample:
+ *   - fmod(p + f, 2 pi) in double (p + f < 4 pi, so it is one exact conditional subtraction) and
+ *     cabsf == (float)sqrt((double)re*re + (double)im*im) are reproduced exactly;
  *   - sin/cos are evaluated in double and rounded to float, which equals glibc's sinf/cosf except
  *     where glibc's own result is not the correctly rounded one (< 1 ulp apart).  The boxcar sums
  *     integrate such differences, so AFSK soft symbols are NOT claimed bit-exact;
  *     frame bytes are what tests/test_gpu_parity.py checks for the two AFSK sondes. */
-struct afsk_regs {
-	float p_mark, p_space, mre, mim, sre, sim;
-	int idx;
-};
-
-__device__ __forceinline__ float agc_full(float x, float &bias, float &avg)        /* agc.c:19-34 */
-{
-	if (x == 0.0f) return 0.0f;
-	const float s = fsub(x, bias);
-	bias = fadd(fmul(bias, fsub(1.0f, 0.01f)), fmul(s, 0.01f));
-	const float gain = fdiv(5.0f, avg);
-	avg = fadd(fmul(avg, fsub(1.0f, 0.001f)), fmul(fabsf(s), 0.001f));
-	return fmul(s, gain);
-}
-
 __device__ __forceinline__ float cabs_exact(float re, float im)
 {
 	return (float)sqrt(__dadd_rn(__dmul_rn((double)re, (double)re), __dmul_rn((double)im, (double)im)));
 }
 
-__device__ void afsk_chain(const float *x, float *out, int n, float &bias, float &avg, afsk_regs &a,
-                           float2 *mh, float2 *sh, const int len, const float f_mark, const float f_space)
+__device__ __forceinline__ float nco_step(float p, float f)
 {
 	const double two_pi = 2.0 * 3.14159265358979323846;
-	const float flen = (float)len;
-	for (int i = 0; i < n; i++) {
-		const float s = fmul(fdiv(agc_full(x[i], bias, avg), flen), 2.0f);
-		double sn, cs;
-		sincos((double)a.p_mark, &sn, &cs);
-		float2 o = make_float2(fmul(s, (float)cs), fmul(s, -(float)sn));
-		float2 h = mh[a.idx];
-		a.mre = fadd(a.mre, fsub(o.x, h.x));
-		a.mim = fadd(a.mim, fsub(o.y, h.y));
-		mh[a.idx] = o;
-		sincos((double)a.p_space, &sn, &cs);
-		o = make_float2(fmul(s, (float)cs), fmul(s, -(float)sn));
-		h = sh[a.idx];
-		a.sre = fadd(a.sre, fsub(o.x, h.x));
-		a.sim = fadd(a.sim, fsub(o.y, h.y));
-		sh[a.idx] = o;
-		out[i] = fsub(cabs_exact(a.mre, a.mim), cabs_exact(a.sre, a.sim));
-		a.idx = (a.idx + 1) % len;
-		a.p_mark = (float)fmod((double)fadd(a.p_mark, f_mark), two_pi);
-		a.p_space = (float)fmod((double)fadd(a.p_space, f_space), two_pi);
-	}
+	const double x = (double)fadd(p, f);
+	return (float)fmod(x, two_pi);
 }
 
 /* ---- S5: Gardner loop + slicer for one channel over n samples ------------------------- */
@@ -260,19 +235,27 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 		if (p.soft) my_soft = p.soft + (size_t)my_ch * p.soft_stride;
 		sm.ph[tid][0] = st.disc_prev;
 	}
-	afsk_regs ar = {};
+	/* AFSK: dynamic shared memory continues after smem_t */
+	afsk_smem_t &am = *reinterpret_cast<afsk_smem_t *>(smem_raw + ((sizeof(smem_t) + 15) & ~(size_t)15));
+	const int blen = AFSK ? md.boxcar_len : 1;
+	float nco_p = 0.0f, box_sum = 0.0f;        /* lane state: NCO phase (warp 1, lane = 2g+m) / running sum (warp 2, lane = 4g+comp) */
+	const int warp_id = tid >> 5, lane_id = tid & 31;
 	if (AFSK) {
-		if (my_ch >= 0) {
-			const afsk_state &as = p.ast[my_ch];
-			ar.p_mark = as.p_mark; ar.p_space = as.p_space;
-			ar.mre = as.mark_re; ar.mim = as.mark_im; ar.sre = as.space_re; ar.sim = as.space_im;
-			ar.idx = as.idx;
+		if (warp_id == 1 && lane_id < 2 * G && chans[lane_id >> 1] >= 0) {
+			const afsk_state &as = p.ast[chans[lane_id >> 1]];
+			nco_p = (lane_id & 1) ? as.p_space : as.p_mark;
 		}
-		for (int i = tid; i < G * SONDE_AFSK_MAXLEN; i += NT) {
-			const int g = i / SONDE_AFSK_MAXLEN, k = i % SONDE_AFSK_MAXLEN;
+		if (warp_id == 2 && chans[lane_id >> 2] >= 0) {
+			const afsk_state &as = p.ast[chans[lane_id >> 2]];
+			const int comp = lane_id & 3;
+			box_sum = comp == 0 ? as.mark_re : comp == 1 ? as.mark_im : comp == 2 ? as.space_re : as.space_im;
+		}
+		/* the last `len` mixer outputs, oldest first */
+		for (int i = tid; i < G * blen; i += NT) {
+			const int g = i / blen, k = i % blen;
 			const int ch = chans[g];
-			sm.mhist[g][k] = (ch >= 0) ? make_float2(p.ast[ch].mark_hist[2 * k], p.ast[ch].mark_hist[2 * k + 1]) : make_float2(0, 0);
-			sm.shist[g][k] = (ch >= 0) ? make_float2(p.ast[ch].space_hist[2 * k], p.ast[ch].space_hist[2 * k + 1]) : make_float2(0, 0);
+			am.om[g][k] = (ch >= 0) ? make_float2(p.ast[ch].mark_hist[2 * k], p.ast[ch].mark_hist[2 * k + 1]) : make_float2(0, 0);
+			am.os[g][k] = (ch >= 0) ? make_float2(p.ast[ch].space_hist[2 * k], p.ast[ch].space_hist[2 * k + 1]) : make_float2(0, 0);
 		}
 	}
 	/* FIR history */
@@ -333,11 +316,76 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 		}
 
 		if (AFSK) {
-			/* ---- S2'/S3': AGC + mixers + boxcar, serial per channel ------------------------ */
-			if (my_ch >= 0)
-				afsk_chain(sm.x[tid], &sm.a[tid][SONDE_FIR_HIST], n, bias, avg, ar, sm.mhist[tid], sm.shist[tid],
-				           md.boxcar_len, md.f_mark, md.f_space);
-			for (int i = tid; i < G * (T - n); i += NT) sm.a[i / (T - n)][SONDE_FIR_HIST + n + i % (T - n)] = 0.0f;
+			/* ---- serial: AGC recurrences (warp 0) and the two NCOs per channel (warp 1) -------- */
+			if (my_ch >= 0) {
+				if (any_zero) agc_chains<true>(sm.x[tid], sm.s[tid], sm.v[tid], n, bias, avg);
+				else          agc_chains<false>(sm.x[tid], sm.s[tid], sm.v[tid], n, bias, avg);
+			}
+			if (warp_id == 1 && lane_id < 2 * G) {
+				const int g = lane_id >> 1, m = lane_id & 1;
+				const float f = m ? md.f_space : md.f_mark;
+				for (int i = 0; i < n; i++) {
+					am.pn[m][g][i] = nco_p;
+					nco_p = nco_step(nco_p, f);
+				}
+			}
+			__syncthreads();
+			/* ---- parallel: gain, /len*2, mixers --------------------------------------------- */
+			const float flen = (float)blen;
+#pragma unroll
+			for (int k = 0; k < G * T / NT; k++) {
+				const int idx = tid + k * NT;
+				const int g = idx / T, i = idx % T;
+				float2 m2 = make_float2(0.0f, 0.0f), s2 = m2;
+				if (i < n && chans[g] >= 0) {
+					float o = 0.0f;
+					if (!(any_zero && sm.x[g][i] == 0.0f)) o = fmul(sm.s[g][i], fdiv(5.0f, sm.v[g][i]));
+					const float sv = fmul(fdiv(o, flen), 2.0f);
+					double sn, cs;
+					sincos((double)am.pn[0][g][i], &sn, &cs);
+					m2 = make_float2(fmul(sv, (float)cs), fmul(sv, -(float)sn));
+					sincos((double)am.pn[1][g][i], &sn, &cs);
+					s2 = make_float2(fmul(sv, (float)cs), fmul(sv, -(float)sn));
+				}
+				am.om[g][blen + i] = m2;
+				am.os[g][blen + i] = s2;
+			}
+			__syncthreads();
+			/* ---- serial: running sums, one lane per (channel, component) (warp 2) -------------- */
+			if (warp_id == 2) {
+				const int g = lane_id >> 2, comp = lane_id & 3;
+				const float *o = reinterpret_cast<const float *>(comp < 2 ? &am.om[g][0] : &am.os[g][0]) + (comp & 1);
+				float *dst = reinterpret_cast<float *>(comp < 2 ? &am.msum[g][0] : &am.ssum[g][0]) + (comp & 1);
+				for (int i = 0; i < n; i++) {
+					box_sum = fadd(box_sum, fsub(o[2 * (blen + i)], o[2 * i]));
+					dst[2 * i] = box_sum;
+				}
+			}
+			__syncthreads();
+			/* ---- parallel: |mark| - |space| -> filter input; slide the mixer history ----------- */
+#pragma unroll
+			for (int k = 0; k < G * T / NT; k++) {
+				const int idx = tid + k * NT;
+				const int g = idx / T, i = idx % T;
+				float o = 0.0f;
+				if (i < n && chans[g] >= 0)
+					o = fsub(cabs_exact(am.msum[g][i].x, am.msum[g][i].y), cabs_exact(am.ssum[g][i].x, am.ssum[g][i].y));
+				sm.a[g][SONDE_FIR_HIST + i] = o;
+			}
+			{
+				float2 hm[2], hs[2];
+#pragma unroll
+				for (int k = 0; k < 2; k++) {
+					const int idx = tid + k * NT;
+					if (idx < G * blen) { hm[k] = am.om[idx / blen][n + idx % blen]; hs[k] = am.os[idx / blen][n + idx % blen]; }
+				}
+				__syncthreads();
+#pragma unroll
+				for (int k = 0; k < 2; k++) {
+					const int idx = tid + k * NT;
+					if (idx < G * blen) { am.om[idx / blen][idx % blen] = hm[k]; am.os[idx / blen][idx % blen] = hs[k]; }
+				}
+			}
 			__syncthreads();
 		} else {
 		/* ---- S2: AGC recurrences ------------------------------------------------------ */
@@ -400,19 +448,21 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 		if (ch >= 0) p.st[ch].hist[k] = sm.a[g][k];
 	}
 	if (AFSK) {
-		if (my_ch >= 0) {
-			afsk_state &as = p.ast[my_ch];
-			as.p_mark = ar.p_mark; as.p_space = ar.p_space;
-			as.mark_re = ar.mre; as.mark_im = ar.mim; as.space_re = ar.sre; as.space_im = ar.sim;
-			as.idx = ar.idx;
+		if (warp_id == 1 && lane_id < 2 * G && chans[lane_id >> 1] >= 0) {
+			afsk_state &as = p.ast[chans[lane_id >> 1]];
+			if (lane_id & 1) as.p_space = nco_p; else as.p_mark = nco_p;
 		}
-		__syncthreads();
-		for (int i = tid; i < G * SONDE_AFSK_MAXLEN; i += NT) {
-			const int g = i / SONDE_AFSK_MAXLEN, k = i % SONDE_AFSK_MAXLEN;
+		if (warp_id == 2 && chans[lane_id >> 2] >= 0) {
+			afsk_state &as = p.ast[chans[lane_id >> 2]];
+			const int comp = lane_id & 3;
+			(comp == 0 ? as.mark_re : comp == 1 ? as.mark_im : comp == 2 ? as.space_re : as.space_im) = box_sum;
+		}
+		for (int i = tid; i < G * blen; i += NT) {
+			const int g = i / blen, k = i % blen;
 			const int ch = chans[g];
 			if (ch >= 0) {
-				p.ast[ch].mark_hist[2 * k] = sm.mhist[g][k].x; p.ast[ch].mark_hist[2 * k + 1] = sm.mhist[g][k].y;
-				p.ast[ch].space_hist[2 * k] = sm.shist[g][k].x; p.ast[ch].space_hist[2 * k + 1] = sm.shist[g][k].y;
+				p.ast[ch].mark_hist[2 * k] = am.om[g][k].x; p.ast[ch].mark_hist[2 * k + 1] = am.om[g][k].y;
+				p.ast[ch].space_hist[2 * k] = am.os[g][k].x; p.ast[ch].space_hist[2 * k + 1] = am.os[g][k].y;
 			}
 		}
 	}
@@ -424,17 +474,23 @@ extern "C" size_t sonde_demod_smem_bytes(void) { return sizeof(smem_t); }
 
 /* Launches the phase-by-phase demodulator over groups [group_base, group_base + n_groups) that
  * share the polyphase count `phases`. */
+template <bool AFSK>
+static constexpr size_t legacy_smem_bytes()
+{
+	return ((sizeof(smem_t) + 15) & ~(size_t)15) + (AFSK ? sizeof(afsk_smem_t) : 0);
+}
+
 template <int P, bool AFSK>
 static cudaError_t launch_legacy(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
 	static bool attr_done = false;
 	if (!attr_done) {
 		cudaError_t e = cudaFuncSetAttribute(demod_gfsk_kernel<P, AFSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                                     (int)sizeof(smem_t));
+		                                     (int)legacy_smem_bytes<AFSK>());
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
-	demod_gfsk_kernel<P, AFSK><<<n_groups, NT, sizeof(smem_t), stream>>>(*p, group_base);
+	demod_gfsk_kernel<P, AFSK><<<n_groups, NT, legacy_smem_bytes<AFSK>(), stream>>>(*p, group_base);
 	return cudaGetLastError();
 }
 

@@ -53,6 +53,8 @@ struct sonde_b200 {
 	int32_t *d_counts[2] = {nullptr, nullptr};
 	cudaStream_t cstream = nullptr, dstream = nullptr;        /* H2D copies, D2H fetches */
 	cudaStream_t fstream = nullptr;                          /* framer kernels: frame(i) overlaps demod(i+1) */
+	cudaStream_t vstream[4] = {nullptr, nullptr, nullptr, nullptr};   /* one per demod kernel variant: they run concurrently */
+	cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev_demod[2] = {nullptr, nullptr}, evf[2] = {nullptr, nullptr};
 	uint64_t *d_nbits[2] = {nullptr, nullptr};
 	cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -155,6 +157,11 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	if (cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->dstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->fstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	for (int v = 0; v < 4; v++)
+		if (cudaStreamCreateWithFlags(&h->vstream[v], cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&h->ev_join[v], cudaEventDisableTiming) != cudaSuccess)
+			return bail(SONDE_ERR_CUDA);
 	for (int b = 0; b < 2; b++)
 		if (cudaEventCreateWithFlags(&h->ev_demod[b], cudaEventDisableTiming) != cudaSuccess ||
 		    cudaEventCreate(&h->evf[b]) != cudaSuccess)
@@ -269,6 +276,11 @@ void sonde_b200_destroy(sonde_b200 *h)
 	if (h->cstream) cudaStreamDestroy(h->cstream);
 	if (h->dstream) cudaStreamDestroy(h->dstream);
 	if (h->fstream) cudaStreamDestroy(h->fstream);
+	if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+	for (int v = 0; v < 4; v++) {
+		if (h->vstream[v]) cudaStreamDestroy(h->vstream[v]);
+		if (h->ev_join[v]) cudaEventDestroy(h->ev_join[v]);
+	}
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	for (auto &e : h->ev)
 		if (e) cudaEventDestroy(e);
@@ -314,19 +326,27 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	if (h->n_issued >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_done[par], 0));
 	CK(cudaEventRecord(h->ev[0], h->stream));
 	/* production kernel: the warp-specialised pipeline; reserved bit 0 selects the phase-by-phase
-	 * kernel of demod.cu (kept as an independent cross-check for the tests) */
+	 * kernel of demod.cu (kept as an independent cross-check for the tests).  A batch with several kernel
+	 * variants (sonde mixes) forks them onto their own streams so that they share the GPU. */
+	int n_variants = 0;
+	for (int v = 0; v < 4; v++) n_variants += h->groups_v[v] > 0;
+	const bool fork = n_variants > 1;
+	if (fork) CK(cudaEventRecord(h->ev_fork, h->stream));
 	int base = 0;
-	for (int v = 0; v < 3; v++) {
+	for (int v = 0; v < 4; v++) {
 		if (h->groups_v[v]) {
-			if (h->cfg.reserved & 1) CK(sonde_launch_demod_gfsk(&dp, base, h->groups_v[v], v == 2 ? 2 : 1, h->stream));
-			else                     CK(sonde_launch_demod_pipe(&dp, base, h->groups_v[v], v, h->stream));
+			cudaStream_t st = fork ? h->vstream[v] : h->stream;
+			if (fork) CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+			if (v == 3)                    CK(sonde_launch_demod_afsk(&dp, base, h->groups_v[v], st));
+			else if (h->cfg.reserved & 1)  CK(sonde_launch_demod_gfsk(&dp, base, h->groups_v[v], v == 2 ? 2 : 1, st));
+			else                           CK(sonde_launch_demod_pipe(&dp, base, h->groups_v[v], v, st));
 			h->launches++;
+			if (fork) {
+				CK(cudaEventRecord(h->ev_join[v], st));
+				CK(cudaStreamWaitEvent(h->stream, h->ev_join[v], 0));
+			}
 		}
 		base += h->groups_v[v];
-	}
-	if (h->groups_v[3]) {
-		CK(sonde_launch_demod_afsk(&dp, base, h->groups_v[3], h->stream));
-		h->launches++;
 	}
 	CK(cudaEventRecord(h->ev[1], h->stream));
 	CK(cudaEventRecord(h->ev_demod[par], h->stream));

@@ -1,0 +1,44 @@
+"""Time an arbitrary channel mix (BASELINE configs 3-5 shapes) with inputs resident in HBM.
+
+    python tools/run_config.py <config: 2|3|4|5> [channels]
+Base signals (64 per type) are generated with numpy and replicated with per-channel noise on the GPU.
+"""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, '.'); sys.path.insert(0, '..')
+from sdrpp_radiosonde_b200 import capi, synth
+import bench
+
+cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+C = int(sys.argv[2]) if len(sys.argv) > 2 else {2: 1024, 3: 2048, 4: 1024, 5: 1024}[cfg]
+L, NCH = 48000, 4
+mix = {2: [0], 3: [1, 2], 4: [3], 5: [0, 1, 2, 3, 4, 5, 6]}[cfg]
+types = np.array([mix[c % len(mix)] for c in range(C)], dtype=np.int32)
+NB = 16
+base = {t: torch.from_numpy(bench.gen_batch(t, 1000 * t, NB, L * NCH, 16)).cuda() for t in mix}
+g = torch.Generator(device="cuda"); g.manual_seed(1)
+iq = torch.empty((NCH, C, L), dtype=torch.complex64, device="cuda")
+for c in range(C):
+    row = base[int(types[c])][c % NB]
+    iq[:, c, :] = row.view(NCH, L)
+iq += 0.02 * torch.view_as_complex(torch.randn((NCH, C, L, 2), device="cuda", generator=g))
+dec = capi.BatchDecoder(types, L)
+for i in range(3):
+    dec.process_iq_device(iq[i % NCH].data_ptr(), L)
+dec.sync()
+f0, k0, _ = dec.fetch_totals()
+ext = torch.cuda.ExternalStream(dec.stream)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+steps = 12
+with torch.cuda.stream(ext):
+    e0.record()
+for i in range(steps):
+    dec.process_iq_device(iq[(3 + i) % NCH].data_ptr(), L)
+dec.join()
+with torch.cuda.stream(ext):
+    e1.record()
+dec.sync()
+ms = e0.elapsed_time(e1) / steps
+f1, k1, _ = dec.fetch_totals()
+print(f"config {cfg}: {C} channels, types {mix}: {ms:.3f} ms/step, {C*L/ms/1e3:.0f} MS/s, "
+      f"frames/s {int((f1-f0).sum())/(ms*steps)*1e3:.0f}, ok/s {int((k1-k0).sum())/(ms*steps)*1e3:.0f}, kernel ms {dec.last_kernel_ms()}")
