@@ -27,6 +27,7 @@
 
 #include "device_state.h"
 #include "strict_math.cuh"
+#include "timing_round.cuh"
 
 static __constant__ sonde_modem c_modem[SONDE_NTYPES_];
 
@@ -107,70 +108,10 @@ __device__ __forceinline__ float cabs_exact(float re, float im)
 
 __device__ __forceinline__ float nco_step(float p, float f)
 {
+	/* fmod(x, 2 pi) for 0 <= x < 4 pi is x or x - 2 pi, and that subtraction is exact in double (Sterbenz) */
 	const double two_pi = 2.0 * 3.14159265358979323846;
 	const double x = (double)fadd(p, f);
-	return (float)fmod(x, two_pi);
-}
-
-/* ---- S5: Gardner loop + slicer for one channel over n samples ------------------------- */
-struct timing_regs {
-	float prev, phase, freq, interm;
-	int   state;
-	uint32_t acc;
-	int   cnt;
-	uint64_t nbits;
-	int   nsoft;
-};
-
-__device__ __forceinline__ void emit_bit(timing_regs &t, float sym, uint8_t *ring, uint32_t ring_mask,
-                                         float *soft, int soft_cap)
-{
-	t.acc = (t.acc << 1) | (sym > 0.0f ? 1u : 0u);            /* gfsk.c:107 */
-	t.cnt++;
-	if (soft && t.nsoft < soft_cap) soft[t.nsoft] = sym;
-	t.nsoft++;
-	if (t.cnt == 8) {
-		ring[(uint32_t)(t.nbits >> 3) & ring_mask] = (uint8_t)t.acc;
-		t.acc = 0;
-		t.cnt = 0;
-	}
-	t.nbits++;
-}
-
-template <int P>
-__device__ __forceinline__ void timing_run(const smem_t &sm, int g, int n, timing_regs &t,
-                                           float center, float alpha, float beta, float max_fdev,
-                                           uint8_t *ring, uint32_t ring_mask, float *soft, int soft_cap)
-{
-	for (int i = 0; i < n; i++) {
-#pragma unroll
-		for (int ph = 0; ph < P; ph++) {
-			t.phase = fadd(t.phase, t.freq);                     /* timing.c:32 */
-			if (t.phase >= (float)t.state) {                     /* timing.c:35 */
-				/* filter_get(phase) uses polyphase branch P-1-phase (filter.c:54) */
-				const float yv = sm.y[P - 1 - ph][g][i];
-				if (t.state == 1) {
-					t.interm = yv;
-					t.state = 2;
-				} else {
-					/* retime(): timing.c:45-76 */
-					const float err = (fmul(yv, t.prev) < 0.0f) ? fmul(fsub(yv, t.prev), t.interm) : 0.0f;
-					t.prev = yv;
-					float fd = fsub(t.freq, center);
-					const float ea = fmul(err, alpha);
-					const float lo = (2.0f < ea) ? 2.0f : ea;
-					const float cl = (-2.0f > lo) ? -2.0f : lo;
-					t.phase = fsub(t.phase, fsub(2.0f, cl));
-					fd = fadd(fd, fmul(err, beta));
-					const float fl = (max_fdev < fd) ? max_fdev : fd;
-					fd = (-max_fdev > fl) ? -max_fdev : fl;
-					t.freq = fadd(center, fd);
-					t.state = 1;
-					emit_bit(t, yv, ring, ring_mask, soft, soft_cap);
-				}
-			}
-		}
-	}
+	return (x >= 0.0 && x < 2.0 * two_pi) ? (float)(x >= two_pi ? __dsub_rn(x, two_pi) : x) : (float)fmod(x, two_pi);
 }
 
 /* ---- S4: FIR at R consecutive positions, reference summation order -------------------- */
@@ -221,16 +162,21 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 	const bool serial_lane = tid < G;
 	const int my_ch = serial_lane ? chans[tid] : -1;
 	float bias = 0, avg = 0;
-	timing_regs tr = {};
+	tm_regs tr = {};
+	uint64_t nbits0 = 0;
+	float rf = 1.0f;
+	long long n_rounds = 0, n_slow = 0;
+	constexpr int NTM = (P == 2) ? 12 : 24;
 	const float center = md.freq0, alpha = md.alpha, beta = md.beta, max_fdev = md.max_fdev;
 	uint8_t *my_ring = nullptr;
 	float *my_soft = nullptr;
 	if (my_ch >= 0) {
 		const demod_state &st = p.st[my_ch];
 		bias = st.agc_bias; avg = st.agc_avg;
-		tr.prev = st.t_prev; tr.phase = st.t_phase; tr.freq = st.t_freq; tr.state = st.t_state;
+		tr.prev = st.t_prev; tr.phase = st.t_phase; tr.freq = st.t_freq; tr.target = (float)st.t_state;
 		tr.interm = 0.0f;                                 /* gfsk.c:73 */
-		tr.acc = st.bit_acc; tr.cnt = st.bit_cnt; tr.nbits = st.nbits; tr.nsoft = 0;
+		tr.acc = st.bit_acc; nbits0 = st.nbits; tr.nb = (uint32_t)nbits0; tr.nsoft = 0;
+		rf = rcp_approx(tr.freq);
 		my_ring = p.ring + (size_t)my_ch * p.ring_bytes;
 		if (p.soft) my_soft = p.soft + (size_t)my_ch * p.soft_stride;
 		sm.ph[tid][0] = st.disc_prev;
@@ -412,8 +358,11 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 		__syncthreads();
 
 		/* ---- S5: timing + slicer ------------------------------------------------------- */
-		if (my_ch >= 0)
-			timing_run<P>(sm, tid, n, tr, center, alpha, beta, max_fdev, my_ring, ring_mask, my_soft, p.soft_stride);
+		if (my_ch >= 0) {
+			const float DELTA = 8.0f * ((float)(NTM + 16) * 1.2e-7f) / center;       /* see demod_pipe.cu */
+			tm_tile<P, NTM, true, G, RS>(tr, rf, sm.y, tid, n * P, center, alpha, beta, max_fdev, DELTA, my_ring, ring_mask,
+			                             my_soft, p.soft_stride, n_rounds, n_slow, false);
+		}
 
 		/* ---- slide the FIR history: a[g][0..48) <- a[g][n..n+48) ----------------------- */
 		float hv[2];
@@ -435,12 +384,14 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 	if (my_ch >= 0) {
 		demod_state &st = p.st[my_ch];
 		st.agc_bias = bias; st.agc_avg = avg;
-		st.t_prev = tr.prev; st.t_phase = tr.phase; st.t_freq = tr.freq; st.t_state = tr.state;
-		st.bit_acc = tr.acc; st.bit_cnt = tr.cnt; st.nbits = tr.nbits; st.nsoft = tr.nsoft;
-		p.nbits_out[my_ch] = tr.nbits;
+		const uint64_t nbits = nbits0 + (uint64_t)(tr.nb - (uint32_t)nbits0);
+		const int cnt = (int)(tr.nb & 7u);
+		st.t_prev = tr.prev; st.t_phase = tr.phase; st.t_freq = tr.freq; st.t_state = (int)tr.target;
+		st.bit_acc = tr.acc & ((1u << cnt) - 1u); st.bit_cnt = cnt; st.nbits = nbits; st.nsoft = tr.nsoft;
+		p.nbits_out[my_ch] = nbits;
 		if (p.is_iq) st.disc_prev = sm.ph[tid][0];
-		if (tr.cnt)                                       /* left-aligned partial byte, gfsk.c:78 */
-			my_ring[(uint32_t)(tr.nbits >> 3) & ring_mask] = (uint8_t)(tr.acc << (8 - tr.cnt));
+		if (cnt)                                          /* left-aligned partial byte, gfsk.c:78 */
+			my_ring[(uint32_t)(nbits >> 3) & ring_mask] = (uint8_t)(tr.acc << (8 - cnt));
 	}
 	for (int i = tid; i < G * SONDE_FIR_HIST; i += NT) {
 		const int g = i / SONDE_FIR_HIST, k = i % SONDE_FIR_HIST;
