@@ -54,7 +54,10 @@ enum sonde_type {
 	SONDE_MRZN1  = 4,   /* MRZ-N1                   SD/sonde/mrz-n1/ */
 	SONDE_IMET4  = 5,   /* InterMet iMet-1/4        SD/sonde/imet4/  */
 	SONDE_C50    = 6,   /* Meteolabor SRS-C50       SD/sonde/c50/    */
-	SONDE_NTYPES = 7
+	SONDE_NTYPES = 7,
+	/* AUTO: run all seven decoders on the channel until one yields a decodable frame, then lock to it
+	 * (sondedump's autodetect, SD/decode.c:174-224; order rs41, m10, ims100, dfm09, imet4, c50, mrzn1) */
+	SONDE_AUTO   = -1
 };
 
 /* Error codes (all entry points return 0 on success, <0 on failure). */
@@ -140,6 +143,12 @@ SONDE_API int  sonde_b200_fetch(sonde_b200 *h, sonde_frame_rec *recs, int32_t *c
 
 /* Only the per-channel counters (cheap D2H): frames[C], ok[C]; same call selection as fetch(). */
 SONDE_API int  sonde_b200_fetch_counts(sonde_b200 *h, int32_t *frames, int32_t *ok);
+
+/* AUTO channels: types[C] receives the decoder each channel is locked to (SONDE_AUTO while undetermined; fixed
+ * channels report their own type).  A channel locks at the fetch() of the first call in which one of the seven
+ * decoders, tried in the reference's order, produced a frame passing its gate; until then fetch() reports no
+ * records for it, from then on the records of the locked decoder; the six others stop running. */
+SONDE_API int  sonde_b200_detected_types(sonde_b200 *h, int32_t *types);
 
 /* Running totals since create, per channel: framer windows, windows passing the gate, demodulated bits. */
 SONDE_API int  sonde_b200_fetch_totals(sonde_b200 *h, int64_t *frames, int64_t *ok, int64_t *bits);

@@ -23,7 +23,7 @@ _ERR_NAMES = {ERR_ARG: "SONDE_ERR_ARG", ERR_CUDA: "SONDE_ERR_CUDA", ERR_NODEVICE
 EXPORTS = [
     "sonde_b200_create", "sonde_b200_destroy", "sonde_b200_process_iq", "sonde_b200_process_fm",
     "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
-    "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
+    "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_detected_types", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
     "sonde_b200_soft_stride", "sonde_b200_fetch_soft", "sonde_b200_fetch_state", "sonde_b200_modem_info",
     "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
     "sonde_b200_last_kernel_ms", "sonde_b200_launch_count", "sonde_b200_last_error", "sonde_b200_version",
@@ -92,6 +92,7 @@ def load():
         "sonde_b200_fetch": (ctypes.c_int, [vp, vp, i32p]),
         "sonde_b200_fetch_counts": (ctypes.c_int, [vp, i32p, i32p]),
         "sonde_b200_fetch_totals": (ctypes.c_int, [vp, vp, vp, vp]),
+        "sonde_b200_detected_types": (ctypes.c_int, [vp, i32p]),
         "sonde_b200_bits_stride": (ctypes.c_int, [vp]),
         "sonde_b200_fetch_bits": (ctypes.c_int, [vp, vp, i32p]),
         "sonde_b200_soft_stride": (ctypes.c_int, [vp]),
@@ -237,6 +238,12 @@ class BatchDecoder:
         ok = np.zeros(self.C, dtype=np.int32)
         self._ck(self.lib.sonde_b200_fetch_counts(self.h, _i32p(frames), _i32p(ok)))
         return frames, ok
+
+    def detected_types(self):
+        """Decoder each channel reports (-1 = AUTO channel not locked yet)."""
+        t = np.zeros(self.C, dtype=np.int32)
+        self._ck(self.lib.sonde_b200_detected_types(self.h, _i32p(t)))
+        return t
 
     def fetch_totals(self):
         """-> (frames, ok, bits) int64[C] running totals since create"""

@@ -228,7 +228,7 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 				const int ch = chans[g];
 				float phv = 0.0f;
 				if (ch >= 0 && i < n) {
-					const float2 q = __ldg(&in[(size_t)ch * p.row_stride + base + i]);
+					const float2 q = __ldg(&in[(size_t)p.in_row[ch] * p.row_stride + base + i]);
 					phv = det_phase(q.x, q.y);
 				}
 				sm.ph[g][i + 1] = phv;
@@ -254,7 +254,7 @@ demod_gfsk_kernel(const demod_params p, const int group_base)
 				const int g = idx / T, i = idx % T;
 				const int ch = chans[g];
 				float xv = 0.0f;
-				if (ch >= 0 && i < n) xv = __ldg(&in[(size_t)ch * p.row_stride + base + i]);
+				if (ch >= 0 && i < n) xv = __ldg(&in[(size_t)p.in_row[ch] * p.row_stride + base + i]);
 				sm.x[g][i] = xv;
 				zero |= (i < n && ch >= 0 && xv == 0.0f);
 			}

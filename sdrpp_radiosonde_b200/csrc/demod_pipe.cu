@@ -99,7 +99,7 @@ struct smem_t {
 	int   zflag[NX];                     /* tile contains exact-zero samples         */
 	unsigned long long negzero2;         /* (-0.0f, -0.0f), read at run time so that the packed product stays an FFMA2 */
 	unsigned long long rawfull[2], rawfree[2];   /* complete_tx barriers of the bulk copies / slot released by PW */
-	int chan[G];
+	int chan[G], row[G];
 	unsigned long long xfull[NX], sfull[NS2], sfree[NS2], vfull[NS2], vfree[NS2], yfull[NS2], yfree[NS2];
 };
 
@@ -251,7 +251,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 		sm.a[1][g][T + k] = (ch >= 0) ? p.st[ch].hist[k] : 0.0f;
 	}
 	if (tid < G) sm.carry[0][tid] = (chans[tid] >= 0) ? p.st[chans[tid]].disc_prev : 0.0f;
-	if (tid < G) sm.chan[tid] = chans[tid];
+	if (tid < G) { sm.chan[tid] = chans[tid]; sm.row[tid] = chans[tid] >= 0 ? p.in_row[chans[tid]] : 0; }
 	__syncthreads();
 
 	if (RL::idle(warp)) return;
@@ -273,7 +273,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 				for (int g = 0; g < G; g++)
 					if (sm.chan[g] >= 0)
 						tma_load_1d(&sm.raw[slot][g][0],
-						            static_cast<const char *>(p.in) + ((size_t)sm.chan[g] * p.row_stride + (size_t)tile * T) * ESZ,
+						            static_cast<const char *>(p.in) + ((size_t)sm.row[g] * p.row_stride + (size_t)tile * T) * ESZ,
 						            bytes, &sm.rawfull[slot]);
 			}
 		}
@@ -287,9 +287,12 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 		const int g0 = (pt / T) * CPT;           /* first of the CPT channels owned in S1 / S3   */
 		const int fir_g = pw % G;                /* channel row owned in S4                      */
 		const int fir_seg = (pw / G) * 32 + lane;/* segment of R outputs owned in S4             */
-		int ch_of[CPT];
+		int ch_of[CPT], row_of[CPT];
 #pragma unroll
-		for (int c = 0; c < CPT; c++) ch_of[c] = chans[g0 + c];
+		for (int c = 0; c < CPT; c++) {
+			ch_of[c] = chans[g0 + c];
+			row_of[c] = ch_of[c] >= 0 ? p.in_row[ch_of[c]] : 0;
+		}
 
 		const unsigned long long negzero2 = *reinterpret_cast<volatile unsigned long long *>(&sm.negzero2);
 		/* Input staging.  When the rows are 16-byte aligned (p.use_tma, decided on the host) one elected thread
@@ -305,8 +308,8 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			for (int c = 0; c < CPT; c++) {
 				q[c] = make_float2(0.0f, 0.0f);
 				if (i < L && ch_of[c] >= 0) {
-					if (IQ) q[c] = __ldg(static_cast<const float2 *>(p.in) + (size_t)ch_of[c] * p.row_stride + i);
-					else    q[c].x = __ldg(static_cast<const float *>(p.in) + (size_t)ch_of[c] * p.row_stride + i);
+					if (IQ) q[c] = __ldg(static_cast<const float2 *>(p.in) + (size_t)row_of[c] * p.row_stride + i);
+					else    q[c].x = __ldg(static_cast<const float *>(p.in) + (size_t)row_of[c] * p.row_stride + i);
 				}
 			}
 		};

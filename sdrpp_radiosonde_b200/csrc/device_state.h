@@ -82,6 +82,7 @@ struct demod_params {
 	float        *soft;           /* [C][soft_stride] or NULL                         */
 	int32_t       soft_stride;
 	long long    *prof;           /* optional [n_groups][16] cycle counters (diagnostics) */
+	const int32_t *in_row;        /* [C] input row of each (virtual) channel          */
 	uint64_t     *nbits_out;      /* [C] stream length after this call (snapshot for the framer, which
 	                                 may run concurrently with the next call's demodulator)             */
 };
@@ -97,6 +98,7 @@ struct frame_params {
 	int32_t        max_frames;
 	int32_t        chunk_index;
 	int32_t       *counts;        /* [C][2] frames / ok of this call                 */
+	const int32_t *active;        /* [C] 0 = channel switched off (AUTO loser)        */
 };
 
 #endif

@@ -650,6 +650,10 @@ frame_kernel(const frame_params p)
 
 	const int ch = blockIdx.x * WARPS_PER_CTA + wid;
 	if (ch >= p.n_channels) return;
+	if (p.active && !p.active[ch]) {
+		if (lane == 0 && p.counts) { p.counts[2 * ch] = 0; p.counts[2 * ch + 1] = 0; }
+		return;
+	}
 	warp_smem &ws = sm.w[wid];
 
 	const int type = p.types[ch];

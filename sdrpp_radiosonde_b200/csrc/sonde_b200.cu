@@ -32,7 +32,16 @@ extern "C" cudaError_t sonde_launch_frames(const frame_params *p, cudaStream_t s
 
 struct sonde_b200 {
 	sonde_b200_config cfg;
-	std::vector<int32_t> types;
+	std::vector<int32_t> types;          /* per VIRTUAL channel (AUTO channels expand to seven)            */
+	int n_user = 0;                      /* channels as the caller sees them                               */
+	std::vector<int32_t> user_types;     /* as given, SONDE_AUTO allowed                                   */
+	std::vector<int32_t> slot0;          /* first virtual channel of each user channel                     */
+	std::vector<int32_t> locked;         /* decoder type a user channel reports (SONDE_AUTO = undetermined)*/
+	std::vector<int32_t> gchan_host;     /* host copy of d_group_chan                                      */
+	int32_t *d_in_row = nullptr, *d_active = nullptr;
+	std::vector<sonde_frame_rec> h_recs; /* staging for fetch() when virtual != user channels              */
+	std::vector<int32_t> h_vcounts;
+	bool has_auto = false;
 	sonde_modem modems[SONDE_NTYPES_];
 	int device = 0;
 	cudaStream_t stream = nullptr;
@@ -122,7 +131,7 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	if (!cfg || cfg->n_channels <= 0 || cfg->samplerate <= 0 || cfg->max_chunk_len <= 0 || !cfg->types)
 		return SONDE_ERR_ARG;
 	for (int c = 0; c < cfg->n_channels; c++)
-		if (cfg->types[c] < 0 || cfg->types[c] >= SONDE_NTYPES) return SONDE_ERR_ARG;
+		if (cfg->types[c] != SONDE_AUTO && (cfg->types[c] < 0 || cfg->types[c] >= SONDE_NTYPES)) return SONDE_ERR_ARG;
 
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev)
@@ -133,7 +142,25 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 
 	sonde_b200 *h = new sonde_b200();
 	h->cfg = *cfg;
-	h->types.assign(cfg->types, cfg->types + cfg->n_channels);
+	/* virtual channels: a fixed channel is itself; an AUTO channel is the seven decoders in the order of
+	 * SD/decode.c:174-224, all fed from the same input row */
+	static const int32_t kAutoOrder[SONDE_NTYPES] = {SONDE_RS41, SONDE_M10, SONDE_IMS100, SONDE_DFM09, SONDE_IMET4,
+	                                                SONDE_C50, SONDE_MRZN1};
+	h->n_user = cfg->n_channels;
+	h->user_types.assign(cfg->types, cfg->types + cfg->n_channels);
+	std::vector<int32_t> in_row;
+	for (int c = 0; c < cfg->n_channels; c++) {
+		h->slot0.push_back((int32_t)h->types.size());
+		if (cfg->types[c] == SONDE_AUTO) {
+			h->has_auto = true;
+			for (int k = 0; k < SONDE_NTYPES; k++) { h->types.push_back(kAutoOrder[k]); in_row.push_back(c); }
+		} else {
+			h->types.push_back(cfg->types[c]);
+			in_row.push_back(c);
+		}
+	}
+	h->locked = h->user_types;
+	h->cfg.n_channels = (int32_t)h->types.size();        /* device-side channel count from here on */
 	h->cfg.types = h->types.data();
 	h->device = cfg->device;
 	if (h->cfg.fm_gain == 0.0f) h->cfg.fm_gain = 0.636619747f;
@@ -143,8 +170,8 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	for (int t = 0; t < SONDE_NTYPES; t++)
 		if (sonde_modem_init(&h->modems[t], t, cfg->samplerate)) {
 			/* a type that does not exist at this rate is only an error if a channel uses it */
-			for (int c = 0; c < cfg->n_channels; c++)
-				if (cfg->types[c] == t) return bail(SONDE_ERR_ARG);
+			for (size_t c = 0; c < h->types.size(); c++)
+				if (h->types[c] == t) return bail(SONDE_ERR_ARG);
 			memset(&h->modems[t], 0, sizeof(sonde_modem));
 		}
 
@@ -174,7 +201,7 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 			return bail(SONDE_ERR_CUDA);
 
 	/* ---- channel groups: type-homogeneous CTAs, ordered by kernel variant ---------------- */
-	const int C = cfg->n_channels;
+	const int C = h->cfg.n_channels;
 	std::vector<int32_t> gchan, gtype;
 	auto add_groups = [&](auto pred) {
 		int added = 0;
@@ -221,6 +248,18 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	CKB(cudaMemcpy(h->d_group_chan, gchan.data(), gchan.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
 	CKB(cudaMemcpy(h->d_group_type, gtype.data(), gtype.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
 	CKB(cudaMemcpy(h->d_types, h->types.data(), C * sizeof(int32_t), cudaMemcpyHostToDevice));
+	h->gchan_host = gchan;
+	CKB(cudaMalloc(&h->d_in_row, C * sizeof(int32_t)));
+	CKB(cudaMemcpy(h->d_in_row, in_row.data(), C * sizeof(int32_t), cudaMemcpyHostToDevice));
+	{
+		std::vector<int32_t> ones(C, 1);
+		CKB(cudaMalloc(&h->d_active, C * sizeof(int32_t)));
+		CKB(cudaMemcpy(h->d_active, ones.data(), C * sizeof(int32_t), cudaMemcpyHostToDevice));
+	}
+	if (h->has_auto) {
+		h->h_recs.resize((size_t)C * h->max_frames);
+		h->h_vcounts.resize((size_t)C * 2);
+	}
 
 	CKB(cudaMalloc(&h->d_demod, (size_t)C * sizeof(demod_state)));
 	CKB(cudaMalloc(&h->d_framer, (size_t)C * sizeof(framer_state)));
@@ -264,7 +303,7 @@ void sonde_b200_destroy(sonde_b200 *h)
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_group_chan); cudaFree(h->d_group_type); cudaFree(h->d_types);
 	cudaFree(h->d_demod); cudaFree(h->d_afsk); cudaFree(h->d_framer); cudaFree(h->d_ring);
-	cudaFree(h->d_prof);
+	cudaFree(h->d_prof); cudaFree(h->d_in_row); cudaFree(h->d_active);
 	for (int b = 0; b < 2; b++) {
 		cudaFree(h->d_recs[b]); cudaFree(h->d_counts[b]); cudaFree(h->d_in[b]); cudaFree(h->d_nbits[b]);
 		if (h->ev_demod[b]) cudaEventDestroy(h->ev_demod[b]);
@@ -319,6 +358,7 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	dp.soft = h->d_soft;
 	dp.soft_stride = h->soft_stride;
 	dp.prof = h->d_prof;
+	dp.in_row = h->d_in_row;
 
 	const int par = (int)(h->n_issued & 1);
 	dp.nbits_out = h->d_nbits[par];
@@ -364,6 +404,7 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	fp.max_frames = h->max_frames;
 	fp.chunk_index = h->chunk_index;
 	fp.counts = h->d_counts[par];
+	fp.active = h->d_active;
 	CK(cudaStreamWaitEvent(h->fstream, h->ev_demod[par], 0));
 	CK(cudaEventRecord(h->evf[0], h->fstream));
 	CK(sonde_launch_frames(&fp, h->fstream));
@@ -393,13 +434,13 @@ static int process_host(sonde_b200 *h, const float *src, size_t len, int is_iq)
 	if (len > (size_t)h->cfg.max_chunk_len) return fail(h, SONDE_ERR_TOOLONG, "len > max_chunk_len");
 	CK(cudaSetDevice(h->device));
 	const size_t esz = is_iq ? 2 * sizeof(float) : sizeof(float);
-	const size_t need = (size_t)h->cfg.n_channels * h->cfg.max_chunk_len * 2 * sizeof(float);
+	const size_t need = (size_t)h->n_user * h->cfg.max_chunk_len * 2 * sizeof(float);
 	const int par = (int)(h->n_issued & 1);
 	if (!h->d_in[par]) CK(cudaMalloc(&h->d_in[par], need));
 	/* copy on the copy stream once the kernels that last read this staging buffer are done; the compute
 	 * stream then waits for the copy.  With pinned `src` the H2D of this call overlaps the previous call's kernels. */
 	if (h->n_issued >= 2) CK(cudaStreamWaitEvent(h->cstream, h->ev_done[par], 0));
-	CK(cudaMemcpyAsync(h->d_in[par], src, (size_t)h->cfg.n_channels * len * esz, cudaMemcpyHostToDevice, h->cstream));
+	CK(cudaMemcpyAsync(h->d_in[par], src, (size_t)h->n_user * len * esz, cudaMemcpyHostToDevice, h->cstream));
 	CK(cudaEventRecord(h->ev_copied[par], h->cstream));
 	CK(cudaStreamWaitEvent(h->stream, h->ev_copied[par], 0));
 	return run_chunk(h, h->d_in[par], len, len, is_iq);
@@ -447,15 +488,70 @@ static int fetch_slot(sonde_b200 *h, long *call)
 	return (int)(c & 1);
 }
 
+/* per-virtual-channel counters of one call into h->h_counts */
+static int pull_counts(sonde_b200 *h, int par)
+{
+	const int V = h->cfg.n_channels;
+	CK(cudaStreamWaitEvent(h->dstream, h->ev_done[par], 0));
+	CK(cudaMemcpyAsync(h->h_counts, h->d_counts[par], (size_t)V * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->dstream));
+	CK(cudaStreamSynchronize(h->dstream));
+	return SONDE_OK;
+}
+
+/* AUTO policy (SD/decode.c:174-224): an undetermined channel locks to the first decoder, in the reference's
+ * order, that produced a frame passing its gate in this call; the losers are switched off for later calls. */
+static int auto_update(sonde_b200 *h)
+{
+	bool changed = false;
+	std::vector<int32_t> active;
+	for (int c = 0; c < h->n_user; c++) {
+		if (h->user_types[c] != SONDE_AUTO || h->locked[c] != SONDE_AUTO) continue;
+		const int v0 = h->slot0[c];
+		for (int k = 0; k < SONDE_NTYPES; k++) {
+			if (h->h_counts[2 * (v0 + k) + 1] > 0) {
+				h->locked[c] = h->types[v0 + k];
+				changed = true;
+				break;
+			}
+		}
+	}
+	if (!changed) return SONDE_OK;
+	const int V = h->cfg.n_channels;
+	active.assign(V, 1);
+	for (int c = 0; c < h->n_user; c++) {
+		if (h->user_types[c] != SONDE_AUTO || h->locked[c] == SONDE_AUTO) continue;
+		for (int k = 0; k < SONDE_NTYPES; k++)
+			if (h->types[h->slot0[c] + k] != h->locked[c]) active[h->slot0[c] + k] = 0;
+	}
+	std::vector<int32_t> gchan = h->gchan_host;
+	for (auto &g : gchan)
+		if (g >= 0 && !active[g]) g = -1;
+	/* ordered on the main stream: takes effect from the next process call on */
+	CK(cudaMemcpyAsync(h->d_group_chan, gchan.data(), gchan.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+	CK(cudaMemcpyAsync(h->d_active, active.data(), active.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+	CK(cudaStreamSynchronize(h->stream));        /* the host vectors above go out of scope */
+	return SONDE_OK;
+}
+
+/* virtual channel whose results user channel c reports, -1 while an AUTO channel is undetermined */
+static int report_slot(const sonde_b200 *h, int c)
+{
+	if (h->user_types[c] != SONDE_AUTO) return h->slot0[c];
+	if (h->locked[c] == SONDE_AUTO) return -1;
+	for (int k = 0; k < SONDE_NTYPES; k++)
+		if (h->types[h->slot0[c] + k] == h->locked[c]) return h->slot0[c] + k;
+	return -1;
+}
+
 static int fetch_counts_of(sonde_b200 *h, int par, int32_t *frames, int32_t *ok)
 {
-	const int C = h->cfg.n_channels;
-	CK(cudaStreamWaitEvent(h->dstream, h->ev_done[par], 0));
-	CK(cudaMemcpyAsync(h->h_counts, h->d_counts[par], (size_t)C * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->dstream));
-	CK(cudaStreamSynchronize(h->dstream));
-	for (int c = 0; c < C; c++) {
-		if (frames) frames[c] = h->h_counts[2 * c];
-		if (ok) ok[c] = h->h_counts[2 * c + 1];
+	int rc = pull_counts(h, par);
+	if (rc) return rc;
+	if (h->has_auto && (rc = auto_update(h))) return rc;
+	for (int c = 0; c < h->n_user; c++) {
+		const int v = report_slot(h, c);
+		if (frames) frames[c] = v < 0 ? 0 : h->h_counts[2 * v];
+		if (ok) ok[c] = v < 0 ? 0 : h->h_counts[2 * v + 1];
 	}
 	return SONDE_OK;
 }
@@ -472,21 +568,29 @@ int sonde_b200_fetch_counts(sonde_b200 *h, int32_t *frames, int32_t *ok)
 	return rc;
 }
 
+int sonde_b200_detected_types(sonde_b200 *h, int32_t *types)
+{
+	if (!h || !types) return SONDE_ERR_ARG;
+	for (int c = 0; c < h->n_user; c++) types[c] = h->locked[c];
+	return SONDE_OK;
+}
+
 int sonde_b200_fetch_totals(sonde_b200 *h, int64_t *frames, int64_t *ok, int64_t *bits)
 {
 	if (!h) return SONDE_ERR_ARG;
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->stream));
 	CK(cudaStreamSynchronize(h->fstream));
-	const int C = h->cfg.n_channels;
-	std::vector<framer_state> fs(C);
-	std::vector<demod_state> ds(C);
+	const int V = h->cfg.n_channels;
+	std::vector<framer_state> fs(V);
+	std::vector<demod_state> ds(V);
 	CK(cudaMemcpy(fs.data(), h->d_framer, fs.size() * sizeof(framer_state), cudaMemcpyDeviceToHost));
 	CK(cudaMemcpy(ds.data(), h->d_demod, ds.size() * sizeof(demod_state), cudaMemcpyDeviceToHost));
-	for (int c = 0; c < C; c++) {
-		if (frames) frames[c] = fs[c].frames_total;
-		if (ok) ok[c] = fs[c].ok_total;
-		if (bits) bits[c] = (int64_t)ds[c].nbits;
+	for (int c = 0; c < h->n_user; c++) {
+		const int v = report_slot(h, c);
+		if (frames) frames[c] = v < 0 ? 0 : fs[v].frames_total;
+		if (ok) ok[c] = v < 0 ? 0 : fs[v].ok_total;
+		if (bits) bits[c] = v < 0 ? 0 : (int64_t)ds[v].nbits;
 	}
 	return SONDE_OK;
 }
@@ -500,12 +604,24 @@ int sonde_b200_fetch(sonde_b200 *h, sonde_frame_rec *recs, int32_t *counts)
 	if (par < 0) return fail(h, SONDE_ERR_STATE, "no process call yet");
 	int rc = fetch_counts_of(h, par, counts, nullptr);
 	if (rc) return rc;
-	const int C = h->cfg.n_channels;
-	for (int c = 0; c < C; c++)
-		if (counts[c] > h->max_frames) return fail(h, SONDE_ERR_STATE, "frame record overflow");
-	CK(cudaMemcpyAsync(recs, h->d_recs[par], (size_t)C * h->max_frames * sizeof(sonde_frame_rec),
-	                   cudaMemcpyDeviceToHost, h->dstream));
-	CK(cudaStreamSynchronize(h->dstream));
+	const int V = h->cfg.n_channels;
+	for (int v = 0; v < V; v++)
+		if (h->h_counts[2 * v] > h->max_frames) return fail(h, SONDE_ERR_STATE, "frame record overflow");
+	if (!h->has_auto) {
+		CK(cudaMemcpyAsync(recs, h->d_recs[par], (size_t)V * h->max_frames * sizeof(sonde_frame_rec),
+		                   cudaMemcpyDeviceToHost, h->dstream));
+		CK(cudaStreamSynchronize(h->dstream));
+	} else {
+		/* only the reporting slot of each user channel crosses PCIe */
+		for (int c = 0; c < h->n_user; c++) {
+			const int v = report_slot(h, c);
+			sonde_frame_rec *dst = recs + (size_t)c * h->max_frames;
+			if (v < 0 || counts[c] == 0) continue;
+			CK(cudaMemcpyAsync(dst, h->d_recs[par] + (size_t)v * h->max_frames, (size_t)counts[c] * sizeof(sonde_frame_rec),
+			                   cudaMemcpyDeviceToHost, h->dstream));
+		}
+		CK(cudaStreamSynchronize(h->dstream));
+	}
 	if (call >= h->n_fetched) h->n_fetched = call + 1;
 	return SONDE_OK;
 }
@@ -516,6 +632,7 @@ int sonde_b200_fetch_bits(sonde_b200 *h, uint8_t *bits, int32_t *nbits)
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->stream));
 	CK(cudaStreamSynchronize(h->fstream));
+	if (h->has_auto) return fail(h, SONDE_ERR_STATE, "parity taps are per decoder: not available with AUTO channels");
 	const int C = h->cfg.n_channels;
 	std::vector<demod_state> st(C);
 	std::vector<uint8_t> ring((size_t)C * h->ring_bytes);
@@ -542,6 +659,7 @@ int sonde_b200_fetch_soft(sonde_b200 *h, float *soft, int32_t *nsoft)
 {
 	if (!h || !soft || !nsoft) return SONDE_ERR_ARG;
 	if (!h->d_soft) return fail(h, SONDE_ERR_STATE, "created without keep_soft");
+	if (h->has_auto) return fail(h, SONDE_ERR_STATE, "parity taps are per decoder: not available with AUTO channels");
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->stream));
 	CK(cudaStreamSynchronize(h->fstream));
@@ -556,6 +674,7 @@ int sonde_b200_fetch_soft(sonde_b200 *h, float *soft, int32_t *nsoft)
 int sonde_b200_fetch_state(sonde_b200 *h, float *state /*[C][8]*/)
 {
 	if (!h || !state) return SONDE_ERR_ARG;
+	if (h->has_auto) return fail(h, SONDE_ERR_STATE, "parity taps are per decoder: not available with AUTO channels");
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->stream));
 	CK(cudaStreamSynchronize(h->fstream));

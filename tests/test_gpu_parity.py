@@ -265,3 +265,34 @@ def test_argument_errors_on_device():
     st = dec.fetch_state()
     assert st[0, 0] == 0.0 and st[0, 1] == 5.0
     dec.close()
+
+
+def test_auto_channels_through_the_c_abi():
+    """SONDE_AUTO channels in the C ABI itself (a22): seven decoders per channel until one locks, then the losers
+    stop; from the locking call on the channel reports exactly what a dedicated decoder reports."""
+    from sdrpp_radiosonde_b200 import capi
+    n, chunk = 48000 * 3, 24000
+    sig_types = [synth.DFM09, synth.RS41, synth.C50, synth.MRZN1, synth.IMET4, synth.M10, synth.IMS100, synth.RS41]
+    batch = np.stack([synth.make_fm(synth.default_spec(t, 60 + c), n) for c, t in enumerate(sig_types)])
+    types = [capi_auto if c != 7 else synth.RS41 for c, capi_auto in enumerate([-1] * 8)]      # last channel is fixed
+    dec = capi.BatchDecoder(types, chunk)
+    frames = [[] for _ in types]
+    lock_call = [None] * len(types)
+    for ci, pos in enumerate(range(0, n, chunk)):
+        dec.process_fm(np.ascontiguousarray(batch[:, pos:pos + chunk]))
+        recs, counts = dec.fetch()
+        det = dec.detected_types()
+        for c in range(len(types)):
+            if det[c] >= 0 and lock_call[c] is None:
+                lock_call[c] = ci
+            frames[c].extend(recs[c, :counts[c]].copy())
+    launches = dec.launch_count
+    dec.close()
+    assert list(det) == sig_types
+    chk = checkers()[0]
+    for c, t in enumerate(sig_types):
+        want = [w for w in chk.frames_run(t, batch[c], chunk) if w.chunk >= lock_call[c]]
+        rb = (synth.MODEMS[t].frame_bits + 7) // 8
+        assert [rec_key(g, rb) for g in frames[c]] == [rec_key(w, rb) for w in want], (c, t)
+        assert len(want) > 0
+    assert launches > 0
