@@ -296,3 +296,30 @@ def test_auto_channels_through_the_c_abi():
         assert [rec_key(g, rb) for g in frames[c]] == [rec_key(w, rb) for w in want], (c, t)
         assert len(want) > 0
     assert launches > 0
+
+
+def test_handles_are_independent_and_reusable():
+    """Two handles interleaved on one device give what each gives alone; create/destroy cycles do not leak state."""
+    from sdrpp_radiosonde_b200 import capi
+    n, chunk = 48000, 8000
+    a_types, b_types = [synth.RS41, synth.DFM09], [synth.M10, synth.C50, synth.RS41]
+    a_in = np.stack([synth.make_iq(synth.default_spec(t, 70 + c), n) for c, t in enumerate(a_types)])
+    b_in = np.stack([synth.make_iq(synth.default_spec(t, 80 + c), n) for c, t in enumerate(b_types)])
+    alone_a = run_gpu(a_types, a_in, chunk, kind="iq")["frames"]
+    alone_b = run_gpu(b_types, b_in, chunk, kind="iq")["frames"]
+    for _ in range(3):                                   # repeated create/destroy
+        da, db = capi.BatchDecoder(a_types, chunk), capi.BatchDecoder(b_types, chunk)
+        fa, fb = [[] for _ in a_types], [[] for _ in b_types]
+        for pos in range(0, n, chunk):
+            da.process_iq(a_in[:, pos:pos + chunk])
+            db.process_iq(b_in[:, pos:pos + chunk])
+            for dec, out in ((db, fb), (da, fa)):
+                recs, counts = dec.fetch()
+                for c in range(len(out)):
+                    out[c].extend(recs[c, :counts[c]].copy())
+        da.close()
+        db.close()
+        for got, want, types in ((fa, alone_a, a_types), (fb, alone_b, b_types)):
+            for c, t in enumerate(types):
+                rb = (synth.MODEMS[t].frame_bits + 7) // 8
+                assert [rec_key(g, rb) for g in got[c]] == [rec_key(w, rb) for w in want[c]]
