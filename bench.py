@@ -151,7 +151,20 @@ def summarize_clocks(samples):
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(samples)}
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints to fd 1 (e.g. NCCL's version
+    banner) has been rerouted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -201,7 +214,7 @@ def main():
                 "config": dict(config, frames_per_s=frames / t, ok_frames_per_s=ok / t),
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": cpu.kind, "sample": desc},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ---------------------------------------------------------------- B200 arm
@@ -367,7 +380,7 @@ def main():
                                     "kind": cpu.kind,
                                     "sample": f"first {n_ch} channels x {n_total} samples, {reps} passes",
                                     "ok_frames_per_s": k * reps / t}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     dec.close()
     if world > 1:
