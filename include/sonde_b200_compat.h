@@ -54,6 +54,12 @@ SONDE_COMPAT_DECL(mrzn1, MRZN1Decoder)      /* SD/include/mrzn1.h           */
 SONDE_COMPAT_DECL(imet4, IMET4Decoder)      /* SD/include/imet4.h           */
 SONDE_COMPAT_DECL(c50, C50Decoder)          /* SD/include/c50.h             */
 
+/* Telemetry parsers alone (host only, no GPU): frame record -> SondeData with the per-channel state the
+ * reference keeps in its decoder structs (SD/sonde/<type>/<type>.c, parser.c). */
+SONDE_API void *sonde_telemetry_create(int type);
+SONDE_API void  sonde_telemetry_destroy(void *t);
+SONDE_API int   sonde_telemetry_parse(void *t, const sonde_frame_rec *rec, SondeData *out);
+
 #ifdef __cplusplus
 }
 #endif

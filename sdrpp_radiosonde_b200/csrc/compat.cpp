@@ -13,6 +13,7 @@
 
 #include "../../include/sonde_b200_compat.h"
 #include "../host/gpu_decoder.hpp"
+#include "../host/telemetry.hpp"
 
 struct sonde_compat_decoder {
 	sonde_b200 *h = nullptr;
@@ -21,6 +22,7 @@ struct sonde_compat_decoder {
 	int n_recs = 0, next = 0;
 	bool armed = false;              /* records of the current buffer are queued */
 	const sonde_frame_rec *last = nullptr;
+	radiosonde::Telemetry tele;
 };
 
 namespace {
@@ -41,6 +43,7 @@ sonde_compat_decoder *make(int type, int samplerate)
 		return nullptr;
 	}
 	d->type = type;
+	d->tele.reset(type);
 	d->max_chunk = cfg.max_chunk_len;
 	d->max_frames = sonde_b200_max_frames(d->h);
 	d->recs.resize(d->max_frames);
@@ -69,9 +72,7 @@ ParserStatus step(sonde_compat_decoder *d, SondeData *dst, const float *src, siz
 	if (d->next < d->n_recs) {
 		d->last = &d->recs[d->next++];
 		if (dst) {
-			::SondeData tmp;
-			radiosonde::fragment_from_record(*d->last, &tmp);
-			memcpy(dst, &tmp, sizeof(tmp));
+			d->tele.parse(*d->last, dst);
 		}
 		return PARSED;
 	}
@@ -97,3 +98,13 @@ SONDE_COMPAT_IMPL(ims100, IMS100Decoder, SONDE_IMS100)
 SONDE_COMPAT_IMPL(mrzn1, MRZN1Decoder, SONDE_MRZN1)
 SONDE_COMPAT_IMPL(imet4, IMET4Decoder, SONDE_IMET4)
 SONDE_COMPAT_IMPL(c50, C50Decoder, SONDE_C50)
+
+/* Host-only telemetry entry points (no GPU needed): one parser state per channel, fed with frame records. */
+extern "C" SONDE_API void *sonde_telemetry_create(int type) { return new (std::nothrow) radiosonde::Telemetry(type); }
+extern "C" SONDE_API void sonde_telemetry_destroy(void *t) { delete static_cast<radiosonde::Telemetry *>(t); }
+extern "C" SONDE_API int sonde_telemetry_parse(void *t, const sonde_frame_rec *rec, SondeData *out)
+{
+	if (!t || !rec || !out) return SONDE_ERR_ARG;
+	static_cast<radiosonde::Telemetry *>(t)->parse(*rec, out);
+	return SONDE_OK;
+}

@@ -443,7 +443,11 @@ def random_frame_bits(stype: int, rng: np.random.Generator, index: int = 0) -> n
         p[15] = 0xC1 if index % 2 == 0 else 0xA2
         return ims100_raw_bits(bytes(p))
     if stype == MRZN1:
-        return mrzn1_raw_bits(bytes(rng.integers(0, 256, 45, dtype=np.uint8)))
+        body = bytearray(rng.integers(0, 256, 45, dtype=np.uint8))
+        # calib_frag_seq (frame byte 44) is 1..16 on air; the reference indexes its 64-byte calibration
+        # image with it unchecked (mrzn1.c:136-141), so anything else corrupts the reference's own state
+        body[40] = 1 + index % 16
+        return mrzn1_raw_bits(bytes(body))
     if stype == IMET4:
         return imet4_raw_bits(rng)
     if stype == C50:
