@@ -6,10 +6,11 @@
  * frame record the GPU path produced (sonde_frame_rec: post-FEC frame bytes + gate) and fills one
  * SondeData exactly where the reference's xxx_decode() would (fields == 0: nothing decodable).
  *
- * Covered: RS41 status / GPS position / GPS time (rs41.c:205-273), M10 and M20 (m10.c:104-183,
- * m10/parser.c), MRZ-N1 (mrzn1.c:93-142, mrz-n1/parser.c), iMet-1/4 (imet4.c:91-145,158-226,
- * imet4/parser.c), SRS-C50 (c50.c:82-137, c50/parser.c).  Not yet: RS41 PTU/XDATA (need the 816-byte
- * calibration state), DFM06/09/17, iMS-100/RS-11G — their frames still reach the frame callback.
+ * Covered: RS41 incl. PTU, XDATA ozone and the 51-fragment calibration image (rs41.c:126-323, rs41/parser.c),
+ * DFM06/09/17 (dfm09.c:69-237, dfm09/parser.c), M10 and M20 (m10.c:104-183, m10/parser.c), iMS-100 and RS-11G
+ * (ims100.c:81-346, ims100/parser.c), MRZ-N1 (mrzn1.c:93-142, mrz-n1/parser.c), iMet-1/4 (imet4.c:91-145,158-226,
+ * imet4/parser.c), SRS-C50 (c50.c:82-137, c50/parser.c).  Where the reference indexes its state with an unchecked
+ * value from the frame (calibration fragment numbers) this bounds the index instead of writing out of range.
  *
  * Float expressions keep the reference's evaluation types (float vs double constants) so that the values
  * agree to rounding; tests/test_telemetry.py compares against the compiled reference.
@@ -125,6 +126,46 @@ inline float wv_sat_pressure(float temp)
 	return (float)(p / 100.0);
 }
 
+/* MSB-first merge of nbits starting at a byte boundary (SD/bitops.c:32-43).  Like the reference it always ORs in the
+ * top (nbits % 8) + 1 bits of the byte that follows the whole bytes, i.e. for nbits = 8k it reads one byte more and
+ * takes its most significant bit into bit 0 of the result. */
+inline uint64_t merge_bits(const uint8_t *p, int nbits)
+{
+	uint64_t v = 0;
+	for (; nbits >= 8; nbits -= 8) v = v << 8 | *p++;
+	return v << nbits | (uint64_t)(*p >> (7 - nbits));
+}
+
+/* Microsoft binary format, little endian -> float (SD/bitops.c:132-152) */
+inline float mbf_le(const uint8_t *p)
+{
+	const uint32_t u = (uint32_t)(p[2] >> 7) << 31 | (uint32_t)(uint8_t)(p[3] - 2) << 23 | (uint32_t)(p[2] & 0x7F) << 16 | (uint32_t)p[1] << 8 | p[0];
+	float f;
+	memcpy(&f, &u, 4);
+	return f;
+}
+
+/* cubic Hermite spline through (xs, ys) with finite-difference tangents, evaluated at x; -1 outside the table or in its
+ * first interval (SD/utils.c:41-65,88-101) */
+inline float spline_slope(const float *xs, const float *ys, int k)
+{
+	if (k == 0) return (ys[1] - ys[0]) / (xs[1] - xs[0]);
+	return (float)(0.5 * ((ys[k + 1] - ys[k]) / (xs[k + 1] - xs[k]) + (ys[k] - ys[k - 1]) / (xs[k] - xs[k - 1])));
+}
+inline float cubic_spline(const float *xs, const float *ys, float count, float x)
+{
+	for (int i = 1; i < count - 1; i++) {
+		if ((x - xs[i + 1]) * (x - xs[i]) <= 0) {
+			const float m0 = spline_slope(xs, ys, i), m1 = spline_slope(xs, ys, i + 1);
+			const float t = (x - xs[i]) / (xs[i + 1] - xs[i]);
+			const float h00 = (1 + 2 * t) * (1 - t) * (1 - t), h10 = t * (1 - t) * (1 - t);
+			const float h01 = t * t * (3 - 2 * t), h11 = t * t * (t - 1);
+			return h00 * ys[i] + h10 * (xs[i + 1] - xs[i]) * m0 + h01 * ys[i + 1] + h11 * (xs[i + 1] - xs[i]) * m1;
+		}
+	}
+	return -1;
+}
+
 /* days since the epoch used by the reference's own timegm (SD/utils.c:42-52,68-95) */
 inline unsigned day_number(unsigned year, unsigned month, unsigned day)
 {
@@ -177,6 +218,7 @@ public:
 	void reset(int type)
 	{
 		m_type = type;
+		const time_t zero = 0;
 		memset(&m_partial, 0, sizeof(m_partial));
 		memset(m_mrz_calib, 0, sizeof(m_mrz_calib));
 		static const uint8_t rs41_default[816] = {
@@ -184,8 +226,18 @@ public:
 		};
 		memcpy(m_rs41_calib, rs41_default, sizeof(m_rs41_calib));
 		memset(m_rs41_have, 0, sizeof(m_rs41_have));
+		memset(m_dfm_raw, 0, sizeof(m_dfm_raw));
+		m_dfm_serial_ch = 0;
+		m_dfm_serial = 0;
+		m_dfm_tm = *gmtime(&zero);
+		memset(&m_dfm_tm, 0, sizeof(m_dfm_tm));
+		memset(m_ims_calib, 0, sizeof(m_ims_calib));
+		m_ims_mask = 0;
+		m_ims_date = 0;
+		m_ims_prev_alt = 0;
+		m_ims_prev_time = -1;
+		m_adc_ref = m_adc_temp = m_adc_rh = m_adc_rh_temp = 0;
 		m_mrz_mask = 0;
-		const time_t zero = 0;
 		m_c50_tm = *gmtime(&zero);
 		m_imet_prev[0] = m_imet_prev[1] = m_imet_prev[2] = 0;
 		m_imet_prev_time = 0;
@@ -201,6 +253,13 @@ public:
 		case SONDE_MRZN1: if (r.ok) mrzn1(r.data, dst); break;
 		case SONDE_IMET4: imet4(r, dst); break;
 		case SONDE_C50:   if (r.ok) c50(r.data, dst); break;
+		case SONDE_DFM09: if (r.ok) dfm09(r.data + 64, dst); break;
+		case SONDE_IMS100:
+			if (r.ok) {
+				if (r.data[80 + 15] == 0xA2) rs11g(r.data + 80, dst);
+				else if (r.data[80 + 15] == 0xC1) ims100(r.data + 80, dst);
+			}
+			break;
 		default: break;
 		}
 	}
@@ -614,8 +673,305 @@ private:
 		m_partial.fields = 0;
 	}
 
+	/* ---- DFM06/09/17: 18-byte unpacked frame = PTU channel (type, 24 bits) + 2 GPS slots (type, 48 bits); the output
+	 * record is assembled across frames (dfm09.c:69-237, dfm09/parser.c) ------------------------------------------ */
+	void dfm09(const uint8_t *f, SondeData *dst)
+	{
+		uint8_t fr[20];
+		memcpy(fr, f, 18);
+		fr[18] = fr[19] = 0;                                   /* what merge_bits() may touch past the frame */
+		dfm09_ptu(fr);
+		dfm09_gps(fr + 4);
+		dfm09_gps(fr + 11);
+		m_partial.pressure = tl::altitude_to_pressure(m_partial.alt);
+		memcpy(dst, &m_partial, sizeof(*dst));
+		m_partial.fields = 0;
+	}
+
+	static float dfm09_mantissa(uint32_t raw) { return (float)(raw & 0xFFFFF) / (1 << (raw >> 20)); }
+
+	void dfm09_ptu(const uint8_t *sf)
+	{
+		const uint8_t type = sf[0];
+		const uint32_t ch = (uint32_t)tl::merge_bits(sf + 1, 24);
+		m_dfm_raw[type & 15] = ch;
+		if ((ch & 0xFFFF) == 0) m_dfm_serial_ch = (uint8_t)(type + 1);     /* the channel before the serial is all zero */
+		if (type == 0) {                                       /* thermistor against the two reference channels 3, 4 */
+			const uint32_t r1 = m_dfm_raw[3], r2 = m_dfm_raw[4];
+			const float bb0 = 3260.0f, t0 = (float)(25 + 273.15), r0 = 5.0e3f, rf = 220e3f;
+			const float g = dfm09_mantissa(r2) / rf;
+			float res = (dfm09_mantissa(ch) - dfm09_mantissa(r1)) / g;
+			float temp = 0;
+			if (!ch || !r1 || !r2) res = 0;
+			if (res > 0) temp = (float)(1.0 / (1 / t0 + 1 / bb0 * logf(res / r0)) - 273.15);
+			m_partial.temp = temp;
+			m_partial.fields |= DATA_PTU;
+			m_partial.calib_percent = 100.0;
+		} else if (type == 1) {
+			m_partial.rh = 0;
+		} else if (type == m_dfm_serial_ch) {
+			if (type == 0x06) {                                  /* DFM06: the serial in one piece */
+				m_partial.fields |= DATA_SERIAL;
+				sprintf(m_partial.serial, "D%06X", ch);
+			} else {                                             /* DFM09/17: four 16-bit shards, index in the low nibble */
+				const int idx = 3 - (int)(ch & 0xF);
+				const uint64_t shard = (ch >> 4) & 0xFFFF;
+				if (idx >= 0) {                                  /* (a negative shift is undefined in the reference) */
+					m_dfm_serial &= ~((uint64_t)0xFFFF << (16 * idx));
+					m_dfm_serial |= shard << (16 * idx);
+				}
+				if ((ch & 0xF) == 0) {
+					uint64_t v = m_dfm_serial;
+					while (v && !(v & 0xFFFF)) v >>= 16;
+					m_partial.fields |= DATA_SERIAL;
+					sprintf(m_partial.serial, "D%08ld", (long)v);
+				}
+			}
+		}
+	}
+
+	void dfm09_gps(const uint8_t *sf)
+	{
+		const uint8_t *d = sf + 1;
+		switch (sf[0]) {
+		case 0x00:
+			m_partial.fields |= DATA_SEQ;
+			m_partial.seq = (int)(uint32_t)tl::merge_bits(d + 3, 8);
+			break;
+		case 0x01:
+			m_dfm_tm.tm_sec = (int)(tl::merge_bits(d + 4, 16) / 1000);
+			break;
+		case 0x02:
+			m_partial.lat = (float)((int32_t)tl::merge_bits(d, 32) / 1e7);
+			m_partial.speed = (float)(tl::merge_bits(d + 4, 16) / 1e2);
+			break;
+		case 0x03:
+			m_partial.lon = (float)((int32_t)tl::merge_bits(d, 32) / 1e7);
+			m_partial.heading = (float)(tl::merge_bits(d + 4, 16) / 1e2);
+			break;
+		case 0x04:
+			m_partial.alt = (float)((int32_t)tl::merge_bits(d, 32) / 1e2);
+			m_partial.climb = (float)((int16_t)tl::merge_bits(d + 4, 16) / 1e2);
+			m_partial.fields |= DATA_POS | DATA_SPEED;
+			break;
+		case 0x08: {
+			const uint32_t raw = (uint32_t)tl::merge_bits(d, 32);
+			m_dfm_tm.tm_year = (int)((raw >> 20) & 0xFFF) - 1900;
+			m_dfm_tm.tm_mon = (int)((raw >> 16) & 0xF) - 1;
+			m_dfm_tm.tm_mday = (raw >> 11) & 0x1F;
+			m_dfm_tm.tm_hour = (raw >> 6) & 0x1F;
+			m_dfm_tm.tm_min = raw & 0x3F;
+			m_partial.fields |= DATA_TIME;
+			m_partial.time = tl::utc_seconds(&m_dfm_tm);
+			break;
+		}
+		default:
+			break;
+		}
+	}
+
+	/* ---- Meisei iMS-100 / RS-11G: 48 payload bytes + 24-bit validity mask (one bit per 16-bit word, MSB = word 0);
+	 * 64 calibration floats arrive one per frame, indexed by seq % 64 (ims100.c:129-346, ims100/parser.c) -------- */
+	static bool has(uint32_t valid, uint32_t mask) { return (valid & mask) == mask; }
+	static uint16_t be16u(const uint8_t *p) { return (uint16_t)(p[0] << 8 | p[1]); }
+	static int32_t be32s(const uint8_t *p) { return (int32_t)tl::be32(p); }
+
+	/* oscillator count ratio -> thermistor resistance polynomial -> spline over the calibration points */
+	static float meisei_temp(float cnt, float ref, const float *poly, const float *ohms, const float *temps, size_t n)
+	{
+		const float fc = (float)(4.0 * cnt / ref);
+		const float x = (float)(1.0 / (fc - 1.0));
+		const float r = poly[0] + poly[1] * x + poly[2] * x * x + poly[3] * x * x * x;
+		float lg[12];
+		for (size_t i = 0; i < n; i++) lg[i] = logf(ohms[i]);
+		const float t = tl::cubic_spline(lg, temps, (float)n, logf(r));
+		const float hi = (100 < t) ? 100 : t;
+		return (-100 > hi) ? -100 : hi;
+	}
+	static float meisei_rh(float cnt, float ref, const float *poly)
+	{
+		const float f = (float)(4.0 * cnt / ref);
+		return poly[0] + poly[1] * f + poly[2] * f * f + poly[3] * f * f * f;
+	}
+	static float clamp_pct(float v)
+	{
+		const float hi = (100 < v) ? 100 : v;
+		return (0 > hi) ? 0 : hi;
+	}
+	void meisei_common_head(const uint8_t *f, uint32_t valid, SondeData *dst, bool rs11g_frag)
+	{
+		if (has(valid, 0x800000)) {
+			dst->fields |= DATA_SEQ;
+			dst->seq = be16u(f);
+		}
+		if (has(valid, 0x800000 | 0x300000)) {
+			const int k = dst->seq % 64;
+			float coeff;
+			if (rs11g_frag) {
+				coeff = tl::mbf_le(f + 4);
+			} else {
+				const uint8_t swapped[4] = {f[6], f[7], f[4], f[5]};
+				coeff = tl::f32be(swapped);
+			}
+			m_ims_calib[k] = coeff;
+			m_ims_mask |= 1ULL << (63 - k);
+		}
+	}
+	void meisei_serial(SondeData *dst, const char *fmt)
+	{
+		if (dst->fields && (m_ims_mask & 0x8000000000000000ULL)) {
+			dst->fields |= DATA_SERIAL;
+			sprintf(dst->serial, fmt, (int)m_ims_calib[0]);
+		}
+	}
+
+	void ims100(const uint8_t *f, SondeData *dst)
+	{
+		uint32_t valid;
+		memcpy(&valid, f + 48, 4);
+		const float *cal = m_ims_calib;                        /* IMS100Calibration as 64 floats (ims100/protocol.h:155-176) */
+		meisei_common_head(f, valid, dst, false);
+		if (has(valid, 0x800000 | 0x460000)) {
+			m_adc_temp = be16u(f + 10);
+			switch (be16u(f) & 3) {                              /* two of the ADC slots are multiplexed by seq */
+			case 0: m_adc_ref = be16u(f + 2); m_adc_rh = be16u(f + 12); break;
+			case 1:
+			case 2: m_adc_rh = be16u(f + 12); break;
+			default: m_adc_rh_temp = be16u(f + 2); m_adc_ref = be16u(f + 12); break;
+			}
+			const float poly[4] = {cal[53] - cal[56], cal[54], cal[55], 0};
+			const float air = 1 + meisei_temp(m_adc_temp, m_adc_ref, poly, cal + 33, cal + 17, 12);
+			/* humidity sensor temperature: resistance -> Steinhart-Hart-like cubic in ln R */
+			const float fc = (float)(4.0 * m_adc_rh_temp / m_adc_ref);
+			float x = (float)(1.0 / (fc - 1.0));
+			const float r = poly[0] + poly[1] * x + poly[2] * x * x + poly[3] * x * x * x;
+			x = logf(r);
+			const float rh_t = 1 + (float)(1.0 / (cal[57] * x * x * x + cal[58] * x + cal[59]) - 273.15);
+			float rh = meisei_rh(m_adc_rh, m_adc_ref, cal + 49);
+			if (air < 100 && air > -100) rh *= tl::wv_sat_pressure(rh_t) / tl::wv_sat_pressure(air);
+			dst->fields |= DATA_PTU;
+			dst->temp = air;
+			dst->rh = clamp_pct(rh);
+			dst->pressure = 0;
+			dst->calib_percent = (float)(100.0 * __builtin_popcountll(m_ims_mask) / 64);
+		}
+		if ((f[14] << 8 | f[15]) == 0x30C1) {                    /* GPS page */
+			if (has(valid, 0x006000 | 0x001000)) {
+				dst->fields |= DATA_TIME;
+				dst->time = ims100_time(f);
+			}
+			if (has(valid, 0x000C00 | 0x000300 | 0x0000C0)) {
+				const int32_t la = be32s(f + 26), lo = be32s(f + 30);
+				const int32_t al = (int32_t)((uint32_t)f[34] << 24 | (uint32_t)f[35] << 16 | (uint32_t)f[36] << 8);
+				dst->fields |= DATA_POS;
+				dst->lat = (float)((int)(la / 1e6) + (la % 1000000 / 60.0 * 100.0) / 1e6);      /* NMEA ddmm.mmmm */
+				dst->lon = (float)((int)(lo / 1e6) + (lo % 1000000 / 60.0 * 100.0) / 1e6);
+				dst->alt = (float)((al >> 8) / 1e2);
+			}
+			if (has(valid, 0x000002 | 0x000004)) {
+				dst->fields |= DATA_SPEED;
+				dst->speed = (float)(be16u(f + 44) / 1.943844e2);                              /* knots * 100 */
+				dst->heading = (float)(abs((int16_t)be16u(f + 42)) / 1e2);
+				dst->climb = NAN;
+			}
+		}
+		if ((dst->fields & (DATA_POS | DATA_TIME)) == (DATA_POS | DATA_TIME)) {             /* climb from successive fixes */
+			if (dst->time > m_ims_prev_time) dst->climb = (dst->alt - m_ims_prev_alt) / (dst->time - m_ims_prev_time);
+			m_ims_prev_alt = dst->alt;
+			m_ims_prev_time = dst->time;
+		}
+		meisei_serial(dst, "IMS%d");
+	}
+
+	/* the frame carries day/month and the last digit of the year; the decade comes from the wall clock
+	 * (ims100/parser.c:18-41) */
+	static time_t ims100_time(const uint8_t *f)
+	{
+		const uint16_t date = be16u(f + 24), ms = be16u(f + 20);
+		time_t now = time(nullptr);
+		struct tm tm = *gmtime(&now);
+		const int unit = tm.tm_year % 10;
+		tm.tm_year -= unit;
+		tm.tm_year += date % 10 - (unit < date % 10 ? 10 : 0);
+		tm.tm_mon = (date / 10) % 100 - 1;
+		tm.tm_mday = date / 1000;
+		tm.tm_hour = f[22];
+		tm.tm_min = f[23];
+		tm.tm_sec = ms / 1000;
+		return tl::utc_seconds(&tm);
+	}
+
+	void rs11g(const uint8_t *f, SondeData *dst)
+	{
+		uint32_t valid;
+		memcpy(&valid, f + 48, 4);
+		const float *cal = m_ims_calib;                        /* RS11GCalibration as 64 floats (ims100/protocol.h:178-195) */
+		meisei_common_head(f, valid, dst, true);
+		if (has(valid, 0x800000 | 0x460000)) {
+			if ((be16u(f) & 3) == 0) m_adc_ref = be16u(f + 2);
+			m_adc_temp = be16u(f + 10);
+			m_adc_rh = be16u(f + 12);
+			const float air = meisei_temp(m_adc_temp, m_adc_ref, cal + 33, cal + 37, cal + 17, 11);
+			const float rh = meisei_rh(m_adc_rh, m_adc_ref, cal + 49);
+			/* temperature dependence of the humidity sensor (fit of the GRUAN TD-5 curves, parser.c:243-266) */
+			const float k[] = {5.79231318e-02, -2.64030081e-03, -1.32089353e-05, 7.15251769e-07,
+			                   -4.81000481e-04, 1.86628187e+00, -7.69600770e-01};
+			float corr = k[0] + k[1] * air + k[2] * air * air + k[3] * air * air * air;
+			corr *= k[4] + k[5] * rh / 100 + k[6] * rh / 100 * rh / 100;
+			dst->fields |= DATA_PTU;
+			dst->temp = air;
+			dst->rh = clamp_pct(rh + corr * 100);
+			dst->pressure = 0;
+			dst->calib_percent = (float)(100.0 * __builtin_popcountll(m_ims_mask) / 64);
+		}
+		switch (f[14] << 8 | f[15]) {
+		case 0x30A2:                                             /* position, velocity, date */
+			if (has(valid, 0x000600 | 0x000180 | 0x000060)) {
+				dst->fields |= DATA_POS;
+				dst->lat = (float)(be32s(f + 26) / 1e7);
+				dst->lon = (float)(be32s(f + 30) / 1e7);
+				dst->alt = (float)(be32s(f + 34) / 1e2);
+			}
+			if (has(valid, 0x000010 | 0x000008 | 0x000004)) {
+				dst->fields |= DATA_SPEED;
+				dst->speed = (float)(be16u(f + 38) / 1e2);
+				dst->heading = (float)(abs((int16_t)be16u(f + 40)) / 1e2);
+				dst->climb = (float)(abs((int16_t)be16u(f + 42)) / 1e2);
+			}
+			if (has(valid, 0x000003)) {
+				struct tm tm;
+				memset(&tm, 0, sizeof(tm));
+				tm.tm_year = f[45] + 0x700 - 1900;
+				tm.tm_mon = f[46] - 1;
+				tm.tm_mday = f[47];
+				m_ims_date = tl::utc_seconds(&tm);
+			}
+			break;
+		case 0x31A2:                                             /* time of day (ms is little endian on this page) */
+			if (has(valid, 0x006000)) {
+				const uint16_t ms = (uint16_t)(f[20] | f[21] << 8);
+				dst->fields |= DATA_TIME;
+				dst->time = m_ims_date + (f[22] * 3600 + f[23] * 60 + ms / 1000);
+			}
+			break;
+		default:
+			break;
+		}
+		meisei_serial(dst, "RS11G-%d");
+	}
+
 	int m_type;
 	SondeData m_partial;
+	uint32_t m_dfm_raw[16];
+	uint8_t m_dfm_serial_ch;
+	uint64_t m_dfm_serial;
+	struct tm m_dfm_tm;
+	float m_ims_calib[64];
+	uint64_t m_ims_mask;
+	time_t m_ims_date;
+	float m_ims_prev_alt;
+	time_t m_ims_prev_time;
+	uint16_t m_adc_ref, m_adc_temp, m_adc_rh, m_adc_rh_temp;
 	uint8_t m_mrz_calib[64];
 	uint8_t m_rs41_calib[816];
 	uint8_t m_rs41_have[7];

@@ -457,6 +457,121 @@ def random_frame_bits(stype: int, rng: np.random.Generator, index: int = 0) -> n
 
 
 # ----------------------------------------------------------------------------------------
+# telemetry "flights": consecutive frames with running counters and a complete calibration,
+# so that the host parsers' stateful paths (calibration assembly, serial shards, climb rate) run
+# ----------------------------------------------------------------------------------------
+
+def _mbf_le(x: float) -> bytes:
+    """float -> Microsoft binary format, little endian (inverse of SD/bitops.c:132-152)."""
+    u = int(np.float32(x).view(np.uint32))
+    sign, exp, man = u >> 31, (u >> 23) & 0xFF, u & 0x7FFFFF
+    return bytes([man & 0xFF, (man >> 8) & 0xFF, (sign << 7) | (man >> 16), (exp + 2) & 0xFF])
+
+
+def meisei_calibration(rs11g: bool) -> np.ndarray:
+    """64 plausible calibration floats laid out like IMS100Calibration / RS11GCalibration (ims100/protocol.h:155-195)."""
+    c = np.zeros(64, dtype=np.float32)
+    c[0] = 4120537.0 if not rs11g else 2310644.0                  # serial
+    if not rs11g:
+        c[17:29] = [60, 50, 40, 30, 20, 10, 0, -20, -40, -60, -75, -85]                  # temps
+        c[33:45] = [5.6, 7.9, 11.4, 16.9, 25.7, 40.2, 64.9, 187.0, 640.0, 2730.0, 9600.0, 24500.0]   # kOhm
+        c[49:53] = [-120.0, 310.0, -170.0, 35.0]                  # rh_poly
+        c[53:57] = [-3.2, 41.0, 2.5, 0.7]                         # temp_poly
+        c[57:60] = [2.1e-7, 2.9e-4, 1.9e-3]                       # rh_temp_poly
+    else:
+        c[17:28] = [40, 30, 20, 10, 0, -20, -40, -55, -65, -75, -85]
+        c[33:37] = [-2.9, 40.0, 2.0, 0.1]                         # temp_poly
+        c[37:48] = [11.4, 16.9, 25.7, 40.2, 64.9, 187.0, 640.0, 1900.0, 4300.0, 9600.0, 24500.0]
+        c[49:53] = [-110.0, 300.0, -160.0, 30.0]
+    return c
+
+
+def meisei_flight_bits(rs11g: bool, n_frames: int, rng: np.random.Generator, seq0: int = 0) -> np.ndarray:
+    cal = meisei_calibration(rs11g)
+    out = []
+    for k in range(n_frames):
+        seq = seq0 + k
+        p = bytearray(rng.integers(0, 256, 48, dtype=np.uint8))
+        p[0:2] = seq.to_bytes(2, "big")
+        if rs11g:
+            p[4:8] = _mbf_le(float(cal[seq % 64]))
+        else:
+            b = np.float32(cal[seq % 64]).view(np.uint32).item().to_bytes(4, "big")
+            p[4:8] = bytes([b[2], b[3], b[0], b[1]])
+        ref = 31000 + int(rng.integers(0, 50))
+        p[10:12] = int(rng.integers(9000, 22000)).to_bytes(2, "big")                      # temperature count
+        if rs11g or seq % 4 != 3:
+            p[2:4] = ref.to_bytes(2, "big")
+            p[12:14] = int(rng.integers(9000, 14000)).to_bytes(2, "big")                  # humidity count
+        else:
+            p[2:4] = int(rng.integers(9000, 22000)).to_bytes(2, "big")                    # humidity-sensor temperature
+            p[12:14] = ref.to_bytes(2, "big")
+        p[14] = 0x30 if k % 2 == 0 else 0x31
+        p[15] = 0xA2 if rs11g else 0xC1
+        if not rs11g and p[14] == 0x30:
+            p[20:22] = int((k % 60) * 1000).to_bytes(2, "big")
+            p[22], p[23] = 11, (k // 60) % 60
+            p[24:26] = (17 * 1000 + 10 * 10 + 6).to_bytes(2, "big")                       # 17 Oct, year ...6
+            p[26:30] = (35123456 + 20 * k).to_bytes(4, "big")
+            p[30:34] = (139456789 + 31 * k).to_bytes(4, "big")
+            p[34:37] = (120000 + 550 * k).to_bytes(3, "big")
+        elif rs11g and p[14] == 0x30:
+            p[26:30] = (351234560 + 200 * k).to_bytes(4, "big")
+            p[30:34] = (1394567890 + 310 * k).to_bytes(4, "big")
+            p[34:38] = (120000 + 550 * k).to_bytes(4, "big")
+            p[45], p[46], p[47] = (2026 - 0x700) & 0xFF, 10, 17
+        elif rs11g:
+            p[20:22] = int((k % 60) * 1000).to_bytes(2, "little")
+            p[22], p[23] = 11, (k // 60) % 60
+        out.append(ims100_raw_bits(bytes(p)))
+    return np.concatenate(out)
+
+
+def dfm_flight_bits(n_frames: int, rng: np.random.Generator, dfm06: bool = False) -> np.ndarray:
+    """PTU channels cycle 0..7 (channel 6 all zero, channel 7 = serial shards), GPS slots cycle through 0,1 / 2,3 / 4,8."""
+    out = []
+    serial = 0x0017_4C2B
+    zero_ch = 5 if dfm06 else 6
+    for k in range(n_frames):
+        t = k % 8
+        if t == 0:
+            ptu = bytes([0x25, 0x13, 0x40 + k % 16])                 # thermistor reading
+        elif t in (3, 4):
+            ptu = bytes([0x27 if t == 3 else 0x2B, 0x10 + t, 0x55])  # the two reference channels
+        elif t == zero_ch:
+            ptu = bytes([0x40, 0, 0])                                # low 16 bits zero: the serial follows
+        elif t == zero_ch + 1:
+            if dfm06:
+                ptu = bytes([0x00, 0x61, 0x23])
+            else:
+                shard_idx = (k // 8) % 2
+                shard = (serial >> (16 * (1 - shard_idx))) & 0xFFFF
+                ptu = ((shard << 4) | shard_idx).to_bytes(3, "big")
+        else:
+            ptu = bytes(rng.integers(1, 256, 3, dtype=np.uint8))
+        ptu_type = t
+        pairs = [(0, 1), (2, 3), (4, 8)][k % 3]
+        gps = []
+        for g in pairs:
+            if g == 0:
+                d = bytes([0, 0, 0, k & 0xFF, 0, 0])
+            elif g == 1:
+                d = bytes([0, 0, 0, 0]) + int((k % 60) * 1000).to_bytes(2, "big")
+            elif g == 2:
+                d = (481234567 + 35 * k).to_bytes(4, "big") + (1234 + k).to_bytes(2, "big")
+            elif g == 3:
+                d = (116543210 + 51 * k).to_bytes(4, "big") + (9000 + 7 * k).to_bytes(2, "big")
+            elif g == 4:
+                d = (1500000 + 480 * k).to_bytes(4, "big") + ((520 - 3 * k) & 0xFFFF).to_bytes(2, "big")
+            else:
+                raw = (2026 << 20) | (10 << 16) | (17 << 11) | (11 << 6) | (k // 60 % 60)
+                d = raw.to_bytes(4, "big") + bytes([0, 0])
+            gps.append((g, d))
+        out.append(dfm_raw_bits(ptu_type, ptu, gps))
+    return np.concatenate(out)
+
+
+# ----------------------------------------------------------------------------------------
 # modulation
 # ----------------------------------------------------------------------------------------
 
@@ -498,9 +613,12 @@ class ChannelSpec:
     n_distinct_frames: int = 4
     bit_errors: int = 0          # random raw-bit flips per frame (FEC exercise)
     gap_bits: int = 0            # idle bits between frames
+    custom_bits: np.ndarray | None = None   # on-air bits to send instead of the random frames (telemetry "flights")
 
 
 def channel_bits(spec: ChannelSpec) -> np.ndarray:
+    if spec.custom_bits is not None:
+        return spec.custom_bits
     rng = np.random.default_rng(spec.seed)
     frames = []
     for k in range(spec.n_distinct_frames):

@@ -16,10 +16,34 @@ sys.path.insert(0, ROOT)
 SECONDS = {0: 8.0, 1: 6.0, 2: 5.0, 3: 8.0, 4: 8.0, 5: 8.0, 6: 4.0}
 
 
-def cases(ref, synth, stype, channel=3, chunk=48000):
+def flight_spec(synth, name):
+    """Consecutive frames with running counters and complete calibration (synth.*_flight_bits)."""
     import numpy as np
-    n = int(48000 * SECONDS[stype])
-    fm = synth.make_fm(synth.default_spec(stype, channel), n)
+    rng = np.random.default_rng(0xF11687)
+    if name == "dfm09_flight":
+        stype, bits, frames = synth.DFM09, synth.dfm_flight_bits(48, rng), 48
+    elif name == "dfm06_flight":
+        stype, bits, frames = synth.DFM09, synth.dfm_flight_bits(24, rng, dfm06=True), 24
+    elif name == "ims100_flight":
+        stype, bits, frames = synth.IMS100, synth.meisei_flight_bits(False, 72, rng, seq0=60), 72
+    else:
+        stype, bits, frames = synth.IMS100, synth.meisei_flight_bits(True, 72, rng, seq0=3), 72
+    spec = synth.ChannelSpec(stype, 0xF1, snr_db=30.0, custom_bits=bits)
+    n = int(48000 * (frames + 1.5) * synth.MODEMS[stype].frame_bits / synth.MODEMS[stype].baud)
+    return stype, spec, n
+
+
+FLIGHTS = ("dfm09_flight", "dfm06_flight", "ims100_flight", "rs11g_flight")
+
+
+def cases(ref, synth, stype, channel=3, chunk=48000, flight=None):
+    import numpy as np
+    if flight:
+        stype, spec, n = flight_spec(synth, flight)
+        fm = synth.make_fm(spec, n)
+    else:
+        n = int(48000 * SECONDS[stype])
+        fm = synth.make_fm(synth.default_spec(stype, channel), n)
     recs = ref.frames_run(stype, fm, chunk)
     sd, _ = ref.decode_run(stype, fm, chunk)
     assert len(recs) == len(sd), (stype, len(recs), len(sd))
@@ -40,6 +64,10 @@ def main():
         out[synth.TYPE_NAMES[stype]] = cases(ref, synth, stype)
         c = out[synth.TYPE_NAMES[stype]]
         print(synth.TYPE_NAMES[stype], len(c), sum(1 for x in c if int.from_bytes(bytes.fromhex(x["sonde_data_hex"])[:4], "little")))
+    for name in FLIGHTS:
+        out[name] = cases(ref, synth, None, flight=name)
+        c = out[name]
+        print(name, len(c), sum(1 for x in c if int.from_bytes(bytes.fromhex(x["sonde_data_hex"])[:4], "little")))
     with open(os.path.join(HERE, "telemetry.json"), "w") as f:
         json.dump(out, f)
 
