@@ -115,7 +115,8 @@ typedef struct {
 	float   fm_gain;          /* discriminator gain (1/deviation); 0 -> 2/pi, i.e.
 	                             dsp::demod::FM(samplerate=bw, bandwidth=bw/2)  src/main.cpp:57 */
 	int32_t keep_soft;        /* !=0: keep soft symbols for sonde_b200_fetch_soft()  */
-	int32_t reserved;         /* bit 0: use the phase-by-phase demod kernel (cross-check only); bit 1: never stage with TMA */
+	int32_t reserved;         /* bit 0: use the phase-by-phase demod kernel (cross-check only); bit 1: never stage with TMA;
+	                             bit 2: alternative warp placement of the AFSK pipeline kernel (diagnostics) */
 } sonde_b200_config;
 
 SONDE_API int  sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg);

@@ -166,13 +166,13 @@ class BatchDecoder:
     """
 
     def __init__(self, types, max_chunk_len, samplerate=48000, device=0, fm_gain=0.0, keep_soft=False,
-                 legacy_kernel=False, no_tma=False):
+                 legacy_kernel=False, no_tma=False, afsk_layout=0):
         self.lib = load()
         self.types = np.ascontiguousarray(types, dtype=np.int32)
         self.C = int(self.types.size)
         self.max_chunk_len = int(max_chunk_len)
         cfg = Config(self.C, samplerate, self.max_chunk_len, device, _i32p(self.types), fm_gain,
-                     1 if keep_soft else 0, (1 if legacy_kernel else 0) | (2 if no_tma else 0))
+                     1 if keep_soft else 0, (1 if legacy_kernel else 0) | (2 if no_tma else 0) | (4 if afsk_layout else 0))
         h = ctypes.c_void_p()
         rc = self.lib.sonde_b200_create(ctypes.byref(h), ctypes.byref(cfg))
         if rc != SONDE_OK:

@@ -26,8 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "device_state.h"
-#include "strict_math.cuh"
+#include "pipe_common.cuh"
 #include "timing_round.cuh"
 
 static __constant__ sonde_modem c_modem[SONDE_NTYPES_];
@@ -39,11 +38,8 @@ extern "C" cudaError_t sonde_upload_modems_pipe(const sonde_modem *m)
 
 namespace {
 
-constexpr int G = 8;                     /* channels per CTA                       */
-constexpr int T = 256;                   /* samples per tile                       */
-constexpr int NPW = 16;                  /* parallel-work warps                    */
-constexpr int NPWT = NPW * 32;           /* PW threads                             */
-constexpr int CPT = G * T / NPWT;        /* channels per PW thread in S1 / S3 (one sample column each) */
+using namespace pipe;
+
 /* Warp roles by scheduler (warp id % 4).  The serial lanes are latency-bound (IPC ~0.3) and lose issue slots
  * to any PW warp on their scheduler.  Two placements, picked per kernel variant from measurements
  * (tools/stalls.py):
@@ -75,16 +71,6 @@ struct roles<1> {
 		return r == 0 ? q : r == 1 ? 6 + q : 11 + q;
 	}
 };
-constexpr int RS = T + 4;                /* row stride: 16 B aligned, lanes (= rows) hit distinct banks */
-constexpr int AS = SONDE_FIR_HIST + T + 4;
-constexpr int R = G * T / NPWT;           /* FIR outputs per thread                 */
-constexpr int SEGS = T / R;              /* FIR segments per channel row           */
-constexpr int NX = 3, NS2 = 2;           /* ring depths                            */
-constexpr unsigned FULL = 0xffffffffu;
-
-static_assert(NPWT % T == 0 && CPT * (NPWT / T) == G && R % 4 == 0 && SEGS % 32 == 0 && (SEGS / 32) * G == NPW,
-              "thread <-> work mappings below rely on this");
-
 template <int P>
 struct smem_t {
 	float x[NX][G][RS];                  /* discriminator output / FM input          */
@@ -102,113 +88,6 @@ struct smem_t {
 	int chan[G], row[G];
 	unsigned long long xfull[NX], sfull[NS2], sfree[NS2], vfull[NS2], vfree[NS2], yfull[NS2], yfree[NS2];
 };
-
-/* ---- mbarrier helpers (CTA scope) --------------------------------------------------------- */
-__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *b, int count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *b)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity)
-{
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"W_%=:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra D_%=;\n"
-		"bra W_%=;\n"
-		"D_%=:\n"
-		"}\n" ::"r"(s32(b)), "r"(parity) : "memory");
-}
-/* wait that charges the stalled cycles to a diagnostics counter */
-__device__ __forceinline__ void mbar_wait_t(unsigned long long *b, uint32_t parity, long long &acc, bool on)
-{
-	if (!on) { mbar_wait(b, parity); return; }
-	const long long t0 = clock64();
-	mbar_wait(b, parity);
-	acc += clock64() - t0;
-}
-/* TMA: one elected thread starts a bulk global->shared copy whose completion is signalled on an mbarrier
- * (cp.async.bulk, SASS UBLKCP).  Addresses and size must be multiples of 16 bytes. */
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *b)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             ::"r"(s32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(s32(b)) : "memory");
-}
-/* all lanes of a warp finished their writes -> one arrival */
-__device__ __forceinline__ void warp_arrive(unsigned long long *b, int lane)
-{
-	__syncwarp();
-	if (lane == 0) mbar_arrive(b);
-}
-__device__ __forceinline__ void pw_barrier()
-{
-	asm volatile("bar.sync 1, %0;" ::"n"(NPWT) : "memory");
-}
-
-/* ---- S4: FIR at R consecutive positions, reference summation order (filter.c:59-61) ----------
- * Two neighbouring outputs share one packed fp32x2 multiply and one packed add (sm_100 FMUL2/FADD2,
- * round-to-nearest per lane, never fused), which halves the issue slots of the dominant loop. */
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
-{
-	unsigned long long r;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-	return r;
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
-{
-	unsigned long long r;
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-	return r;
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
-{
-	unsigned long long r;
-	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-	return r;
-}
-
-template <int P>
-__device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS], const float2 *taps2,
-                                            const unsigned long long negzero2, int g, int seg)
-{
-	float w[R + SONDE_FIR_HIST];
-	const float4 *src = reinterpret_cast<const float4 *>(arow + seg * R);
-#pragma unroll
-	for (int k = 0; k < (R + SONDE_FIR_HIST) / 4; k++) {
-		const float4 q = src[k];
-		w[4 * k + 0] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
-	}
-#pragma unroll
-	for (int br = 0; br < P; br++) {
-		unsigned long long acc[R / 2];
-#pragma unroll
-		for (int r = 0; r < R / 2; r++) acc[r] = 0ull;                 /* (+0, +0) */
-#pragma unroll
-		for (int i = 0; i < SONDE_FIR_TAPS; i++) {
-			const unsigned long long c = reinterpret_cast<const unsigned long long *>(taps2)[br * SONDE_FIR_TAPS + i];
-#pragma unroll
-			for (int r = 0; r < R / 2; r++) {
-				/* a*c + (-0) == fl(a*c): the product rounded once, then the reference's add */
-				const unsigned long long prod = fma2(pack2(w[2 * r + i], w[2 * r + i + 1]), c, negzero2);
-				acc[r] = add2(acc[r], prod);
-			}
-		}
-		unsigned long long *dst = reinterpret_cast<unsigned long long *>(&y[br][g][seg * R]);
-#pragma unroll
-		for (int r = 0; r < R / 2; r++) dst[r] = acc[r];
-	}
-}
 
 template <int P, int N, bool IQ, bool SOFT, int LAYOUT, bool TMA>
 __global__ void __launch_bounds__(roles<LAYOUT>::NWARPS * 32, 1)

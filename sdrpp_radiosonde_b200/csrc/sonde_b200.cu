@@ -24,6 +24,9 @@ extern "C" cudaError_t sonde_upload_gf_tables(void);
 extern "C" cudaError_t sonde_launch_demod_gfsk(const demod_params *p, int group_base, int n_groups, int phases,
                                                cudaStream_t stream);
 extern "C" cudaError_t sonde_upload_modems_pipe(const sonde_modem *m);
+extern "C" cudaError_t sonde_upload_modems_afsk_pipe(const sonde_modem *m);
+extern "C" cudaError_t sonde_launch_demod_pipe_afsk(const demod_params *p, int group_base, int n_groups, int layout,
+                                                    cudaStream_t stream);
 extern "C" cudaError_t sonde_launch_demod_pipe(const demod_params *p, int group_base, int n_groups, int phases,
                                               cudaStream_t stream);
 extern "C" cudaError_t sonde_launch_demod_afsk(const demod_params *p, int group_base, int n_groups,
@@ -179,6 +182,7 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	if (sonde_upload_modems(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_frame(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (sonde_upload_modems_afsk_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_gf_tables() != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
@@ -377,7 +381,8 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 		if (h->groups_v[v]) {
 			cudaStream_t st = fork ? h->vstream[v] : h->stream;
 			if (fork) CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
-			if (v == 3)                    CK(sonde_launch_demod_afsk(&dp, base, h->groups_v[v], st));
+			if (v == 3 && (h->cfg.reserved & 1)) CK(sonde_launch_demod_afsk(&dp, base, h->groups_v[v], st));
+			else if (v == 3)               CK(sonde_launch_demod_pipe_afsk(&dp, base, h->groups_v[v], (h->cfg.reserved >> 2) & 1, st));
 			else if (h->cfg.reserved & 1)  CK(sonde_launch_demod_gfsk(&dp, base, h->groups_v[v], v == 2 ? 2 : 1, st));
 			else                           CK(sonde_launch_demod_pipe(&dp, base, h->groups_v[v], v, st));
 			h->launches++;

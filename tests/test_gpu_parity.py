@@ -113,6 +113,29 @@ def test_pipeline_kernel_equals_phase_by_phase_kernel(kind):
         assert np.array_equal(a["state"].view(np.uint32), b["state"].view(np.uint32))
 
 
+@pytest.mark.parametrize("kind", ["fm", "iq"])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_afsk_pipeline_kernel_equals_phase_by_phase_kernel(kind, layout):
+    """AFSK: the warp-specialised pipeline (demod_pipe_afsk.cu) and the phase-by-phase kernel (demod.cu) use the
+    same libm restatements (double sincos, glibc-style cabsf), so bits, soft symbols and the final loop state
+    must agree bit for bit — at chunk sizes that exercise full, ragged and sub-boxcar-length tiles."""
+    types = [synth.IMET4, synth.C50, synth.C50, synth.IMET4, synth.IMET4, synth.C50, synth.IMET4,
+             synth.IMET4, synth.IMET4, synth.IMET4, synth.C50]
+    n = 48000 + 333
+    mk = synth.make_fm if kind == "fm" else synth.make_iq
+    batch = np.stack([mk(synth.default_spec(t, c), n) for c, t in enumerate(types)])
+    batch[3, 1000:1300] = 0          # exact-zero run: AGC bypass (agc.c:23) inside the AFSK chain
+    for chunk in (48333, 5000, 255, 17):
+        a = run_gpu(types, batch, chunk, kind=kind, keep_soft=True, want_bits=True, afsk_layout=layout)
+        b = run_gpu(types, batch, chunk, kind=kind, keep_soft=True, want_bits=True, legacy_kernel=True)
+        for c in range(len(types)):
+            assert np.array_equal(a["bits"][c], b["bits"][c]), (chunk, c)
+            assert np.array_equal(a["soft"][c].view(np.uint32), b["soft"][c].view(np.uint32)), (chunk, c)
+            assert [rec_key(g, 75) for g in a["frames"][c]] == [rec_key(w, 75) for w in b["frames"][c]], (chunk, c)
+        assert np.array_equal(a["state"].view(np.uint32), b["state"].view(np.uint32))
+        assert sum(int(r["ok"]) for f in a["frames"] for r in f) > 0
+
+
 @pytest.mark.parametrize("stype", GFSK_TYPES)
 def test_iq_path_matches_oracle(stype):
     """IQ entry point: discriminator (deterministic fp32, shared definition) + chain vs the C restatement."""
