@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--seconds", type=int, default=10, help="seconds of signal per channel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scatter", action="store_true", help="N > 1: skip the rank-0 -> all scatter measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -320,10 +321,47 @@ def main():
         for pb in pins:
             pb.free()
 
+    # N > 1: the one exchange step the path can have — the whole batch originates on rank 0 and is
+    # scattered over NVLink chunk by chunk, double-buffered against the decode.  Reported beside the main number,
+    # which is measured with every rank's shard already resident.
+    scatter = None
+    if world > 1 and not args.no_scatter:
+        from sdrpp_radiosonde_b200 import shard
+        n_sc = 6
+        full = [dev_iq[k].repeat(world, 1) for k in range(2)] if rank == 0 else [None, None]
+        bufs = [torch.empty((C, L), dtype=torch.complex64, device="cuda") for _ in range(2)]
+        dec3 = capi.BatchDecoder(types, L, device=local_rank)
+        shard.scatter_channels(full[0], bufs[0], world, rank)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_sc):
+            dec3.sync()                                   # decode(i-1) no longer reads bufs[(i+1) % 2]
+            works = shard.scatter_channels(full[(i + 1) % 2], bufs[(i + 1) % 2], world, rank, async_op=True) \
+                if i + 1 < n_sc else []
+            dec3.process_iq_device(bufs[i % 2].data_ptr(), L)      # overlaps the scatter of the next chunk
+            for w in works:
+                w.wait()
+            torch.cuda.current_stream().synchronize()
+        dec3.sync()
+        barrier()
+        t_sc = time.perf_counter() - t0
+        # scatter alone
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_sc):
+            shard.scatter_channels(full[i % 2], bufs[i % 2], world, rank)
+            torch.cuda.current_stream().synchronize()
+        barrier()
+        t_so = time.perf_counter() - t0
+        scatter = {"t": t_sc, "t_only": t_so, "n": n_sc}
+        dec3.close()
+        del full, bufs
+
     stop.set()
     th.join(timeout=2)
 
-    t_all = torch.tensor([ms, (e2e["t"] * 1e3) if e2e else 0.0], dtype=torch.float64, device="cuda")
+    t_all = torch.tensor([ms, (e2e["t"] * 1e3) if e2e else 0.0, scatter["t"] * 1e3 if scatter else 0.0,
+                          scatter["t_only"] * 1e3 if scatter else 0.0], dtype=torch.float64, device="cuda")
     tot = torch.tensor([frames, ok], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
@@ -367,6 +405,13 @@ def main():
             line["e2e"] = {"value": world * args.steps * C * L / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "ms_per_step": e2e_ms_max / args.steps}
+        if scatter:
+            sc_ms, so_ms = float(t_all[2]) / scatter["n"], float(t_all[3]) / scatter["n"]
+            line["scatter"] = {"what": "batch resident on rank 0, NCCL send/recv of each rank's [C][L] complex64 block per chunk, "
+                                       "double-buffered against the decode",
+                               "ms_per_step_with_scatter": sc_ms, "value_with_scatter": world * C * L / (sc_ms * 1e-3) / 1e6,
+                               "scatter_only_ms": so_ms,
+                               "rank0_egress_gbs": (world - 1) * C * L * 8 / (so_ms * 1e-3) / 1e9}
         if not args.no_cpu_baseline:
             cpu = CpuPath()
             n_ch = 2 * ncores

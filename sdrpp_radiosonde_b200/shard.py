@@ -3,7 +3,9 @@
 Channels share nothing (one decoder object per channel in the reference: src/main.hpp:36-42,
 SD/decode.c:24-30), so the only multi-GPU step is the partition itself: rank r of W owns the contiguous
 block [r*C/W, (r+1)*C/W).  No collective sits on the data path; frame counts are
-gathered with one small all_gather for reporting.
+gathered with one small all_gather for reporting.  When the whole channel batch originates on one rank
+(one SDR front end feeding the box), scatter_channels() hands every rank its block with point-to-point
+sends (NCCL over NVLink on the GPU box) — the only exchange step the path has.
 """
 from __future__ import annotations
 
@@ -40,6 +42,41 @@ def gather_counts(local_counts: np.ndarray, n_channels: int, world: int, rank: i
     out = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(out, mine)
     return np.concatenate([o[: sizes[r]].cpu().numpy() for r, o in enumerate(out)])
+
+
+def scatter_channels(full, out, world: int, rank: int, src: int = 0, async_op: bool = False):
+    """Scatter the channel batch `full[C][L]` held by rank `src` so that every rank gets its shard_range()
+    block in `out[(hi-lo)][L]` (torch tensors on the backend's device; complex64 is sent as float pairs).
+
+    Blocks are contiguous row ranges, so each transfer is one send of a view, no staging copy; shards may
+    differ by one channel, hence point-to-point sends rather than dist.scatter (equal sizes only).
+    Returns the list of outstanding work handles when async_op is set (wait on them before using `out`),
+    which lets the caller overlap the scatter of chunk i+1 with the decode of chunk i."""
+    import torch
+    import torch.distributed as dist
+
+    def as_real(t):
+        return torch.view_as_real(t) if t.is_complex() else t
+
+    if world == 1:
+        out.copy_(full)
+        return []
+    works = []
+    if rank == src:
+        C = full.shape[0]
+        for r in range(world):
+            lo, hi = shard_range(C, world, r)
+            if r == src:
+                out.copy_(full[lo:hi])
+            elif hi > lo:
+                works.append(dist.isend(as_real(full[lo:hi]), dst=r))
+    elif out.shape[0] > 0:
+        works.append(dist.irecv(as_real(out), src=src))
+    if async_op:
+        return works
+    for w in works:
+        w.wait()
+    return []
 
 
 class AutoPlan:

@@ -33,6 +33,18 @@ def _worker(rank, world, port, C, q):
     # every rank "decodes" its own shard: count = global channel index * 10 + type
     local = np.array([c * 10 + types[c] for c in range(lo, hi)], dtype=np.int64)
     allc = shard.gather_counts(local, C, world, rank)
+    # the batch originates on rank 0: scatter [C][L] complex64, every rank must end up with its own rows
+    import torch
+    L = 5
+    full = (torch.arange(C * L, dtype=torch.float32).reshape(C, L) * (1 + 2j)).to(torch.complex64) if rank == 0 else None
+    mine_iq = torch.zeros((hi - lo, L), dtype=torch.complex64)
+    shard.scatter_channels(full, mine_iq, world, rank)
+    want_iq = (torch.arange(C * L, dtype=torch.float32).reshape(C, L) * (1 + 2j)).to(torch.complex64)[lo:hi]
+    assert torch.equal(mine_iq, want_iq)
+    works = shard.scatter_channels(full, mine_iq.zero_(), world, rank, async_op=True)
+    for w in works:
+        w.wait()
+    assert torch.equal(mine_iq, want_iq)
     q.put((rank, allc.tolist()))
     dist.barrier()
     dist.destroy_process_group()
