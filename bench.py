@@ -320,6 +320,32 @@ def main():
         dec2.close()
         for pb in pins:
             pb.free()
+        # the same loop through the int16 entry point (half the PCIe bytes; informational, `e2e` stays complex64)
+        pins16 = [capi.PinnedBuffer((C, L, 2), np.int16) for _ in range(nbuf)]
+        for k, pb in enumerate(pins16):
+            blk = host_iq[:, k * L:(k + 1) * L]
+            pb.array[..., 0] = np.clip(np.round(blk.real * 16384.0), -32768, 32767)
+            pb.array[..., 1] = np.clip(np.round(blk.imag * 16384.0), -32768, 32767)
+        dec4 = capi.BatchDecoder(types, L, device=local_rank)
+        for i in range(2):
+            dec4.process_s16_host_ptr(pins16[i % nbuf].ptr, L)
+            dec4.fetch()
+        barrier()
+        t0 = time.perf_counter()
+        ok16 = 0
+        dec4.process_s16_host_ptr(pins16[0].ptr, L)
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                dec4.process_s16_host_ptr(pins16[(i + 1) % nbuf].ptr, L)
+            recs, counts = dec4.fetch()
+            ok16 += int(sum(int(recs[c, j]["ok"]) for c in range(0, C, 64) for j in range(counts[c])))
+        torch.cuda.synchronize()
+        dec4.sync()
+        e2e["t16"] = time.perf_counter() - t0
+        e2e["ok16"] = ok16
+        dec4.close()
+        for pb in pins16:
+            pb.free()
 
     # N > 1: the one exchange step the path can have — the whole batch originates on rank 0 and is
     # scattered over NVLink chunk by chunk, double-buffered against the decode.  Reported beside the main number,
@@ -361,7 +387,8 @@ def main():
     th.join(timeout=2)
 
     t_all = torch.tensor([ms, (e2e["t"] * 1e3) if e2e else 0.0, scatter["t"] * 1e3 if scatter else 0.0,
-                          scatter["t_only"] * 1e3 if scatter else 0.0], dtype=torch.float64, device="cuda")
+                          scatter["t_only"] * 1e3 if scatter else 0.0, (e2e["t16"] * 1e3) if e2e else 0.0],
+                         dtype=torch.float64, device="cuda")
     tot = torch.tensor([frames, ok], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
@@ -405,6 +432,12 @@ def main():
             line["e2e"] = {"value": world * args.steps * C * L / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "ms_per_step": e2e_ms_max / args.steps}
+            t16 = float(t_all[4])
+            line["e2e_s16"] = {"value": world * args.steps * C * L / (t16 * 1e-3) / 1e6, "unit": UNIT,
+                               "h2d_bytes_per_step": C * L * 4, "ms_per_step": t16 / args.steps,
+                               "note": "same loop through sonde_b200_process_iq_s16 (int16 IQ quantised from the same "
+                                       "signals, converted on the GPU); informational — `e2e` is the complex64 entry point",
+                               "decodable_frames_sampled": e2e["ok16"]}
         if scatter:
             sc_ms, so_ms = float(t_all[2]) / scatter["n"], float(t_all[3]) / scatter["n"]
             line["scatter"] = {"what": "batch resident on rank 0, NCCL send/recv of each rank's [C][L] complex64 block per chunk, "

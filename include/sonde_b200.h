@@ -127,6 +127,12 @@ SONDE_API void sonde_b200_destroy(sonde_b200 *h);
 SONDE_API int  sonde_b200_process_iq(sonde_b200 *h, const float *iq /*[C][len][2]*/, size_t len);
 SONDE_API int  sonde_b200_process_fm(sonde_b200 *h, const float *fm /*[C][len]*/,    size_t len);
 
+/* 16-bit IQ as SDR hardware delivers it (interleaved I,Q int16): sample = (float)i16 * scale, which is exact for a
+ * power-of-two scale, so the result equals sonde_b200_process_iq() on the converted floats bit for bit.  Halves
+ * the bytes crossing PCIe — the bound of the host entry points (the complex64 path replaces what SDR++ hands the
+ * plugin, src/main.cpp:55-57; this one is for callers that own the front end).  The conversion runs on the GPU. */
+SONDE_API int  sonde_b200_process_iq_s16(sonde_b200 *h, const int16_t *iq /*[C][len][2]*/, size_t len, float scale);
+
 /* Device-buffer entry points (inputs already resident in HBM). row_stride in samples. */
 SONDE_API int  sonde_b200_process_iq_device(sonde_b200 *h, const void *d_iq, size_t len, size_t row_stride);
 SONDE_API int  sonde_b200_process_fm_device(sonde_b200 *h, const void *d_fm, size_t len, size_t row_stride);

@@ -22,7 +22,7 @@ _ERR_NAMES = {ERR_ARG: "SONDE_ERR_ARG", ERR_CUDA: "SONDE_ERR_CUDA", ERR_NODEVICE
 # every symbol include/sonde_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
     "sonde_b200_create", "sonde_b200_destroy", "sonde_b200_process_iq", "sonde_b200_process_fm",
-    "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
+    "sonde_b200_process_iq_s16", "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
     "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_detected_types", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
     "sonde_b200_soft_stride", "sonde_b200_fetch_soft", "sonde_b200_fetch_state", "sonde_b200_modem_info",
     "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
@@ -86,6 +86,7 @@ def load():
         "sonde_b200_destroy": (None, [vp]),
         "sonde_b200_process_iq": (ctypes.c_int, [vp, vp, sz]),
         "sonde_b200_process_fm": (ctypes.c_int, [vp, vp, sz]),
+        "sonde_b200_process_iq_s16": (ctypes.c_int, [vp, vp, sz, ctypes.c_float]),
         "sonde_b200_process_iq_device": (ctypes.c_int, [vp, vp, sz, sz]),
         "sonde_b200_process_fm_device": (ctypes.c_int, [vp, vp, sz, sz]),
         "sonde_b200_max_frames": (ctypes.c_int, [vp]),
@@ -213,6 +214,15 @@ class BatchDecoder:
         iq = np.ascontiguousarray(iq, dtype=np.complex64)
         assert iq.ndim == 2 and iq.shape[0] == self.C, iq.shape
         self._ck(self.lib.sonde_b200_process_iq(self.h, iq.ctypes.data, iq.shape[1]))
+
+    def process_iq_s16(self, iq16: np.ndarray, scale: float = 1.0 / 32768.0):
+        """iq16: [C][len][2] int16 (interleaved I, Q); sample = int16 * scale."""
+        iq16 = np.ascontiguousarray(iq16, dtype=np.int16)
+        assert iq16.ndim == 3 and iq16.shape[0] == self.C and iq16.shape[2] == 2
+        self._ck(self.lib.sonde_b200_process_iq_s16(self.h, iq16.ctypes.data, iq16.shape[1], ctypes.c_float(scale)))
+
+    def process_s16_host_ptr(self, ptr: int, length: int, scale: float = 1.0 / 32768.0):
+        self._ck(self.lib.sonde_b200_process_iq_s16(self.h, ptr, length, ctypes.c_float(scale)))
 
     def process_host_ptr(self, ptr: int, length: int, is_iq=True):
         fn = self.lib.sonde_b200_process_iq if is_iq else self.lib.sonde_b200_process_fm

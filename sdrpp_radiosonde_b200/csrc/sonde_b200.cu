@@ -74,6 +74,7 @@ struct sonde_b200 {
 	float *d_soft = nullptr;
 	int max_frames = 0, soft_stride = 0, bits_stride = 0;
 	void *d_in[2] = {nullptr, nullptr};   /* staging for the host-buffer entry points */
+	void *d_in16[2] = {nullptr, nullptr}; /* raw int16 IQ staging of sonde_b200_process_iq_s16 */
 	int32_t *h_counts = nullptr;     /* pinned */
 	long long *d_prof = nullptr;     /* diagnostics: per-CTA stall counters of the pipeline kernel */
 
@@ -309,7 +310,7 @@ void sonde_b200_destroy(sonde_b200 *h)
 	cudaFree(h->d_demod); cudaFree(h->d_afsk); cudaFree(h->d_framer); cudaFree(h->d_ring);
 	cudaFree(h->d_prof); cudaFree(h->d_in_row); cudaFree(h->d_active);
 	for (int b = 0; b < 2; b++) {
-		cudaFree(h->d_recs[b]); cudaFree(h->d_counts[b]); cudaFree(h->d_in[b]); cudaFree(h->d_nbits[b]);
+		cudaFree(h->d_recs[b]); cudaFree(h->d_counts[b]); cudaFree(h->d_in[b]); cudaFree(h->d_in16[b]); cudaFree(h->d_nbits[b]);
 		if (h->ev_demod[b]) cudaEventDestroy(h->ev_demod[b]);
 		if (h->evf[b]) cudaEventDestroy(h->evf[b]);
 		if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
@@ -449,6 +450,53 @@ static int process_host(sonde_b200 *h, const float *src, size_t len, int is_iq)
 	CK(cudaEventRecord(h->ev_copied[par], h->cstream));
 	CK(cudaStreamWaitEvent(h->stream, h->ev_copied[par], 0));
 	return run_chunk(h, h->d_in[par], len, len, is_iq);
+}
+
+/* int16 IQ -> complex64, 4 samples (16 B in, 32 B out) per thread step; pure streaming, grid-stride */
+__global__ void __launch_bounds__(256) s16_to_c64_kernel(const int4 *__restrict__ in, float4 *__restrict__ out, size_t n4,
+                                                         const short2 *__restrict__ in_tail, float2 *__restrict__ out_tail,
+                                                         int n_tail, float scale)
+{
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+		const int4 q = __ldg(in + i);
+		const short2 a = *reinterpret_cast<const short2 *>(&q.x), b = *reinterpret_cast<const short2 *>(&q.y);
+		const short2 c = *reinterpret_cast<const short2 *>(&q.z), d = *reinterpret_cast<const short2 *>(&q.w);
+		out[2 * i]     = make_float4(__fmul_rn((float)a.x, scale), __fmul_rn((float)a.y, scale),
+		                             __fmul_rn((float)b.x, scale), __fmul_rn((float)b.y, scale));
+		out[2 * i + 1] = make_float4(__fmul_rn((float)c.x, scale), __fmul_rn((float)c.y, scale),
+		                             __fmul_rn((float)d.x, scale), __fmul_rn((float)d.y, scale));
+	}
+	if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) {
+		const short2 a = in_tail[threadIdx.x];
+		out_tail[threadIdx.x] = make_float2(__fmul_rn((float)a.x, scale), __fmul_rn((float)a.y, scale));
+	}
+}
+
+int sonde_b200_process_iq_s16(sonde_b200 *h, const int16_t *iq, size_t len, float scale)
+{
+	if (!h) return SONDE_ERR_ARG;
+	if (!iq || len == 0) return fail(h, SONDE_ERR_ARG, "null input or zero length");
+	if (len > (size_t)h->cfg.max_chunk_len) return fail(h, SONDE_ERR_TOOLONG, "len > max_chunk_len");
+	CK(cudaSetDevice(h->device));
+	const size_t cap = (size_t)h->n_user * h->cfg.max_chunk_len;
+	const int par = (int)(h->n_issued & 1);
+	if (!h->d_in[par]) CK(cudaMalloc(&h->d_in[par], cap * 2 * sizeof(float)));
+	if (!h->d_in16[par]) CK(cudaMalloc(&h->d_in16[par], cap * 2 * sizeof(int16_t)));
+	const size_t n = (size_t)h->n_user * len;                    /* complex samples */
+	if (h->n_issued >= 2) CK(cudaStreamWaitEvent(h->cstream, h->ev_done[par], 0));
+	CK(cudaMemcpyAsync(h->d_in16[par], iq, n * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, h->cstream));
+	const size_t n4 = n / 4;
+	const int n_tail = (int)(n % 4);
+	const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? ((n4 + 255) / 256 ? (n4 + 255) / 256 : 1) : 148 * 8);
+	s16_to_c64_kernel<<<blocks, 256, 0, h->cstream>>>(
+		static_cast<const int4 *>(h->d_in16[par]), static_cast<float4 *>(h->d_in[par]), n4,
+		static_cast<const short2 *>(h->d_in16[par]) + 4 * n4, static_cast<float2 *>(h->d_in[par]) + 4 * n4, n_tail, scale);
+	CK(cudaGetLastError());
+	h->launches++;
+	CK(cudaEventRecord(h->ev_copied[par], h->cstream));
+	CK(cudaStreamWaitEvent(h->stream, h->ev_copied[par], 0));
+	return run_chunk(h, h->d_in[par], len, len, 1);
 }
 
 int sonde_b200_process_iq(sonde_b200 *h, const float *iq, size_t len) { return process_host(h, iq, len, 1); }

@@ -5,7 +5,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from sdrpp_radiosonde_b200 import synth
+from sdrpp_radiosonde_b200 import capi, synth
 from tests import reflib
 from tests.gpu_util import rec_key, run_gpu
 
@@ -346,3 +346,40 @@ def test_handles_are_independent_and_reusable():
             for c, t in enumerate(types):
                 rb = (synth.MODEMS[t].frame_bits + 7) // 8
                 assert [rec_key(g, rb) for g in got[c]] == [rec_key(w, rb) for w in want[c]]
+
+
+def test_int16_iq_entry_point_equals_float_entry_point():
+    """sonde_b200_process_iq_s16: int16 IQ converted on the GPU (sample = i16 * 2^-15, exact) gives the same bits,
+    soft symbols, records and loop state as process_iq on the converted floats — odd lengths included (the
+    conversion kernel's 4-sample vector path has a tail)."""
+    types = [synth.RS41, synth.M10, synth.IMET4, synth.DFM09, synth.C50]
+    n = 48000 + 331
+    iq = np.stack([synth.make_iq(synth.default_spec(t, c), n) for c, t in enumerate(types)])
+    q = np.empty(iq.shape + (2,), dtype=np.int16)
+    q[..., 0] = np.clip(np.round(iq.real * 20000.0), -32768, 32767)
+    q[..., 1] = np.clip(np.round(iq.imag * 20000.0), -32768, 32767)
+    scale = np.float32(1.0 / 32768.0)
+    as_float = (q[..., 0].astype(np.float32) * scale + 1j * (q[..., 1].astype(np.float32) * scale)).astype(np.complex64)
+    for chunk in (48331, 4097, 333):
+        a = run_gpu(types, as_float, chunk, kind="iq", keep_soft=True, want_bits=True)
+        dec = capi.BatchDecoder(types, min(chunk, n), keep_soft=True)
+        frames = [[] for _ in types]
+        bits = [[] for _ in types]
+        soft = [[] for _ in types]
+        for pos in range(0, n, chunk):
+            dec.process_iq_s16(q[:, pos:pos + chunk])
+            recs, counts = dec.fetch()
+            for c in range(len(types)):
+                frames[c].extend(recs[c, :counts[c]].copy())
+            for c, b in enumerate(dec.fetch_bits()):
+                bits[c].append(b)
+            for c, sft in enumerate(dec.fetch_soft()):
+                soft[c].append(sft)
+        state = dec.fetch_state()
+        dec.close()
+        for c in range(len(types)):
+            assert np.array_equal(np.concatenate(bits[c]), a["bits"][c]), (chunk, c)
+            assert np.array_equal(np.concatenate(soft[c]).view(np.uint32), a["soft"][c].view(np.uint32)), (chunk, c)
+            assert [rec_key(g, 75) for g in frames[c]] == [rec_key(w, 75) for w in a["frames"][c]], (chunk, c)
+        assert np.array_equal(state.view(np.uint32), a["state"].view(np.uint32))
+    assert sum(int(r["ok"]) for f in frames for r in f) > 0
