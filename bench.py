@@ -232,6 +232,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # the decode kernel runs one CTA per SM on 128 of the 148 SMs; keep NCCL's copy kernels inside the 20 free
+        # SMs so that a scatter running beside it does not push decode CTAs into a second wave
+        # (and NCCL's default 4-CTA clusters cannot be placed at all in the scattered free SMs while the decode kernel
+        # is resident: with clusters the scatter simply queues behind the decode — measured, tools/scatter_probe.py)
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
+        os.environ.setdefault("NCCL_CGA_CLUSTER_SIZE", "1")
+        os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # [n_chunks][C][L] complex64 in HBM
@@ -362,9 +369,9 @@ def main():
         t0 = time.perf_counter()
         for i in range(n_sc):
             dec3.sync()                                   # decode(i-1) no longer reads bufs[(i+1) % 2]
+            dec3.process_iq_device(bufs[i % 2].data_ptr(), L)      # overlaps the scatter of the next chunk
             works = shard.scatter_channels(full[(i + 1) % 2], bufs[(i + 1) % 2], world, rank, async_op=True) \
                 if i + 1 < n_sc else []
-            dec3.process_iq_device(bufs[i % 2].data_ptr(), L)      # overlaps the scatter of the next chunk
             for w in works:
                 w.wait()
             torch.cuda.current_stream().synchronize()
