@@ -307,3 +307,119 @@ class BatchDecoder:
     @property
     def stream(self):
         return self.lib.sonde_b200_stream(self.h)
+
+
+# ------------------------------------------------------------------------------------------------
+# wideband channelizer (include/sonde_b200_channelizer.h)
+CHAN_EXPORTS = [
+    "sonde_chan_create", "sonde_chan_destroy", "sonde_chan_process_c64", "sonde_chan_process_c64_device",
+    "sonde_chan_process_s16", "sonde_chan_num_taps", "sonde_chan_taps", "sonde_chan_steps",
+    "sonde_chan_last_kernel_ms", "sonde_chan_last_error",
+]
+
+
+class ChanConfig(ctypes.Structure):
+    """sonde_chan_config"""
+    _fields_ = [("n_channels", ctypes.c_int32), ("decim", ctypes.c_int32), ("fs_out", ctypes.c_int32),
+                ("taps_per_phase", ctypes.c_int32), ("cutoff_hz", ctypes.c_float), ("max_in_len", ctypes.c_int32),
+                ("device", ctypes.c_int32), ("freq_hz", ctypes.POINTER(ctypes.c_double))]
+
+
+def _chan_lib():
+    lib = load()
+    if getattr(lib, "_chan_ready", False):
+        return lib
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    pvp, psz = ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)
+    sig = {
+        "sonde_chan_create": (ctypes.c_int, [pvp, ctypes.POINTER(ChanConfig)]),
+        "sonde_chan_destroy": (None, [vp]),
+        "sonde_chan_process_c64": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
+        "sonde_chan_process_c64_device": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
+        "sonde_chan_process_s16": (ctypes.c_int, [vp, vp, sz, ctypes.c_float, vp, pvp, psz]),
+        "sonde_chan_num_taps": (ctypes.c_int, [vp]),
+        "sonde_chan_taps": (ctypes.c_int, [vp, vp, ctypes.c_int]),
+        "sonde_chan_steps": (ctypes.c_int, [vp, vp, ctypes.c_int]),
+        "sonde_chan_last_kernel_ms": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_float)]),
+        "sonde_chan_last_error": (ctypes.c_char_p, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._chan_ready = True
+    return lib
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr: int, shape, typestr="<f4"):
+    """Zero-copy torch view of library-owned device memory (e.g. the channelizer's output)."""
+    import torch
+    return torch.as_tensor(_CudaArray(ptr, shape, typestr), device="cuda")
+
+
+class Channelizer:
+    """Wideband IQ at fs_in = decim * fs_out -> C channels of complex64 at fs_out, on the GPU (tcgen05 GEMM).
+
+    process_*() return (device pointer, row stride in samples, samples per channel); feed them to
+    BatchDecoder.process_iq_device().  `stream` is a raw cudaStream_t (int), e.g. BatchDecoder.stream."""
+
+    def __init__(self, freq_hz, decim, max_in_len, fs_out=48000, taps_per_phase=0, cutoff_hz=0.0, device=0):
+        self.lib = _chan_lib()
+        self.freq = np.ascontiguousarray(freq_hz, dtype=np.float64)
+        self.C, self.D = int(self.freq.size), int(decim)
+        cfg = ChanConfig(self.C, self.D, fs_out, taps_per_phase, cutoff_hz, int(max_in_len), device,
+                         self.freq.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        h = ctypes.c_void_p()
+        rc = self.lib.sonde_chan_create(ctypes.byref(h), ctypes.byref(cfg))
+        if rc != SONDE_OK:
+            raise SondeError(rc, "sonde_chan_create")
+        self.h = h
+        self.K = self.lib.sonde_chan_num_taps(h)
+        self.taps = np.zeros(self.K, dtype=np.float64)
+        self.lib.sonde_chan_taps(h, self.taps.ctypes.data, self.K)
+        self.steps = np.zeros(self.C, dtype=np.uint32)
+        self.lib.sonde_chan_steps(h, self.steps.ctypes.data, self.C)
+
+    def _ck(self, rc, what):
+        if rc != SONDE_OK:
+            raise SondeError(rc, what + ": " + self.lib.sonde_chan_last_error(self.h).decode())
+
+    def _run(self, fn, ptr, n_in, stream, *extra):
+        out, stride = ctypes.c_void_p(), ctypes.c_size_t()
+        self._ck(fn(self.h, ptr, n_in, *extra, ctypes.c_void_p(stream or 0), ctypes.byref(out), ctypes.byref(stride)), fn.__name__)
+        return out.value, int(stride.value), n_in // self.D
+
+    def process_c64(self, wide: np.ndarray, stream=0):
+        wide = np.ascontiguousarray(wide, dtype=np.complex64)
+        self._keep = wide
+        return self._run(self.lib.sonde_chan_process_c64, wide.ctypes.data, wide.size, stream)
+
+    def process_c64_device(self, ptr: int, n_in: int, stream=0):
+        return self._run(self.lib.sonde_chan_process_c64_device, ptr, n_in, stream)
+
+    def process_s16(self, wide16: np.ndarray, scale=1.0 / 32768.0, stream=0):
+        wide16 = np.ascontiguousarray(wide16, dtype=np.int16)
+        assert wide16.ndim == 2 and wide16.shape[1] == 2
+        self._keep = wide16
+        return self._run(self.lib.sonde_chan_process_s16, wide16.ctypes.data, wide16.shape[0], stream, ctypes.c_float(scale))
+
+    def last_kernel_ms(self):
+        a = ctypes.c_float()
+        self._ck(self.lib.sonde_chan_last_kernel_ms(self.h, ctypes.byref(a)), "last_kernel_ms")
+        return a.value
+
+    def close(self):
+        if self.h:
+            self.lib.sonde_chan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

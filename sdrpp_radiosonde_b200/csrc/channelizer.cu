@@ -1,0 +1,510 @@
+/*
+ * channelizer.cu — K3: wideband IQ -> C narrowband channels at 48 kS/s (include/sonde_b200_channelizer.h,
+ * SURVEY.md §8 f-2; replaces the SDR++ VFO + resampler in front of the plugin, src/main.cpp:55-60).
+ *
+ *     y_c[m] = sum_k h[k] x[n0 - k] e^{-j w_c (n0 - k)},  n0 = mD + D - 1
+ *            = e^{-j w_c n0} * sum_k' W_c[k'] x[s_m + k'],   s_m = n0 - Kp + 1,  W_c[k'] = h[Kp-1-k'] e^{+j w_c (Kp-1-k')}
+ *
+ * The sum is a dense contraction, shared-input across channels: one real GEMM on the tensor cores
+ *
+ *     Y[m][n] = sum_j A[m][j] * B[n][j]      m: output sample (M), n = 2c + {re, im} (N = 2C), j = 2k' + {re, im} (2Kp)
+ *
+ *     A[m][j] = the raw interleaved bf16 input stream at element 2 (mD) + j — overlapping windows; never
+ *               materialised: a 2-D TMA tensor map whose row pitch (2D elements) is smaller than its row
+ *               length (2Kp) reads them straight out of the sample buffer
+ *     B[2c][2k'] = Re W, B[2c][2k'+1] = -Im W, B[2c+1][2k'] = Im W, B[2c+1][2k'+1] = Re W      (bf16, built at create)
+ *
+ * Kernel: persistent, one CTA per SM, warp specialised:
+ *     warp 0      TMA producer: A tile 128 x 64 and B tile 256 x 64 (128-byte swizzle) into a 4-stage smem ring
+ *     warp 1      one thread issues tcgen05.mma (M 128, N 256, K 16, kind::f16 bf16 -> fp32) into TMEM;
+ *                 tcgen05.commit releases smem stages and publishes finished accumulators
+ *     warps 4-11  epilogue: tcgen05.ld the 128 x 256 fp32 accumulator (two accumulators = all 512 TMEM columns,
+ *                 so the epilogue of tile i overlaps the MMAs of tile i+1), rotate by e^{-j w_c n0} (32-bit
+ *                 phase accumulator, so the phase is exact for any stream length), store complex64 [C][M]
+ *                 (lanes = consecutive m: 256-byte coalesced rows)
+ *
+ * Roofline: 2 * M * 2C * 2Kp flops per chunk on the tensor cores; 8 B per output sample written to HBM.
+ */
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sonde_b200.h"
+#include "../../include/sonde_b200_channelizer.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, UK = 16, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int N_EPI_WARPS = 8, FIRST_EPI_WARP = 4;
+constexpr int NTHREADS = (FIRST_EPI_WARP + N_EPI_WARPS) * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+
+struct gemm_params {
+	float2 *out;               /* [C][out_stride] */
+	size_t out_stride;
+	const uint32_t *step;      /* [C] */
+	int n_channels;
+	int m_out;                 /* output samples this call */
+	int n_mt, n_nt, n_kb;
+	int decim;
+	uint32_t n0_base;          /* low 32 bits of (absolute index of the chunk's first input sample + D - 1) */
+};
+
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t b, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t b)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t b, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t b, uint32_t parity)
+{
+	asm volatile(
+		"{\n.reg .pred p;\nW_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(b), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+/* K-major operand tile, 128-byte swizzle (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B): UMMA shared-memory
+ * matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14), leading byte offset [16,30)
+ * (unused for swizzled K-major), stride byte offset >> 4 in [32,46) = 1024 B between 8-row groups,
+ * version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64). */
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
+{
+	return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+/* instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A/B bf16 (1 << 7, 1 << 10), both K-major,
+ * N >> 3 in [17,23), M >> 4 in [24,29) */
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+		::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+/* 32 consecutive fp32 columns of this thread's TMEM lane */
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+		"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+		"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+		: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+		  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+		  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+		  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+		: "r"(taddr) : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const gemm_params p)
+{
+	extern __shared__ unsigned char smem_raw[];
+	const uint32_t base = (s32(smem_raw) + 1023u) & ~1023u;            /* swizzle atoms need 1024-byte alignment */
+	const uint32_t bars = base + STAGES * STAGE_BYTES;
+	/* barrier layout (8 B each): full[STAGES], empty[STAGES], tfull[2], tempty[2], then the TMEM base address */
+	auto full = [&](int s) { return bars + 8u * s; };
+	auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+	auto tfull = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+	auto tempty = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+	const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int n_tiles = p.n_mt * p.n_nt;
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < STAGES; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+		for (int a = 0; a < 2; a++) { mbar_init(tfull(a), 1); mbar_init(tempty(a), N_EPI_WARPS); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 2) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	uint32_t tmem_base;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+	if (warp == 0) {
+		/* ===== TMA producer ===== */
+		if (lane == 0) {
+			int stage = 0;
+			uint32_t phase = 0;
+			for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+				const int mt = tile / p.n_nt, nt = tile % p.n_nt;
+				for (int kb = 0; kb < p.n_kb; kb++) {
+					mbar_wait(empty(stage), phase ^ 1);
+					mbar_expect_tx(full(stage), STAGE_BYTES);
+					const uint32_t sa = base + stage * STAGE_BYTES;
+					tma_load_2d(sa, &tmA, kb * BK, mt * BM, full(stage));
+					tma_load_2d(sa + A_BYTES, &tmB, kb * BK, nt * BN, full(stage));
+					if (++stage == STAGES) { stage = 0; phase ^= 1; }
+				}
+			}
+		}
+	} else if (warp == 1) {
+		/* ===== MMA issuer ===== */
+		if (lane == 0) {
+			int stage = 0, as = 0;
+			uint32_t phase = 0, aphase = 0;
+			for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+				mbar_wait(tempty(as), aphase ^ 1);              /* epilogue drained this accumulator */
+				tc_fence_after();
+				const uint32_t d = tmem_base + (uint32_t)as * BN;
+				for (int kb = 0; kb < p.n_kb; kb++) {
+					mbar_wait(full(stage), phase);
+					tc_fence_after();
+					const uint32_t sa = base + stage * STAGE_BYTES;
+					const uint64_t da = umma_desc(sa), db = umma_desc(sa + A_BYTES);
+#pragma unroll
+					for (int k = 0; k < BK / UK; k++)        /* 16 bf16 = 32 B along K inside the swizzle atom: +2 in the address field */
+						umma_bf16(d, da + 2u * k, db + 2u * k, (kb | k) != 0);
+					umma_commit(empty(stage));                /* frees the smem stage when these MMAs retire */
+					if (++stage == STAGES) { stage = 0; phase ^= 1; }
+				}
+				umma_commit(tfull(as));                       /* accumulator complete */
+				if (++as == 2) { as = 0; aphase ^= 1; }
+			}
+		}
+	} else if (warp >= FIRST_EPI_WARP) {
+		/* ===== epilogue ===== */
+		const int q = warp & 3;                               /* TMEM lane quadrant this warp may access */
+		const int half = (warp - FIRST_EPI_WARP) >> 2;        /* which 128 of the 256 accumulator columns */
+		int as = 0;
+		uint32_t aphase = 0;
+		const float k_ang = 3.14159265358979323846f / 2147483648.0f;
+		for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+			const int mt = tile / p.n_nt, nt = tile % p.n_nt;
+			mbar_wait(tfull(as), aphase);
+			tc_fence_after();
+			const int m = mt * BM + q * 32 + lane;
+			const uint32_t n0 = p.n0_base + (uint32_t)m * (uint32_t)p.decim;
+			const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * BN;
+#pragma unroll 1
+			for (int ck = half * 4; ck < half * 4 + 4; ck++) {
+				uint32_t v[32];
+				tmem_ld32(trow + ck * 32, v);
+				const int c0 = nt * (BN / 2) + ck * 16;
+#pragma unroll
+				for (int i = 0; i < 16; i++) {
+					const int c = c0 + i;
+					if (c < p.n_channels && m < p.m_out) {
+						const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
+						const uint32_t ph = __ldg(p.step + c) * n0;             /* phase mod 2^32: exact */
+						float sn, cs;
+						__sincosf((float)(int32_t)ph * k_ang, &sn, &cs);
+						p.out[(size_t)c * p.out_stride + m] = make_float2(re * cs + im * sn, im * cs - re * sn);
+					}
+				}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(tempty(as));
+			if (++as == 2) { as = 0; aphase ^= 1; }
+		}
+	}
+
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 2) {
+		tc_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+	}
+}
+
+/* ---- input conversion into the persistent bf16 sample buffer -------------------------------- */
+__global__ void __launch_bounds__(256) to_bf16_c64_kernel(const float2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n)
+{
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+		out[i] = __float22bfloat162_rn(__ldg(in + i));
+}
+__global__ void __launch_bounds__(256) to_bf16_s16_kernel(const short2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n, float scale)
+{
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const short2 a = __ldg(in + i);
+		out[i] = __float22bfloat162_rn(make_float2((float)a.x * scale, (float)a.y * scale));
+	}
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct sonde_chan {
+	sonde_chan_config cfg;
+	int C = 0, D = 0, K = 0, Kp = 0, H = 0, Np = 0;
+	int max_out = 0;
+	std::vector<double> taps;
+	std::vector<uint32_t> steps;
+	__nv_bfloat162 *d_x = nullptr;      /* [H + max_in] complex bf16: history then the chunk */
+	__nv_bfloat162 *d_tail = nullptr;   /* [H] */
+	__nv_bfloat16 *d_w = nullptr;       /* [Np][2 Kp] */
+	uint32_t *d_step = nullptr;
+	float2 *d_out[2] = {nullptr, nullptr};
+	void *d_in = nullptr;               /* staging of the host entry points */
+	size_t out_stride = 0;
+	CUtensorMap tmA, tmB;
+	uint64_t n_consumed = 0;            /* wideband samples consumed so far */
+	long n_calls = 0;
+	cudaEvent_t ev[2] = {nullptr, nullptr};
+	bool have_timing = false;
+	int n_sms = 148;
+	std::string err;
+};
+
+static int cfail(sonde_chan *h, int code, const char *msg)
+{
+	if (h) h->err = msg;
+	return code;
+}
+#define CCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (h) h->err = std::string(#x) + ": " + cudaGetErrorString(e_); return SONDE_ERR_CUDA; } } while (0)
+
+static uint16_t bf16_bits(double v)
+{
+	const __nv_bfloat16 b = __float2bfloat16_rn((float)v);
+	uint16_t u;
+	memcpy(&u, &b, 2);
+	return u;
+}
+
+extern "C" {
+
+int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
+{
+	if (!out || !cfg || !cfg->freq_hz) return SONDE_ERR_ARG;
+	*out = nullptr;
+	if (cfg->n_channels <= 0 || cfg->decim < 4 || cfg->decim % 4 || cfg->fs_out <= 0 || cfg->max_in_len <= 0 ||
+	    cfg->max_in_len % cfg->decim)
+		return SONDE_ERR_ARG;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return SONDE_ERR_NODEVICE;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) return SONDE_ERR_NODEVICE;
+	if (cudaSetDevice(cfg->device) != cudaSuccess) return SONDE_ERR_CUDA;
+
+	sonde_chan *h = new sonde_chan;
+	h->cfg = *cfg;
+	h->cfg.freq_hz = nullptr;
+	h->C = cfg->n_channels;
+	h->D = cfg->decim;
+	const int tpp = cfg->taps_per_phase > 0 ? cfg->taps_per_phase : 8;
+	h->K = tpp * h->D;
+	h->Kp = (h->K + 31) / 32 * 32;                   /* 2 Kp a multiple of the 64-element K block */
+	h->H = h->Kp - h->D;
+	h->Np = (2 * h->C + BN - 1) / BN * BN;
+	h->max_out = cfg->max_in_len / h->D;
+	h->out_stride = ((size_t)h->max_out + 3) & ~(size_t)3;
+	h->n_sms = prop.multiProcessorCount;
+	const double fs_in = (double)cfg->fs_out * h->D;
+	const double fc = cfg->cutoff_hz > 0 ? cfg->cutoff_hz : 0.42 * cfg->fs_out;
+
+	/* prototype low-pass: Hamming-windowed sinc, -6 dB at fc, unit DC gain */
+	h->taps.resize(h->K);
+	double sum = 0;
+	for (int k = 0; k < h->K; k++) {
+		const double t = k - 0.5 * (h->K - 1);
+		const double x = 2.0 * fc / fs_in * t;
+		const double sinc = fabs(x) < 1e-12 ? 1.0 : sin(M_PI * x) / (M_PI * x);
+		const double w = 0.54 - 0.46 * cos(2.0 * M_PI * k / (h->K - 1));
+		h->taps[k] = sinc * w;
+		sum += h->taps[k];
+	}
+	for (double &v : h->taps) v /= sum;
+
+	/* oscillator steps and the weight matrix B[n][j] (see the header comment) */
+	h->steps.resize(h->C);
+	std::vector<uint16_t> w((size_t)h->Np * 2 * h->Kp, 0);
+	for (int c = 0; c < h->C; c++) {
+		const double f = cfg->freq_hz[c] / fs_in;             /* cycles per input sample */
+		if (!(fabs(f) < 0.5)) { delete h; return SONDE_ERR_ARG; }
+		const long long st = llround(f * 4294967296.0);
+		h->steps[c] = (uint32_t)st;
+		uint16_t *row_re = &w[(size_t)(2 * c) * 2 * h->Kp], *row_im = &w[(size_t)(2 * c + 1) * 2 * h->Kp];
+		for (int kk = 0; kk < h->Kp; kk++) {
+			const int k = h->Kp - 1 - kk;                     /* tap index of window position kk */
+			if (k >= h->K) continue;                          /* zero padding (oldest samples)   */
+			/* phase reduced before the trig call: w_c k mod 2 pi via the integer step */
+			const uint32_t ph = h->steps[c] * (uint32_t)k;
+			const double a = 2.0 * M_PI * (double)(int32_t)ph / 4294967296.0;
+			const double wr = h->taps[k] * cos(a), wi = h->taps[k] * sin(a);
+			row_re[2 * kk] = bf16_bits(wr);  row_re[2 * kk + 1] = bf16_bits(-wi);
+			row_im[2 * kk] = bf16_bits(wi);  row_im[2 * kk + 1] = bf16_bits(wr);
+		}
+	}
+
+	auto bail = [&](int code, const char *msg) { h->err = msg; sonde_chan_destroy(h); return code; };
+	const size_t nx = (size_t)h->H + cfg->max_in_len + 2 * BK;      /* + slack: the last K block of the last row may overrun */
+	if (cudaMalloc(&h->d_x, nx * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
+	if (cudaMemset(h->d_x, 0, nx * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMemset");
+	if (cudaMalloc(&h->d_tail, (size_t)h->H * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
+	if (cudaMalloc(&h->d_w, w.size() * 2) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
+	if (cudaMemcpy(h->d_w, w.data(), w.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMemcpy");
+	if (cudaMalloc(&h->d_step, (size_t)h->C * 4) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
+	if (cudaMemcpy(h->d_step, h->steps.data(), (size_t)h->C * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMemcpy");
+	for (int b = 0; b < 2; b++)
+		if (cudaMalloc(&h->d_out[b], (size_t)h->C * h->out_stride * sizeof(float2)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
+	for (int b = 0; b < 2; b++)
+		if (cudaEventCreate(&h->ev[b]) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaEventCreate");
+
+	/* tensor maps (driver entry point through the runtime: libcuda is not linked) */
+	encode_tiled_fn encode = nullptr;
+	cudaDriverEntryPointQueryResult qres;
+	if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode)
+		return bail(SONDE_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+	{
+		/* A: rows = output samples (pitch 2D elements), columns = 2 Kp interleaved re/im of the window */
+		const cuuint64_t gdim[2] = {(cuuint64_t)(2 * h->Kp), (cuuint64_t)h->max_out};     /* rows past max_out: zero fill, no access */
+		const cuuint64_t gstr[1] = {(cuuint64_t)(2 * h->D) * 2};
+		const cuuint32_t box[2] = {BK, BM}, estr[2] = {1, 1};
+		if (encode(&h->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+			return bail(SONDE_ERR_CUDA, "tensor map A");
+		const cuuint64_t gdimb[2] = {(cuuint64_t)(2 * h->Kp), (cuuint64_t)h->Np};
+		const cuuint64_t gstrb[1] = {(cuuint64_t)(2 * h->Kp) * 2};
+		const cuuint32_t boxb[2] = {BK, BN};
+		if (encode(&h->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_w, gdimb, gstrb, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+			return bail(SONDE_ERR_CUDA, "tensor map B");
+	}
+	if (cudaFuncSetAttribute(chan_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+		return bail(SONDE_ERR_CUDA, "smem attribute");
+	*out = h;
+	return SONDE_OK;
+}
+
+void sonde_chan_destroy(sonde_chan *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->cfg.device);
+	cudaDeviceSynchronize();
+	cudaFree(h->d_x); cudaFree(h->d_tail); cudaFree(h->d_w); cudaFree(h->d_step); cudaFree(h->d_in);
+	for (int b = 0; b < 2; b++) { cudaFree(h->d_out[b]); if (h->ev[b]) cudaEventDestroy(h->ev[b]); }
+	delete h;
+}
+
+/* kind: 0 = float2 on the device, 1 = float2 on the host, 2 = short2 on the host */
+static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float scale, void *stream_, void **d_out, size_t *out_stride)
+{
+	if (!h) return SONDE_ERR_ARG;
+	if (!src || !d_out || !out_stride || n_in == 0) return cfail(h, SONDE_ERR_ARG, "null argument or zero length");
+	if (n_in % h->D) return cfail(h, SONDE_ERR_ARG, "n_in is not a multiple of the decimation");
+	if (n_in > (size_t)h->cfg.max_in_len) return cfail(h, SONDE_ERR_TOOLONG, "n_in > max_in_len");
+	CCK(cudaSetDevice(h->cfg.device));
+	cudaStream_t st = (cudaStream_t)stream_;
+	const int blocks = h->n_sms * 4;
+	__nv_bfloat162 *dst = h->d_x + h->H;
+	if (kind == 0) {
+		to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(src), dst, n_in);
+	} else {
+		const size_t esz = kind == 1 ? sizeof(float2) : sizeof(short2);
+		if (!h->d_in) CCK(cudaMalloc(&h->d_in, (size_t)h->cfg.max_in_len * sizeof(float2)));
+		CCK(cudaMemcpyAsync(h->d_in, src, n_in * esz, cudaMemcpyHostToDevice, st));
+		if (kind == 1) to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(h->d_in), dst, n_in);
+		else           to_bf16_s16_kernel<<<blocks, 256, 0, st>>>(static_cast<const short2 *>(h->d_in), dst, n_in, scale);
+	}
+	CCK(cudaGetLastError());
+
+	gemm_params gp;
+	const int par = (int)(h->n_calls & 1);
+	gp.out = h->d_out[par];
+	gp.out_stride = h->out_stride;
+	gp.step = h->d_step;
+	gp.n_channels = h->C;
+	gp.m_out = (int)(n_in / h->D);
+	gp.n_mt = (gp.m_out + BM - 1) / BM;
+	gp.n_nt = h->Np / BN;
+	gp.n_kb = 2 * h->Kp / BK;
+	gp.decim = h->D;
+	gp.n0_base = (uint32_t)(h->n_consumed + (uint64_t)h->D - 1);
+	const int n_tiles = gp.n_mt * gp.n_nt;
+	const int grid = n_tiles < h->n_sms ? n_tiles : h->n_sms;
+	CCK(cudaEventRecord(h->ev[0], st));
+	chan_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(h->tmA, h->tmB, gp);
+	CCK(cudaGetLastError());
+	CCK(cudaEventRecord(h->ev[1], st));
+	h->have_timing = true;
+	/* carry the last H samples to the front for the next call (through a side buffer: the ranges may overlap) */
+	CCK(cudaMemcpyAsync(h->d_tail, h->d_x + n_in, (size_t)h->H * sizeof(__nv_bfloat162), cudaMemcpyDeviceToDevice, st));
+	CCK(cudaMemcpyAsync(h->d_x, h->d_tail, (size_t)h->H * sizeof(__nv_bfloat162), cudaMemcpyDeviceToDevice, st));
+	h->n_consumed += n_in;
+	h->n_calls++;
+	*d_out = gp.out;
+	*out_stride = h->out_stride;
+	return SONDE_OK;
+}
+
+int sonde_chan_process_c64(sonde_chan *h, const float *wide_iq, size_t n_in, void *stream, void **d_out, size_t *out_stride)
+{
+	return chan_run(h, wide_iq, n_in, 1, 1.0f, stream, d_out, out_stride);
+}
+int sonde_chan_process_c64_device(sonde_chan *h, const void *d_wide_iq, size_t n_in, void *stream, void **d_out, size_t *out_stride)
+{
+	return chan_run(h, d_wide_iq, n_in, 0, 1.0f, stream, d_out, out_stride);
+}
+int sonde_chan_process_s16(sonde_chan *h, const int16_t *wide_iq, size_t n_in, float scale, void *stream, void **d_out, size_t *out_stride)
+{
+	return chan_run(h, wide_iq, n_in, 2, scale, stream, d_out, out_stride);
+}
+
+int sonde_chan_num_taps(const sonde_chan *h) { return h ? h->K : SONDE_ERR_ARG; }
+int sonde_chan_taps(const sonde_chan *h, double *taps, int cap)
+{
+	if (!h || !taps) return SONDE_ERR_ARG;
+	const int n = cap < h->K ? cap : h->K;
+	memcpy(taps, h->taps.data(), (size_t)n * sizeof(double));
+	return n;
+}
+int sonde_chan_steps(const sonde_chan *h, uint32_t *steps, int cap)
+{
+	if (!h || !steps) return SONDE_ERR_ARG;
+	const int n = cap < h->C ? cap : h->C;
+	memcpy(steps, h->steps.data(), (size_t)n * 4);
+	return n;
+}
+int sonde_chan_last_kernel_ms(sonde_chan *h, float *gemm_ms)
+{
+	if (!h || !gemm_ms) return SONDE_ERR_ARG;
+	*gemm_ms = -1.0f;
+	if (!h->have_timing) return SONDE_OK;
+	CCK(cudaSetDevice(h->cfg.device));
+	CCK(cudaEventSynchronize(h->ev[1]));
+	CCK(cudaEventElapsedTime(gemm_ms, h->ev[0], h->ev[1]));
+	return SONDE_OK;
+}
+const char *sonde_chan_last_error(const sonde_chan *h) { return h ? h->err.c_str() : "null handle"; }
+
+}  /* extern "C" */
