@@ -18,7 +18,7 @@
  *     warp 0      TMA producer: A tile 128 x 64 and B tile 256 x 64 (128-byte swizzle) into a 4-stage smem ring
  *     warp 1      one thread issues tcgen05.mma (M 128, N 256, K 16, kind::f16 bf16 -> fp32) into TMEM;
  *                 tcgen05.commit releases smem stages and publishes finished accumulators
- *     warps 4-11  epilogue: tcgen05.ld the 128 x 256 fp32 accumulator (two accumulators = all 512 TMEM columns,
+ *     warps 4-19  epilogue: tcgen05.ld the 128 x 256 fp32 accumulator (two accumulators = all 512 TMEM columns,
  *                 so the epilogue of tile i overlaps the MMAs of tile i+1), rotate by e^{-j w_c n0} (32-bit
  *                 phase accumulator, so the phase is exact for any stream length), store complex64 [C][M]
  *                 (lanes = consecutive m: 256-byte coalesced rows)
@@ -43,7 +43,8 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int N_EPI_WARPS = 8, FIRST_EPI_WARP = 4;
+constexpr int N_EPI_WARPS = 16, FIRST_EPI_WARP = 4;
+constexpr int CHUNKS_PER_WARP = (BN / 32) / (N_EPI_WARPS / 4);     /* 32-column chunks of the accumulator per epilogue warp */
 constexpr int NTHREADS = (FIRST_EPI_WARP + N_EPI_WARPS) * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
@@ -199,7 +200,7 @@ chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	} else if (warp >= FIRST_EPI_WARP) {
 		/* ===== epilogue ===== */
 		const int q = warp & 3;                               /* TMEM lane quadrant this warp may access */
-		const int half = (warp - FIRST_EPI_WARP) >> 2;        /* which 128 of the 256 accumulator columns */
+		const int part = (warp - FIRST_EPI_WARP) >> 2;        /* which slice of the 256 accumulator columns */
 		int as = 0;
 		uint32_t aphase = 0;
 		const float k_ang = 3.14159265358979323846f / 2147483648.0f;
@@ -211,7 +212,7 @@ chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			const uint32_t n0 = p.n0_base + (uint32_t)m * (uint32_t)p.decim;
 			const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * BN;
 #pragma unroll 1
-			for (int ck = half * 4; ck < half * 4 + 4; ck++) {
+			for (int ck = part * CHUNKS_PER_WARP; ck < (part + 1) * CHUNKS_PER_WARP; ck++) {
 				uint32_t v[32];
 				tmem_ld32(trow + ck * 32, v);
 				const int c0 = nt * (BN / 2) + ck * 16;
