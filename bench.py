@@ -354,6 +354,50 @@ def main():
         for pb in pins16:
             pb.free()
 
+    # wideband front end: one host buffer of wideband IQ per step -> tcgen05 channelizer -> the same
+    # C-channel decode, chained on the decoder's stream.  H2D is D*48 kS/s * 8 B instead of C*48 kS/s * 8 B.
+    wide = None
+    if not args.no_e2e:
+        Dw = 48
+        n_in = L * Dw
+        rngw = np.random.default_rng(7 + rank)
+        freqs = rngw.uniform(-0.45, 0.45, C) * FS * Dw
+        pinw = [capi.PinnedBuffer((n_in,), np.complex64) for _ in range(2)]
+        for pb in pinw:
+            pb.array[...] = (0.05 * (rngw.standard_normal(n_in) + 1j * rngw.standard_normal(n_in))).astype(np.complex64)
+        chz = capi.Channelizer(freqs, Dw, n_in, device=local_rank)
+        dec5 = capi.BatchDecoder(types, L, device=local_rank)
+        # the copy and the channelizer of step i+1 run on a side stream beside the decode of step i
+        side, ext5 = torch.cuda.Stream(), torch.cuda.ExternalStream(dec5.stream)
+        done = [None, None]
+        def wstep(i):
+            if done[i & 1] is not None:
+                side.wait_event(done[i & 1])          # decode(i-2) has read the output buffer this call overwrites
+            ptr, stride, m = chz.process_c64_host_ptr(pinw[i % 2].ptr, n_in, stream=side.cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            ext5.wait_event(ev)
+            dec5.process_iq_device(ptr, m, stride)
+            done[i & 1] = torch.cuda.Event()
+            done[i & 1].record(ext5)
+        for i in range(3):
+            wstep(i)
+            dec5.fetch_counts()
+        barrier()
+        t0 = time.perf_counter()
+        wstep(0)
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                wstep(i + 1)
+            dec5.fetch_counts()
+        dec5.sync()
+        torch.cuda.synchronize()
+        wide = {"t": time.perf_counter() - t0, "gemm_ms": chz.last_kernel_ms(), "h2d": n_in * 8, "D": Dw, "taps": chz.K}
+        chz.close()
+        dec5.close()
+        for pb in pinw:
+            pb.free()
+
     # N > 1: the one exchange step the path can have — the whole batch originates on rank 0 and is
     # scattered over NVLink chunk by chunk, double-buffered against the decode.  Reported beside the main number,
     # which is measured with every rank's shard already resident.
@@ -394,7 +438,8 @@ def main():
     th.join(timeout=2)
 
     t_all = torch.tensor([ms, (e2e["t"] * 1e3) if e2e else 0.0, scatter["t"] * 1e3 if scatter else 0.0,
-                          scatter["t_only"] * 1e3 if scatter else 0.0, (e2e["t16"] * 1e3) if e2e else 0.0],
+                          scatter["t_only"] * 1e3 if scatter else 0.0, (e2e["t16"] * 1e3) if e2e else 0.0,
+                          (wide["t"] * 1e3) if wide else 0.0],
                          dtype=torch.float64, device="cuda")
     tot = torch.tensor([frames, ok], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -445,6 +490,14 @@ def main():
                                "note": "same loop through sonde_b200_process_iq_s16 (int16 IQ quantised from the same "
                                        "signals, converted on the GPU); informational — `e2e` is the complex64 entry point",
                                "decodable_frames_sampled": e2e["ok16"]}
+        if wide:
+            tw = float(t_all[5])
+            line["e2e_wideband"] = {"value": world * args.steps * C * L / (tw * 1e-3) / 1e6, "unit": UNIT,
+                                    "ms_per_step": tw / args.steps, "h2d_bytes_per_step": wide["h2d"],
+                                    "channelizer_gemm_ms": wide["gemm_ms"],
+                                    "note": f"host wideband complex64 IQ at {wide['D']} x 48 kS/s (noise) -> tcgen05 channelizer "
+                                            f"({wide['taps']} taps, {C} channel centres) -> the same {C}-channel decode, per step; "
+                                            "channel samples per second; informational (SURVEY §8 f-2)"}
         if scatter:
             sc_ms, so_ms = float(t_all[2]) / scatter["n"], float(t_all[3]) / scatter["n"]
             line["scatter"] = {"what": "batch resident on rank 0, NCCL send/recv of each rank's [C][L] complex64 block per chunk, "

@@ -402,6 +402,10 @@ class Channelizer:
     def process_c64_device(self, ptr: int, n_in: int, stream=0):
         return self._run(self.lib.sonde_chan_process_c64_device, ptr, n_in, stream)
 
+    def process_c64_host_ptr(self, ptr: int, n_in: int, stream=0):
+        """raw host pointer (pinned memory for an asynchronous copy)"""
+        return self._run(self.lib.sonde_chan_process_c64, ptr, n_in, stream)
+
     def process_s16(self, wide16: np.ndarray, scale=1.0 / 32768.0, stream=0):
         wide16 = np.ascontiguousarray(wide16, dtype=np.int16)
         assert wide16.ndim == 2 and wide16.shape[1] == 2
