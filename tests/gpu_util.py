@@ -52,3 +52,20 @@ def run_gpu(types, batch, chunk, kind="fm", keep_soft=False, want_bits=False, le
         "state": state,
         "launches": launches,
     }
+
+
+def make_wideband(types, freqs, D, nsec, seed=1, amp=0.2, noise=0.01):
+    """Narrowband synthetic sondes (synth.make_iq) resampled to D x 48 kS/s, shifted to their channel centres and
+    summed.  Returns (narrowband[C][n], wideband[n * D] complex64)."""
+    from scipy.signal import resample_poly
+    from sdrpp_radiosonde_b200 import synth
+    n = 48000 * nsec
+    fs_in = 48000.0 * D
+    nb = np.stack([synth.make_iq(synth.default_spec(t, c), n) for c, t in enumerate(types)])
+    t = np.arange(n * D)
+    wide = np.zeros(n * D, dtype=np.complex128)
+    for c in range(len(types)):
+        wide += amp * resample_poly(nb[c].astype(np.complex128), D, 1) * np.exp(2j * np.pi * freqs[c] / fs_in * t)
+    rng = np.random.default_rng(seed)
+    wide += noise * (rng.standard_normal(wide.size) + 1j * rng.standard_normal(wide.size))
+    return nb, wide.astype(np.complex64)

@@ -93,21 +93,12 @@ def test_wideband_to_frames():
     """Three RS41 transmitters and one M10 at different offsets of a 48 x 48 kS/s wideband stream: the chain
     channelizer -> decoder (both on the decoder's stream, no host sync in between) recovers the frames that decoding
     each narrowband signal directly gives."""
-    from scipy.signal import resample_poly
+    from tests.gpu_util import make_wideband
     D, nsec = 48, 4
-    fs_in = 48000.0 * D
     types = [synth.RS41, synth.RS41, synth.M10, synth.RS41]
     freqs = np.array([-500e3, 123.4e3, 420e3, -37.5e3])
     n = 48000 * nsec
-    nb = np.stack([synth.make_iq(synth.default_spec(t, c), n) for c, t in enumerate(types)])
-    t = np.arange(n * D)
-    wide = np.zeros(n * D, dtype=np.complex128)
-    for c in range(len(types)):
-        up = resample_poly(nb[c].astype(np.complex128), D, 1)
-        wide += 0.2 * up * np.exp(2j * np.pi * freqs[c] / fs_in * t)
-    rng = np.random.default_rng(1)
-    wide += 0.01 * (rng.standard_normal(wide.size) + 1j * rng.standard_normal(wide.size))
-    wide = wide.astype(np.complex64)
+    nb, wide = make_wideband(types, freqs, D, nsec)
 
     def decode_direct():
         dec = capi.BatchDecoder(types, 48000)

@@ -22,6 +22,59 @@ def build_exe():
     subprocess.run(cmd, check=True, cwd=ROOT)
 
 
+WEXE = os.path.join(ROOT, "build", "host_wideband_test")
+
+
+def build_wideband_exe():
+    os.makedirs(os.path.dirname(WEXE), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", f"-I{ROOT}/include", f"{ROOT}/tests/cpp/host_wideband_test.cpp", "-o", WEXE,
+           f"-L{ROOT}/sdrpp_radiosonde_b200", "-lsonde_b200", "-Wl,-rpath," + os.path.join(ROOT, "sdrpp_radiosonde_b200"),
+           "-lpthread"]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+
+
+def test_wideband_block_compiles_and_fails_loudly_without_gpu(tmp_path):
+    import torch
+    build_wideband_exe()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    (tmp_path / "w").write_bytes(np.zeros(4800, np.complex64).tobytes())
+    r = subprocess.run([WEXE, str(tmp_path / "w"), "4800", "48", "1000", "0", "0"], capture_output=True, text=True)
+    assert r.returncode == 3 and "NOGPU" in r.stdout and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_wideband_block_on_gpu(tmp_path):
+    """radiosonde::GpuWidebandBank: one wideband dsp::stream in (buffers of an odd length, so the n mod D carry is
+    exercised), three sondes out with telemetry callbacks."""
+    from sdrpp_radiosonde_b200 import capi
+    from tests.gpu_util import make_wideband
+    build_wideband_exe()
+    D, nsec = 48, 4
+    types = [synth.RS41, synth.M10, synth.RS41]
+    freqs = [-400e3, 250e3, 31.25e3]
+    nb, wide = make_wideband(types, freqs, D, nsec)
+    (tmp_path / "w").write_bytes(wide.tobytes())
+    args = [WEXE, str(tmp_path / "w"), str(wide.size), str(D), "100003"]
+    for f, t in zip(freqs, types):
+        args += [str(f), str(t)]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    ch = [dict(kv.split("=") for kv in l.split()[2:]) for l in lines if l.startswith("CH ")]
+    dec = capi.BatchDecoder(types, 48000)
+    want_ok = np.zeros(len(types), dtype=int)
+    for pos in range(0, nb.shape[1], 48000):
+        dec.process_iq(np.ascontiguousarray(nb[:, pos:pos + 48000]))
+        recs, counts = dec.fetch()
+        want_ok += [sum(int(r_["ok"]) for r_ in recs[c, :counts[c]]) for c in range(len(types))]
+    dec.close()
+    for c in range(len(types)):
+        assert int(ch[c]["ok"]) >= want_ok[c] - 1 and want_ok[c] >= 3, (c, ch[c], want_ok[c])
+    assert any(l.startswith("SERIAL R3551568:") for l in lines)          # the golden RS41 frame's serial (SURVEY.md §4)
+    assert int([l for l in lines if l.startswith("CALLBACKS")][0].split()[1]) >= 6
+
+
 def test_compat_library_exports_reference_signatures():
     lib = ctypes.CDLL(os.path.join(ROOT, "sdrpp_radiosonde_b200", "libsonde_b200_compat.so"))
     for x in ("rs41", "dfm09", "m10", "ims100", "mrzn1", "imet4", "c50"):
