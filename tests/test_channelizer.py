@@ -128,3 +128,43 @@ def test_wideband_to_frames():
         assert len(want[c]) >= 3
         common = set(want[c]) & set(got[c])
         assert len(common) >= len(set(want[c])) - 1, (c, len(common), len(want[c]))
+
+
+@pytest.mark.gpu
+def test_channelizer_entry_points_agree_and_reject_bad_arguments():
+    """int16, host-float and device-float entry points give bit-identical outputs on the same samples; argument
+    errors are reported, not absorbed."""
+    import torch
+    D, C = 16, 9
+    rng = np.random.default_rng(3)
+    freqs = rng.uniform(-0.4, 0.4, C) * 48000.0 * D
+    n_in = D * 1000
+    q = rng.integers(-20000, 20000, size=(n_in, 2)).astype(np.int16)
+    xf = (q[:, 0].astype(np.float32) / 32768 + 1j * (q[:, 1].astype(np.float32) / 32768)).astype(np.complex64)
+    outs = []
+    for kind in ("s16", "host", "device"):
+        ch = capi.Channelizer(freqs, D, n_in)
+        if kind == "s16":
+            ptr, stride, m = ch.process_s16(q)
+        elif kind == "host":
+            ptr, stride, m = ch.process_c64(xf)
+        else:
+            xd = torch.view_as_real(torch.from_numpy(xf)).cuda()
+            ptr, stride, m = ch.process_c64_device(xd.data_ptr(), n_in)
+        torch.cuda.synchronize()
+        outs.append(capi.device_view(ptr, (C, stride, 2))[:, :m].cpu().numpy().copy())
+        ch.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    assert np.array_equal(outs[1].view(np.uint32), outs[2].view(np.uint32))
+    assert np.abs(outs[0]).max() > 0
+
+    with pytest.raises(capi.SondeError):
+        capi.Channelizer(freqs, 50, 50 * 100)                 # decimation not a multiple of 4
+    with pytest.raises(capi.SondeError):
+        capi.Channelizer([0.6 * 48000.0 * D], D, n_in)         # centre outside the wideband
+    ch = capi.Channelizer(freqs, D, n_in)
+    with pytest.raises(capi.SondeError):
+        ch.process_c64(xf[:D * 10 + 3])                        # not a whole number of output samples
+    with pytest.raises(capi.SondeError):
+        ch.process_c64(np.concatenate([xf, xf]))               # longer than max_in_len
+    ch.close()
