@@ -324,6 +324,20 @@ def main():
         t_e2e = time.perf_counter() - t0
         d2h = C * dec2.max_frames * capi.REC_DTYPE.itemsize + C * 8
         e2e = {"t": t_e2e, "h2d": C * L * 8, "d2h": d2h}
+        # what the link itself delivers: the same pinned buffer copied to the device with nothing else running
+        dst = torch.empty((C, L), dtype=torch.complex64, device="cuda")
+        src_t = torch.from_numpy(pins[0].array)
+        for _ in range(2):
+            dst.copy_(src_t, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            dst.copy_(src_t, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        e2e["link_gbs"] = 5 * C * L * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del dst
         dec2.close()
         for pb in pins:
             pb.free()
@@ -483,7 +497,11 @@ def main():
         if e2e:
             line["e2e"] = {"value": world * args.steps * C * L / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "ms_per_step": e2e_ms_max / args.steps}
+                           "ms_per_step": e2e_ms_max / args.steps,
+                           "h2d_gbs_achieved": e2e["h2d"] / (e2e_ms_max / args.steps * 1e-3) / 1e9,
+                           "h2d_link_gbs_measured": e2e["link_gbs"],
+                           "note": "bounded by the host link: every step moves C*L*8 bytes of complex64 IQ over PCIe; "
+                                   "h2d_link_gbs_measured is a bare pinned-memory copy of the same buffer on rank 0"}
             t16 = float(t_all[4])
             line["e2e_s16"] = {"value": world * args.steps * C * L / (t16 * 1e-3) / 1e6, "unit": UNIT,
                                "h2d_bytes_per_step": C * L * 4, "ms_per_step": t16 / args.steps,

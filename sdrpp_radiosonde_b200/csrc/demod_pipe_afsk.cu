@@ -356,7 +356,6 @@ demod_pipe_afsk_kernel(const demod_params p, const int group_base)
 		const int g = lane & (G - 1);
 		const bool own = lane < G && chans[g] >= 0;
 		float bias = own ? p.st[chans[g]].agc_bias : 0.0f;
-		const float k1 = fsub(1.0f, 0.01f), k0 = 0.01f;
 		for (int k = 0; k < ntiles; k++) {
 			const int n = min(T, L - k * T);
 			const int xs = k % NX, ss = k % NS2;
@@ -365,35 +364,7 @@ demod_pipe_afsk_kernel(const demod_params p, const int group_base)
 			mbar_wait_t(&sm.sfree[ss], par ^ 1, wacc[1], prof_on);
 			const float *__restrict__ x = sm.x[xs][g];
 			float *__restrict__ s = sm.s[ss][g];
-			if (lane < G) {
-				if (!sm.zflag[xs]) {
-					int i = 0;
-					float4 xv = *reinterpret_cast<const float4 *>(x);
-					for (; i + 4 <= n; i += 4) {
-						const float4 nx = *reinterpret_cast<const float4 *>(x + i + 4);   /* row has 4 floats of slack */
-						float4 o;
-						o.x = fsub(xv.x, bias); bias = fadd(fmul(bias, k1), fmul(o.x, k0));
-						o.y = fsub(xv.y, bias); bias = fadd(fmul(bias, k1), fmul(o.y, k0));
-						o.z = fsub(xv.z, bias); bias = fadd(fmul(bias, k1), fmul(o.z, k0));
-						o.w = fsub(xv.w, bias); bias = fadd(fmul(bias, k1), fmul(o.w, k0));
-						*reinterpret_cast<float4 *>(s + i) = o;
-						xv = nx;
-					}
-					for (; i < n; i++) {
-						const float o = fsub(x[i], bias);
-						bias = fadd(fmul(bias, k1), fmul(o, k0));
-						s[i] = o;
-					}
-				} else {
-					for (int i = 0; i < n; i++) {
-						const float xi = x[i];
-						if (xi == 0.0f) { s[i] = 0.0f; continue; }        /* agc.c:23 */
-						const float o = fsub(xi, bias);
-						bias = fadd(fmul(bias, k1), fmul(o, k0));
-						s[i] = o;
-					}
-				}
-			}
+			if (lane < G) agc_bias_tile(x, s, n, bias, sm.zflag[xs] != 0);
 			warp_arrive(&sm.sfull[ss], lane);
 		}
 		if (own) p.st[chans[g]].agc_bias = bias;
@@ -402,7 +373,6 @@ demod_pipe_afsk_kernel(const demod_params p, const int group_base)
 		const int g = lane & (G - 1);
 		const bool own = lane < G && chans[g] >= 0;
 		float avg = own ? p.st[chans[g]].agc_avg : 5.0f;
-		const float k1 = fsub(1.0f, 0.001f), k0 = 0.001f;
 		for (int k = 0; k < ntiles; k++) {
 			const int n = min(T, L - k * T);
 			const int xs = k % NX, ss = k % NS2;
@@ -412,32 +382,7 @@ demod_pipe_afsk_kernel(const demod_params p, const int group_base)
 			const float *__restrict__ s = sm.s[ss][g];
 			const float *__restrict__ x = sm.x[xs][g];
 			float *__restrict__ v = sm.v[ss][g];
-			if (lane < G) {
-				if (!sm.zflag[xs]) {
-					int i = 0;
-					float4 sv = *reinterpret_cast<const float4 *>(s);
-					for (; i + 4 <= n; i += 4) {
-						const float4 nx = *reinterpret_cast<const float4 *>(s + i + 4);
-						float4 o;
-						o.x = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.x), k0));
-						o.y = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.y), k0));
-						o.z = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.z), k0));
-						o.w = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.w), k0));
-						*reinterpret_cast<float4 *>(v + i) = o;
-						sv = nx;
-					}
-					for (; i < n; i++) {
-						v[i] = avg;
-						avg = fadd(fmul(avg, k1), fmul(fabsf(s[i]), k0));
-					}
-				} else {
-					for (int i = 0; i < n; i++) {
-						v[i] = avg;
-						if (x[i] == 0.0f) continue;
-						avg = fadd(fmul(avg, k1), fmul(fabsf(s[i]), k0));
-					}
-				}
-			}
+			if (lane < G) agc_level_tile(s, x, v, n, avg, sm.zflag[xs] != 0);
 			warp_arrive(&sm.vfull[ss], lane);
 			if (lane == 0) mbar_arrive(&sm.sfree[ss]);
 		}

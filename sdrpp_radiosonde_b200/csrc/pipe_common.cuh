@@ -136,6 +136,73 @@ __device__ __forceinline__ void fir_segment(const float *arow, float (*y)[G][RS]
 	}
 }
 
+/* ---- A1 / A2: the two AGC recurrences of one channel over one tile (SD/demod/dsp/agc.c:23-28) ----------------
+ * bias:  s = x - bias ; bias = bias * (1 - 0.01) + s * 0.01          avg (level):  v = avg ; avg = avg * (1 - 0.001) + |s| * 0.001
+ * `check_zero`: the tile contains exact-zero samples, which bypass the AGC and do not update its state (agc.c:23).
+ * Rows have 4 floats of slack, so the float4 prefetch past the tile end stays inside the row. */
+__device__ __forceinline__ void agc_bias_tile(const float *__restrict__ x, float *__restrict__ s, const int n, float &bias,
+                                              const bool check_zero)
+{
+	const float k1 = fsub(1.0f, 0.01f), k0 = 0.01f;
+	if (!check_zero) {
+		int i = 0;
+		float4 xv = *reinterpret_cast<const float4 *>(x);
+		for (; i + 4 <= n; i += 4) {
+			const float4 nx = *reinterpret_cast<const float4 *>(x + i + 4);
+			float4 o;
+			o.x = fsub(xv.x, bias); bias = fadd(fmul(bias, k1), fmul(o.x, k0));
+			o.y = fsub(xv.y, bias); bias = fadd(fmul(bias, k1), fmul(o.y, k0));
+			o.z = fsub(xv.z, bias); bias = fadd(fmul(bias, k1), fmul(o.z, k0));
+			o.w = fsub(xv.w, bias); bias = fadd(fmul(bias, k1), fmul(o.w, k0));
+			*reinterpret_cast<float4 *>(s + i) = o;
+			xv = nx;
+		}
+		for (; i < n; i++) {
+			const float o = fsub(x[i], bias);
+			bias = fadd(fmul(bias, k1), fmul(o, k0));
+			s[i] = o;
+		}
+	} else {
+		for (int i = 0; i < n; i++) {
+			const float xi = x[i];
+			if (xi == 0.0f) { s[i] = 0.0f; continue; }
+			const float o = fsub(xi, bias);
+			bias = fadd(fmul(bias, k1), fmul(o, k0));
+			s[i] = o;
+		}
+	}
+}
+
+__device__ __forceinline__ void agc_level_tile(const float *__restrict__ s, const float *__restrict__ x, float *__restrict__ v,
+                                               const int n, float &avg, const bool check_zero)
+{
+	const float k1 = fsub(1.0f, 0.001f), k0 = 0.001f;
+	if (!check_zero) {
+		int i = 0;
+		float4 sv = *reinterpret_cast<const float4 *>(s);
+		for (; i + 4 <= n; i += 4) {
+			const float4 nx = *reinterpret_cast<const float4 *>(s + i + 4);
+			float4 o;
+			o.x = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.x), k0));
+			o.y = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.y), k0));
+			o.z = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.z), k0));
+			o.w = avg; avg = fadd(fmul(avg, k1), fmul(fabsf(sv.w), k0));
+			*reinterpret_cast<float4 *>(v + i) = o;
+			sv = nx;
+		}
+		for (; i < n; i++) {
+			v[i] = avg;
+			avg = fadd(fmul(avg, k1), fmul(fabsf(s[i]), k0));
+		}
+	} else {
+		for (int i = 0; i < n; i++) {
+			v[i] = avg;
+			if (x[i] == 0.0f) continue;
+			avg = fadd(fmul(avg, k1), fmul(fabsf(s[i]), k0));
+		}
+	}
+}
+
 }  // namespace pipe
 
 #endif
