@@ -523,7 +523,7 @@ def main():
                                "ms_per_step_with_scatter": sc_ms, "value_with_scatter": world * C * L / (sc_ms * 1e-3) / 1e6,
                                "scatter_only_ms": so_ms,
                                "rank0_egress_gbs": (world - 1) * C * L * 8 / (so_ms * 1e-3) / 1e9}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             cpu = CpuPath()
             n_ch = 2 * ncores
             t, f, k = cpu.run(synth.RS41, host_iq[:n_ch], L, ncores)
