@@ -383,3 +383,72 @@ def test_int16_iq_entry_point_equals_float_entry_point():
             assert [rec_key(g, 75) for g in frames[c]] == [rec_key(w, 75) for w in a["frames"][c]], (chunk, c)
         assert np.array_equal(state.view(np.uint32), a["state"].view(np.uint32))
     assert sum(int(r["ok"]) for f in frames for r in f) > 0
+
+
+FULL_CONFIGS = {
+    # BASELINE.json configs at their per-GPU sizes: name -> (channels, type of channel c)
+    "cfg2_rs41_1024": (1024, lambda c: synth.RS41),
+    "cfg3_dfm_m10_2048": (2048, lambda c: synth.DFM09 if c % 2 == 0 else synth.M10),
+    "cfg4_ims100_1024": (1024, lambda c: synth.IMS100),
+    "cfg5_all_types_1024": (1024, lambda c: c % 7),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_CONFIGS))
+def test_full_size_configs_replica_consistency_and_oracle(name):
+    """The BASELINE configs at full per-GPU size (1024-2048 channels x 10 s = 480000 samples in 1 s buffers).
+    Size-independent properties: the batch is NB distinct signals per type tiled over all channels, so
+    (1) every replica must produce records bit-identical to its base channel — whatever CTA group, SM or lane of
+    the serial warps it landed on — and (2) each base channel's records equal the oracle's on the same signal."""
+    import torch
+    C, type_of = FULL_CONFIGS[name]
+    NB, L, nsec = 4, 48000, 10
+    n = L * nsec
+    types = np.array([type_of(c) for c in range(C)], dtype=np.int32)
+    tset = sorted(set(int(t) for t in types))
+    base = {t: np.stack([synth.make_iq(synth.default_spec(t, 100 + b), n) for b in range(NB)]) for t in tset}
+    # channel c replicates base[type][k]: k = running index of that type's channels mod NB
+    seen = {t: 0 for t in tset}
+    src = []
+    for c in range(C):
+        t = int(types[c])
+        src.append((t, seen[t] % NB))
+        seen[t] += 1
+    dev_base = {t: torch.from_numpy(base[t]).cuda() for t in tset}
+    dec = capi.BatchDecoder(types, L)
+    frames = [[] for _ in range(C)]
+    chunk_dev = torch.empty((C, L), dtype=torch.complex64, device="cuda")
+    idx = {t: (torch.tensor([c for c in range(C) if src[c][0] == t], device="cuda"),
+               torch.tensor([src[c][1] for c in range(C) if src[c][0] == t], device="cuda")) for t in tset}
+    try:
+        for k in range(nsec):
+            for t in tset:
+                rows, which = idx[t]
+                chunk_dev[rows] = dev_base[t][which, k * L:(k + 1) * L]
+            torch.cuda.synchronize()          # the decoder runs on its own stream: the buffer must be complete
+            dec.process_iq_device(chunk_dev.data_ptr(), L)
+            recs, counts = dec.fetch()
+            for c in range(C):
+                frames[c].extend(recs[c, :counts[c]].copy())
+    finally:
+        dec.close()
+    first = {}
+    n_ok = 0
+    for c in range(C):
+        rb = (synth.MODEMS[int(types[c])].frame_bits + 7) // 8
+        keys = [rec_key(r, rb) for r in frames[c]]
+        if src[c] not in first:
+            first[src[c]] = (c, keys)
+        else:
+            assert keys == first[src[c]][1], (name, c, "differs from its base channel", first[src[c]][0])
+        n_ok += sum(int(r["ok"]) for r in frames[c])
+    orc = reflib.OracleLib() if reflib.have_oracle() else None
+    if orc is not None:
+        for (t, b), (c, keys) in first.items():
+            if synth.MODEMS[t].afsk:
+                continue                      # AFSK vs the CPU libm: frames are checked on the float path (test_afsk_frames_match_reference)
+            rb = (synth.MODEMS[t].frame_bits + 7) // 8
+            want = orc.frames_run_iq(t, base[t][b], L)
+            assert keys == [rec_key(w, rb) for w in want], (name, t, b)
+    print(f"{name}: {C} channels x {n} samples, {sum(len(f) for f in frames)} frame windows, {n_ok} pass their gate")
+    assert n_ok > C
