@@ -41,7 +41,8 @@ typedef struct sonde_chan sonde_chan;   /* opaque */
 
 typedef struct {
 	int32_t n_channels;        /* C                                                                     */
-	int32_t decim;             /* D = fs_in / fs_out; a multiple of 4 (16-byte row pitch of the TMA window view) */
+	int32_t decim;             /* D = fs_in / fs_out >= 2.  Multiples of 4 run at full speed; even D costs 2x, odd D 4x
+	                              the tensor work (zero slots keep the TMA window pitch 16-byte aligned)             */
 	int32_t fs_out;            /* output rate per channel, 48000                                        */
 	int32_t taps_per_phase;    /* prototype low-pass length K = taps_per_phase * D; 0 -> 8              */
 	float   cutoff_hz;         /* -6 dB point of the channel filter; 0 -> 0.42 * fs_out                 */
@@ -67,6 +68,10 @@ SONDE_API int  sonde_chan_process_c64_device(sonde_chan *h, const void *d_wide_i
 /* int16 interleaved I,Q as SDR hardware delivers it; sample = i16 * scale */
 SONDE_API int  sonde_chan_process_s16(sonde_chan *h, const int16_t *wide_iq /* host [n_in][2] */, size_t n_in,
                                       float scale, void *stream, void **d_out, size_t *out_stride);
+
+/* offset-binary 8-bit IQ as RTL-SDR dongles deliver it; sample = (u8 - 127.5) / 128 */
+SONDE_API int  sonde_chan_process_u8(sonde_chan *h, const uint8_t *wide_iq /* host [n_in][2] */, size_t n_in,
+                                     void *stream, void **d_out, size_t *out_stride);
 
 /* Parameters the oracle needs (they are inputs of the algorithm, not results): the K prototype taps, the
  * quantised oscillator steps (w_c = 2 pi step_c / 2^32), K itself. */

@@ -313,7 +313,7 @@ class BatchDecoder:
 # wideband channelizer (include/sonde_b200_channelizer.h)
 CHAN_EXPORTS = [
     "sonde_chan_create", "sonde_chan_destroy", "sonde_chan_process_c64", "sonde_chan_process_c64_device",
-    "sonde_chan_process_s16", "sonde_chan_num_taps", "sonde_chan_taps", "sonde_chan_steps",
+    "sonde_chan_process_s16", "sonde_chan_process_u8", "sonde_chan_num_taps", "sonde_chan_taps", "sonde_chan_steps",
     "sonde_chan_last_kernel_ms", "sonde_chan_last_error",
 ]
 
@@ -337,6 +337,7 @@ def _chan_lib():
         "sonde_chan_process_c64": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
         "sonde_chan_process_c64_device": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
         "sonde_chan_process_s16": (ctypes.c_int, [vp, vp, sz, ctypes.c_float, vp, pvp, psz]),
+        "sonde_chan_process_u8": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
         "sonde_chan_num_taps": (ctypes.c_int, [vp]),
         "sonde_chan_taps": (ctypes.c_int, [vp, vp, ctypes.c_int]),
         "sonde_chan_steps": (ctypes.c_int, [vp, vp, ctypes.c_int]),
@@ -411,6 +412,12 @@ class Channelizer:
         assert wide16.ndim == 2 and wide16.shape[1] == 2
         self._keep = wide16
         return self._run(self.lib.sonde_chan_process_s16, wide16.ctypes.data, wide16.shape[0], stream, ctypes.c_float(scale))
+
+    def process_u8(self, wide8: np.ndarray, stream=0):
+        wide8 = np.ascontiguousarray(wide8, dtype=np.uint8)
+        assert wide8.ndim == 2 and wide8.shape[1] == 2
+        self._keep = wide8
+        return self._run(self.lib.sonde_chan_process_u8, wide8.ctypes.data, wide8.shape[0], stream)
 
     def last_kernel_ms(self):
         a = ctypes.c_float()

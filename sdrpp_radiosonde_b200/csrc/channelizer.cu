@@ -11,7 +11,8 @@
  *
  *     A[m][j] = the raw interleaved bf16 input stream at element 2 (mD) + j — overlapping windows; never
  *               materialised: a 2-D TMA tensor map whose row pitch (2D elements) is smaller than its row
- *               length (2Kp) reads them straight out of the sample buffer
+ *               length (2Kp) reads them straight out of the sample buffer (pitch must be a multiple of 16 bytes:
+ *               D % 4 == 0; other decimations store the samples in every 2nd / 4th slot, see sonde_chan_create)
  *     B[2c][2k'] = Re W, B[2c][2k'+1] = -Im W, B[2c+1][2k'] = Im W, B[2c+1][2k'+1] = Re W      (bf16, built at create)
  *
  * Kernel: persistent, one CTA per SM, warp specialised:
@@ -244,18 +245,29 @@ chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 /* ---- input conversion into the persistent bf16 sample buffer -------------------------------- */
-__global__ void __launch_bounds__(256) to_bf16_c64_kernel(const float2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n)
+/* `stride`: complex samples are stored every `stride`-th slot of the sample buffer (the slots in between stay zero),
+ * which makes the window pitch a multiple of 16 bytes for decimations that are not multiples of 4 (see create). */
+__global__ void __launch_bounds__(256) to_bf16_c64_kernel(const float2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n, int stride)
 {
-	const size_t stride = (size_t)gridDim.x * blockDim.x;
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-		out[i] = __float22bfloat162_rn(__ldg(in + i));
+	const size_t step = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+		out[i * stride] = __float22bfloat162_rn(__ldg(in + i));
 }
-__global__ void __launch_bounds__(256) to_bf16_s16_kernel(const short2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n, float scale)
+__global__ void __launch_bounds__(256) to_bf16_s16_kernel(const short2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n, int stride, float scale)
 {
-	const size_t stride = (size_t)gridDim.x * blockDim.x;
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+	const size_t step = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
 		const short2 a = __ldg(in + i);
-		out[i] = __float22bfloat162_rn(make_float2((float)a.x * scale, (float)a.y * scale));
+		out[i * stride] = __float22bfloat162_rn(make_float2((float)a.x * scale, (float)a.y * scale));
+	}
+}
+/* offset-binary 8-bit IQ (RTL-SDR): sample = (u8 - 127.5) / 128 */
+__global__ void __launch_bounds__(256) to_bf16_u8_kernel(const uchar2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n, int stride)
+{
+	const size_t step = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+		const uchar2 a = __ldg(in + i);
+		out[i * stride] = __float22bfloat162_rn(make_float2(((float)a.x - 127.5f) * 0.0078125f, ((float)a.y - 127.5f) * 0.0078125f));
 	}
 }
 
@@ -267,7 +279,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 struct sonde_chan {
 	sonde_chan_config cfg;
-	int C = 0, D = 0, K = 0, Kp = 0, H = 0, Np = 0;
+	int C = 0, D = 0, S = 1, K = 0, Kp = 0, H = 0, Np = 0;   /* S: slot stride of the sample buffer; Kp, H in slots */
 	int max_out = 0;
 	std::vector<double> taps;
 	std::vector<uint32_t> steps;
@@ -308,8 +320,7 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 {
 	if (!out || !cfg || !cfg->freq_hz) return SONDE_ERR_ARG;
 	*out = nullptr;
-	if (cfg->n_channels <= 0 || cfg->decim < 4 || cfg->decim % 4 || cfg->fs_out <= 0 || cfg->max_in_len <= 0 ||
-	    cfg->max_in_len % cfg->decim)
+	if (cfg->n_channels <= 0 || cfg->decim < 2 || cfg->fs_out <= 0 || cfg->max_in_len <= 0 || cfg->max_in_len % cfg->decim)
 		return SONDE_ERR_ARG;
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return SONDE_ERR_NODEVICE;
@@ -324,8 +335,12 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 	h->D = cfg->decim;
 	const int tpp = cfg->taps_per_phase > 0 ? cfg->taps_per_phase : 8;
 	h->K = tpp * h->D;
-	h->Kp = (h->K + 31) / 32 * 32;                   /* 2 Kp a multiple of the 64-element K block */
-	h->H = h->Kp - h->D;
+	/* The TMA window view needs a row pitch of 4 D S bytes that is a multiple of 16.  D % 4 == 0: S = 1.  Otherwise the
+	 * samples are stored every 2nd (even D) or 4th slot with zero slots in between and the weight rows carry zeros at
+	 * those positions: the same GEMM over a 2x / 4x longer K dimension (2x / 4x the tensor work, still exact). */
+	h->S = (h->D % 4 == 0) ? 1 : (h->D % 2 == 0) ? 2 : 4;
+	h->Kp = (h->K * h->S + 31) / 32 * 32;            /* window length in slots; 2 Kp a multiple of the 64-element K block */
+	h->H = h->Kp - h->D * h->S;                      /* history slots in front of the chunk */
 	h->Np = (2 * h->C + BN - 1) / BN * BN;
 	h->max_out = cfg->max_in_len / h->D;
 	h->out_stride = ((size_t)h->max_out + 3) & ~(size_t)3;
@@ -356,7 +371,8 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 		h->steps[c] = (uint32_t)st;
 		uint16_t *row_re = &w[(size_t)(2 * c) * 2 * h->Kp], *row_im = &w[(size_t)(2 * c + 1) * 2 * h->Kp];
 		for (int kk = 0; kk < h->Kp; kk++) {
-			const int k = h->Kp - 1 - kk;                     /* tap index of window position kk */
+			if ((h->Kp - 1 - kk) % h->S) continue;            /* a zero slot between samples     */
+			const int k = (h->Kp - 1 - kk) / h->S;            /* tap index of window position kk */
 			if (k >= h->K) continue;                          /* zero padding (oldest samples)   */
 			/* phase reduced before the trig call: w_c k mod 2 pi via the integer step */
 			const uint32_t ph = h->steps[c] * (uint32_t)k;
@@ -368,7 +384,7 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 	}
 
 	auto bail = [&](int code, const char *msg) { h->err = msg; sonde_chan_destroy(h); return code; };
-	const size_t nx = (size_t)h->H + cfg->max_in_len + 2 * BK;      /* + slack: the last K block of the last row may overrun */
+	const size_t nx = (size_t)h->H + (size_t)cfg->max_in_len * h->S + 2 * BK;      /* + slack */
 	if (cudaMalloc(&h->d_x, nx * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
 	if (cudaMemset(h->d_x, 0, nx * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMemset");
 	if (cudaMalloc(&h->d_tail, (size_t)h->H * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
@@ -389,7 +405,7 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 	{
 		/* A: rows = output samples (pitch 2D elements), columns = 2 Kp interleaved re/im of the window */
 		const cuuint64_t gdim[2] = {(cuuint64_t)(2 * h->Kp), (cuuint64_t)h->max_out};     /* rows past max_out: zero fill, no access */
-		const cuuint64_t gstr[1] = {(cuuint64_t)(2 * h->D) * 2};
+		const cuuint64_t gstr[1] = {(cuuint64_t)(2 * h->D * h->S) * 2};
 		const cuuint32_t box[2] = {BK, BM}, estr[2] = {1, 1};
 		if (encode(&h->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 		           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -417,7 +433,7 @@ void sonde_chan_destroy(sonde_chan *h)
 	delete h;
 }
 
-/* kind: 0 = float2 on the device, 1 = float2 on the host, 2 = short2 on the host */
+/* kind: 0 = float2 on the device, 1 = float2 on the host, 2 = short2 on the host, 3 = uchar2 on the host */
 static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float scale, void *stream_, void **d_out, size_t *out_stride)
 {
 	if (!h) return SONDE_ERR_ARG;
@@ -427,15 +443,16 @@ static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float
 	CCK(cudaSetDevice(h->cfg.device));
 	cudaStream_t st = (cudaStream_t)stream_;
 	const int blocks = h->n_sms * 4;
-	__nv_bfloat162 *dst = h->d_x + h->H;
+	__nv_bfloat162 *dst = h->d_x + h->H + (h->S - 1);          /* sample i lives in slot H + S i + (S - 1) */
 	if (kind == 0) {
-		to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(src), dst, n_in);
+		to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(src), dst, n_in, h->S);
 	} else {
-		const size_t esz = kind == 1 ? sizeof(float2) : sizeof(short2);
+		const size_t esz = kind == 1 ? sizeof(float2) : kind == 2 ? sizeof(short2) : sizeof(uchar2);
 		if (!h->d_in) CCK(cudaMalloc(&h->d_in, (size_t)h->cfg.max_in_len * sizeof(float2)));
 		CCK(cudaMemcpyAsync(h->d_in, src, n_in * esz, cudaMemcpyHostToDevice, st));
-		if (kind == 1) to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(h->d_in), dst, n_in);
-		else           to_bf16_s16_kernel<<<blocks, 256, 0, st>>>(static_cast<const short2 *>(h->d_in), dst, n_in, scale);
+		if (kind == 1)      to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(h->d_in), dst, n_in, h->S);
+		else if (kind == 2) to_bf16_s16_kernel<<<blocks, 256, 0, st>>>(static_cast<const short2 *>(h->d_in), dst, n_in, h->S, scale);
+		else                to_bf16_u8_kernel<<<blocks, 256, 0, st>>>(static_cast<const uchar2 *>(h->d_in), dst, n_in, h->S);
 	}
 	CCK(cudaGetLastError());
 
@@ -459,7 +476,7 @@ static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float
 	CCK(cudaEventRecord(h->ev[1], st));
 	h->have_timing = true;
 	/* carry the last H samples to the front for the next call (through a side buffer: the ranges may overlap) */
-	CCK(cudaMemcpyAsync(h->d_tail, h->d_x + n_in, (size_t)h->H * sizeof(__nv_bfloat162), cudaMemcpyDeviceToDevice, st));
+	CCK(cudaMemcpyAsync(h->d_tail, h->d_x + n_in * h->S, (size_t)h->H * sizeof(__nv_bfloat162), cudaMemcpyDeviceToDevice, st));
 	CCK(cudaMemcpyAsync(h->d_x, h->d_tail, (size_t)h->H * sizeof(__nv_bfloat162), cudaMemcpyDeviceToDevice, st));
 	h->n_consumed += n_in;
 	h->n_calls++;
@@ -479,6 +496,11 @@ int sonde_chan_process_c64_device(sonde_chan *h, const void *d_wide_iq, size_t n
 int sonde_chan_process_s16(sonde_chan *h, const int16_t *wide_iq, size_t n_in, float scale, void *stream, void **d_out, size_t *out_stride)
 {
 	return chan_run(h, wide_iq, n_in, 2, scale, stream, d_out, out_stride);
+}
+
+int sonde_chan_process_u8(sonde_chan *h, const uint8_t *wide_iq, size_t n_in, void *stream, void **d_out, size_t *out_stride)
+{
+	return chan_run(h, wide_iq, n_in, 3, 1.0f, stream, d_out, out_stride);
 }
 
 int sonde_chan_num_taps(const sonde_chan *h) { return h ? h->K : SONDE_ERR_ARG; }

@@ -30,14 +30,14 @@ public:
 	GpuWidebandBank() {}
 	~GpuWidebandBank() { deinit(); }
 
-	/* fs_in must be decim * 48000 with decim a multiple of 4; freq_hz[c] = centre of channel c relative to the
+	/* fs_in must be decim * 48000 with an integer decim >= 2 (multiples of 4 run fastest); freq_hz[c] = centre of channel c relative to the
 	 * centre of the wideband stream; types[c] = enum sonde_type or SONDE_AUTO */
 	void init(dsp::stream<dsp::complex_t> *in, double fs_in, const std::vector<double> &freq_hz, const std::vector<int> &types,
 	          SondeCallback cb, void *ctx, int max_in = dsp::STREAM_BUFFER_SIZE, int device = 0)
 	{
 		if (!in || freq_hz.empty() || freq_hz.size() != types.size()) throw std::invalid_argument("GpuWidebandBank: bad channel list");
 		const int D = (int)(fs_in / 48000.0 + 0.5);
-		if (D < 4 || D % 4 || (double)D * 48000.0 != fs_in) throw std::invalid_argument("GpuWidebandBank: fs_in must be 4k * 48000");
+		if (D < 2 || (double)D * 48000.0 != fs_in) throw std::invalid_argument("GpuWidebandBank: fs_in must be an integer multiple (>= 2) of 48000");
 		m_in = in; m_cb = cb; m_ctx = ctx; m_D = D;
 		m_types.assign(types.begin(), types.end());
 		m_max_in = (max_in + D) / D * D;

@@ -55,7 +55,7 @@ def _wideband(rng, n, freqs, fs_in):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("D,C", [(8, 5), (48, 20), (128, 130)])
+@pytest.mark.parametrize("D,C", [(8, 5), (48, 20), (128, 130), (50, 7), (25, 3)])
 def test_channelizer_matches_oracle(D, C):
     import torch
     rng = np.random.default_rng(5 + D)
@@ -158,8 +158,20 @@ def test_channelizer_entry_points_agree_and_reject_bad_arguments():
     assert np.array_equal(outs[1].view(np.uint32), outs[2].view(np.uint32))
     assert np.abs(outs[0]).max() > 0
 
+    # 8-bit offset-binary IQ == the float entry point on (u8 - 127.5) / 128
+    u8 = rng.integers(0, 256, size=(n_in, 2)).astype(np.uint8)
+    xf8 = ((u8[:, 0].astype(np.float32) - 127.5) / 128 + 1j * ((u8[:, 1].astype(np.float32) - 127.5) / 128)).astype(np.complex64)
+    res = []
+    for kind in ("u8", "host"):
+        ch = capi.Channelizer(freqs, D, n_in)
+        ptr, stride, m = ch.process_u8(u8) if kind == "u8" else ch.process_c64(xf8)
+        torch.cuda.synchronize()
+        res.append(capi.device_view(ptr, (C, stride, 2))[:, :m].cpu().numpy().copy())
+        ch.close()
+    assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))
+
     with pytest.raises(capi.SondeError):
-        capi.Channelizer(freqs, 50, 50 * 100)                 # decimation not a multiple of 4
+        capi.Channelizer(freqs, 1, 100)                        # no decimation
     with pytest.raises(capi.SondeError):
         capi.Channelizer([0.6 * 48000.0 * D], D, n_in)         # centre outside the wideband
     ch = capi.Channelizer(freqs, D, n_in)
