@@ -7,6 +7,8 @@
  * buffer and queues its frame records; each further call pops one (PARSED) and the call after the
  * last one answers PROCEED and re-arms.
  */
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -38,7 +40,10 @@ sonde_compat_decoder *make(int type, int samplerate)
 	cfg.samplerate = samplerate;
 	cfg.max_chunk_len = 1 << 20;
 	cfg.types = &t;
-	if (sonde_b200_create(&d->h, &cfg) != SONDE_OK) {
+	const int rc = sonde_b200_create(&d->h, &cfg);
+	if (rc != SONDE_OK) {
+		/* the reference's init has no error channel besides NULL: say why, loudly */
+		fprintf(stderr, "sonde_b200_compat: decoder init failed (%d): an sm_100 CUDA device is required, there is no CPU fallback\n", rc);
 		delete d;
 		return nullptr;
 	}
@@ -59,7 +64,11 @@ void destroy(sonde_compat_decoder *d)
 
 ParserStatus step(sonde_compat_decoder *d, SondeData *dst, const float *src, size_t len)
 {
-	if (!d || !src) return PROCEED;
+	if (!d) {
+		fprintf(stderr, "sonde_b200_compat: xxx_decode() called with a NULL decoder (init failed: no CUDA device, no CPU fallback)\n");
+		abort();
+	}
+	if (!src) return PROCEED;
 	if (!d->armed) {
 		int32_t count = 0;
 		d->n_recs = d->next = 0;
