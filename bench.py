@@ -183,6 +183,23 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
+    numa_note = None
+    if world > 1 and args.impl == "b200":
+        # one rank per GPU: run (and therefore first-touch / pin host buffers) on the CPU cores local to this rank's GPU,
+        # otherwise all ranks' pinned staging may sit on one socket and the e2e copies share its memory controllers
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = (ncores + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(hnd, words)
+            cpus = {64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1 and 64 * w + b < ncores}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa_note = f"rank pinned to {len(cpus)} GPU-local cores"
+        except Exception as e:                               # affinity is an optimisation, never a requirement
+            numa_note = f"no GPU-local affinity ({type(e).__name__})"
     L, C = args.chunk, args.channels
     n_chunks = max(1, args.seconds * FS // L)
     n_total = n_chunks * L
@@ -484,7 +501,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, frames_per_s=frames / (ms_max * 1e-3), ok_frames_per_s=ok / (ms_max * 1e-3),
-                           realtime_channels_equiv=value * 1e6 / FS, gen_seconds=round(t_gen, 1)),
+                           realtime_channels_equiv=value * 1e6 / FS, gen_seconds=round(t_gen, 1),
+                           **({"host_affinity": numa_note} if numa_note else {})),
             "gpu_launches": launches,
             "clocks": summarize_clocks(samples),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
