@@ -434,13 +434,9 @@ static constexpr size_t legacy_smem_bytes()
 template <int P, bool AFSK>
 static cudaError_t launch_legacy(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
-	static bool attr_done = false;
-	if (!attr_done) {
-		cudaError_t e = cudaFuncSetAttribute(demod_gfsk_kernel<P, AFSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                                     (int)legacy_smem_bytes<AFSK>());
-		if (e != cudaSuccess) return e;
-		attr_done = true;
-	}
+	static std::atomic<unsigned long long> attr_done{0};
+	const cudaError_t ea = sonde_ensure_dynamic_smem(demod_gfsk_kernel<P, AFSK>, (int)legacy_smem_bytes<AFSK>(), attr_done);
+	if (ea != cudaSuccess) return ea;
 	demod_gfsk_kernel<P, AFSK><<<n_groups, NT, legacy_smem_bytes<AFSK>(), stream>>>(*p, group_base);
 	return cudaGetLastError();
 }

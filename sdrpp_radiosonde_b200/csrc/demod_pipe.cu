@@ -395,13 +395,9 @@ template <int P, int N, bool IQ, bool SOFT, bool TMA>
 cudaError_t launch2(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
 	constexpr int LAYOUT = (N == 24) ? 1 : 0;
-	static bool attr_done = false;
-	if (!attr_done) {
-		cudaError_t e = cudaFuncSetAttribute(demod_pipe_kernel<P, N, IQ, SOFT, LAYOUT, TMA>,
-		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem_t<P>));
-		if (e != cudaSuccess) return e;
-		attr_done = true;
-	}
+	static std::atomic<unsigned long long> attr_done{0};
+	const cudaError_t ea = sonde_ensure_dynamic_smem(demod_pipe_kernel<P, N, IQ, SOFT, LAYOUT, TMA>, (int)sizeof(smem_t<P>), attr_done);
+	if (ea != cudaSuccess) return ea;
 	demod_pipe_kernel<P, N, IQ, SOFT, LAYOUT, TMA><<<n_groups, roles<LAYOUT>::NWARPS * 32, sizeof(smem_t<P>), stream>>>(*p, group_base);
 	return cudaGetLastError();
 }

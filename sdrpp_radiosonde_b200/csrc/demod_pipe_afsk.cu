@@ -520,13 +520,9 @@ demod_pipe_afsk_kernel(const demod_params p, const int group_base)
 template <bool IQ, bool SOFT, int LAYOUT>
 cudaError_t launch2(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
-	static bool attr_done = false;
-	if (!attr_done) {
-		cudaError_t e = cudaFuncSetAttribute(demod_pipe_afsk_kernel<IQ, SOFT, LAYOUT>,
-		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(asmem_t));
-		if (e != cudaSuccess) return e;
-		attr_done = true;
-	}
+	static std::atomic<unsigned long long> attr_done{0};
+	const cudaError_t ea = sonde_ensure_dynamic_smem(demod_pipe_afsk_kernel<IQ, SOFT, LAYOUT>, (int)sizeof(asmem_t), attr_done);
+	if (ea != cudaSuccess) return ea;
 	demod_pipe_afsk_kernel<IQ, SOFT, LAYOUT><<<n_groups, aroles<LAYOUT>::NWARPS * 32, sizeof(asmem_t), stream>>>(*p, group_base);
 	return cudaGetLastError();
 }

@@ -101,4 +101,23 @@ struct frame_params {
 	const int32_t *active;        /* [C] 0 = channel switched off (AUTO loser)        */
 };
 
+
+#ifdef __CUDACC__
+#include <atomic>
+/* Opt a kernel into its dynamic shared-memory size once per device.  The attribute is per device, and handles may
+ * live on different devices of one process (sonde_b200_config.device) and be created from different threads, so the
+ * "done" state is a per-kernel bit mask indexed by the current device (devices >= 64 simply set it every time). */
+template <class Kernel>
+static inline cudaError_t sonde_ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned long long> &done)
+{
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	if (dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+	e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (e == cudaSuccess && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+	return e;
+}
+#endif
+
 #endif

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -73,6 +75,7 @@ struct sonde_b200 {
 	long n_issued = 0, n_fetched = 0;
 	float *d_soft = nullptr;
 	int max_frames = 0, soft_stride = 0, bits_stride = 0;
+	bool rate_registered = false;
 	void *d_in[2] = {nullptr, nullptr};   /* staging for the host-buffer entry points */
 	void *d_in16[2] = {nullptr, nullptr}; /* raw int16 IQ staging of sonde_b200_process_iq_s16 */
 	int32_t *h_counts = nullptr;     /* pinned */
@@ -104,6 +107,24 @@ int fail(sonde_b200 *h, int code, const char *what, cudaError_t e = cudaSuccess)
 		cudaError_t e_ = (call);                                        \
 		if (e_ != cudaSuccess) return fail(h, SONDE_ERR_CUDA, #call, e_); \
 	} while (0)
+
+/* live handles per device and the sample rate their (per-device, __constant__) modem tables were built for;
+ * delta = +1 registers (false if the device is in use at another rate), -1 unregisters */
+bool rate_registry(int device, int samplerate, int delta)
+{
+	static std::mutex mtx;
+	static std::map<int, std::pair<int, int>> live;      /* device -> (samplerate, handles) */
+	std::lock_guard<std::mutex> lock(mtx);
+	auto &e = live[device];
+	if (delta > 0) {
+		if (e.second > 0 && e.first != samplerate) return false;
+		e.first = samplerate;
+		e.second++;
+	} else if (e.second > 0) {
+		e.second--;
+	}
+	return true;
+}
 
 uint32_t next_pow2(uint32_t v)
 {
@@ -180,6 +201,10 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 		}
 
 	if (cudaSetDevice(h->device) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	/* The modem tables live in __constant__ memory, one copy per device: all live handles of a device must agree on
+	 * the sample rate they were derived from. */
+	if (!rate_registry(h->device, cfg->samplerate, +1)) return bail(SONDE_ERR_STATE);
+	h->rate_registered = true;
 	if (sonde_upload_modems(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_frame(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
@@ -305,6 +330,7 @@ void sonde_b200_destroy(sonde_b200 *h)
 {
 	if (!h) return;
 	cudaSetDevice(h->device);
+	if (h->rate_registered) rate_registry(h->device, h->cfg.samplerate, -1);
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_group_chan); cudaFree(h->d_group_type); cudaFree(h->d_types);
 	cudaFree(h->d_demod); cudaFree(h->d_afsk); cudaFree(h->d_framer); cudaFree(h->d_ring);

@@ -452,3 +452,19 @@ def test_full_size_configs_replica_consistency_and_oracle(name):
             assert keys == [rec_key(w, rb) for w in want], (name, t, b)
     print(f"{name}: {C} channels x {n} samples, {sum(len(f) for f in frames)} frame windows, {n_ok} pass their gate")
     assert n_ok > C
+
+
+def test_handles_of_one_device_must_share_the_sample_rate():
+    """The modem tables are per-device __constant__ data: a second live handle at another sample rate is refused
+    (SONDE_ERR_STATE) instead of silently corrupting the first one's taps; it is accepted once the first is gone."""
+    a = capi.BatchDecoder([synth.RS41], 4096)
+    try:
+        with pytest.raises(capi.SondeError) as ei:
+            capi.BatchDecoder([synth.RS41], 4096, samplerate=96000)
+        assert ei.value.code == capi.ERR_STATE
+        b = capi.BatchDecoder([synth.DFM09], 4096)           # same rate: fine
+        b.close()
+    finally:
+        a.close()
+    c = capi.BatchDecoder([synth.RS41], 4096, samplerate=96000)
+    c.close()
