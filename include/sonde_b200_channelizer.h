@@ -60,7 +60,9 @@ SONDE_API void sonde_chan_destroy(sonde_chan *h);
  * and oscillator phases carry over).  Work is enqueued on `stream` (a cudaStream_t, e.g. sonde_b200_stream() of
  * the decoder that consumes the result, so that process_iq_device() may be called right after on the same
  * stream without a host sync).  *d_out receives the device address of the result, complex64 [C][*out_stride];
- * it stays valid until the second next process call (results are double buffered). */
+ * it stays valid until the second next process call (results are double buffered).  A host input buffer is copied
+ * asynchronously when it is pinned (sonde_b200_host_alloc) and must then stay untouched until the stream has passed
+ * the call. */
 SONDE_API int  sonde_chan_process_c64(sonde_chan *h, const float *wide_iq /* host [n_in][2] */, size_t n_in,
                                       void *stream, void **d_out, size_t *out_stride);
 SONDE_API int  sonde_chan_process_c64_device(sonde_chan *h, const void *d_wide_iq /* device [n_in][2] float */,

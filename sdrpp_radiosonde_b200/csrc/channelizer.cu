@@ -384,7 +384,9 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 	}
 
 	auto bail = [&](int code, const char *msg) { h->err = msg; sonde_chan_destroy(h); return code; };
-	const size_t nx = (size_t)h->H + (size_t)cfg->max_in_len * h->S + 2 * BK;      /* + slack */
+	/* the tensor map has at least one full tile of rows, so the buffer covers BM windows even for tiny max_in_len */
+	const size_t rows_dim = h->max_out > BM ? (size_t)h->max_out : (size_t)BM;
+	const size_t nx = (size_t)h->H + rows_dim * h->D * h->S + 2 * BK;      /* + slack */
 	if (cudaMalloc(&h->d_x, nx * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
 	if (cudaMemset(h->d_x, 0, nx * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMemset");
 	if (cudaMalloc(&h->d_tail, (size_t)h->H * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
@@ -404,7 +406,7 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 		return bail(SONDE_ERR_CUDA, "cuTensorMapEncodeTiled not available");
 	{
 		/* A: rows = output samples (pitch 2D elements), columns = 2 Kp interleaved re/im of the window */
-		const cuuint64_t gdim[2] = {(cuuint64_t)(2 * h->Kp), (cuuint64_t)h->max_out};     /* rows past max_out: zero fill, no access */
+		const cuuint64_t gdim[2] = {(cuuint64_t)(2 * h->Kp), (cuuint64_t)rows_dim};      /* rows past it: zero fill, no access */
 		const cuuint64_t gstr[1] = {(cuuint64_t)(2 * h->D * h->S) * 2};
 		const cuuint32_t box[2] = {BK, BM}, estr[2] = {1, 1};
 		if (encode(&h->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -170,6 +170,14 @@ def test_channelizer_entry_points_agree_and_reject_bad_arguments():
         ch.close()
     assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))
 
+    # a handle whose largest call is shorter than one 128-row tile
+    ch = capi.Channelizer(freqs, D, D * 10)
+    ptr, stride, m = ch.process_c64(xf[:D * 10])
+    torch.cuda.synchronize()
+    tiny = capi.device_view(ptr, (C, stride, 2))[:, :m].cpu().numpy()
+    ch.close()
+    assert m == 10 and np.array_equal(tiny.view(np.uint32), outs[1][:, :10].view(np.uint32))
+
     with pytest.raises(capi.SondeError):
         capi.Channelizer(freqs, 1, 100)                        # no decimation
     with pytest.raises(capi.SondeError):
