@@ -54,6 +54,7 @@ struct sonde_b200 {
 
 	/* CTA groups, sorted: GFSK 1-phase | GFSK 2-phase | AFSK */
 	int n_groups = 0, groups_v[4] = {0, 0, 0, 0};   /* per kernel variant, see sonde_launch_demod_pipe */
+	int group_capacity = 0;                         /* groups allocated at create (all virtual channels active) */
 	int32_t *d_group_chan = nullptr, *d_group_type = nullptr, *d_types = nullptr;
 
 	demod_state *d_demod = nullptr;
@@ -124,6 +125,38 @@ bool rate_registry(int device, int samplerate, int delta)
 		e.second--;
 	}
 	return true;
+}
+
+/* Sort the (active) virtual channels into type-homogeneous CTA groups of DEMOD_G, ordered by kernel variant:
+ * GFSK 1-phase ~10 slots/symbol | GFSK 1-phase ~20 slots/symbol | GFSK 2-phase | AFSK.  Sets h->groups_v / n_groups.
+ * Called at create (everything active) and again whenever AUTO channels lock, so that the surviving virtual
+ * channels are packed densely: a CTA costs the same whether one or eight of its lanes carry a channel. */
+void build_groups(sonde_b200 *h, const std::vector<int32_t> *active, std::vector<int32_t> &gchan, std::vector<int32_t> &gtype)
+{
+	const int C = h->cfg.n_channels;
+	gchan.clear();
+	gtype.clear();
+	auto add_groups = [&](auto pred) {
+		int added = 0;
+		for (int t = 0; t < SONDE_NTYPES; t++) {
+			if (!pred(h->modems[t])) continue;
+			std::vector<int32_t> ch;
+			for (int c = 0; c < C; c++)
+				if (h->types[c] == t && (!active || (*active)[c])) ch.push_back(c);
+			for (size_t i = 0; i < ch.size(); i += DEMOD_G) {
+				for (int k = 0; k < DEMOD_G; k++) gchan.push_back(i + k < ch.size() ? ch[i + k] : -1);
+				gtype.push_back(t);
+				added++;
+			}
+		}
+		return added;
+	};
+	/* NCO slots per symbol = 2 / freq0 */
+	h->groups_v[0] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 1 && m.freq0 >= 0.19f; });
+	h->groups_v[1] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 1 && m.freq0 < 0.19f; });
+	h->groups_v[2] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 2; });
+	h->groups_v[3] = add_groups([](const sonde_modem &m) { return m.baud && m.afsk; });
+	h->n_groups = (int)gtype.size();
 }
 
 uint32_t next_pow2(uint32_t v)
@@ -233,27 +266,8 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	/* ---- channel groups: type-homogeneous CTAs, ordered by kernel variant ---------------- */
 	const int C = h->cfg.n_channels;
 	std::vector<int32_t> gchan, gtype;
-	auto add_groups = [&](auto pred) {
-		int added = 0;
-		for (int t = 0; t < SONDE_NTYPES; t++) {
-			if (!pred(h->modems[t])) continue;
-			std::vector<int32_t> ch;
-			for (int c = 0; c < C; c++)
-				if (h->types[c] == t) ch.push_back(c);
-			for (size_t i = 0; i < ch.size(); i += DEMOD_G) {
-				for (int k = 0; k < DEMOD_G; k++) gchan.push_back(i + k < ch.size() ? ch[i + k] : -1);
-				gtype.push_back(t);
-				added++;
-			}
-		}
-		return added;
-	};
-	/* NCO slots per symbol = 2 / freq0 */
-	h->groups_v[0] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 1 && m.freq0 >= 0.19f; });
-	h->groups_v[1] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 1 && m.freq0 < 0.19f; });
-	h->groups_v[2] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 2; });
-	h->groups_v[3] = add_groups([](const sonde_modem &m) { return m.baud && m.afsk; });
-	h->n_groups = (int)gtype.size();
+	build_groups(h, nullptr, gchan, gtype);
+	h->group_capacity = (int)gtype.size();
 
 	/* ---- sizes ----------------------------------------------------------------------------- */
 	int bits_max = 0, frames_max = 0;
@@ -602,11 +616,17 @@ static int auto_update(sonde_b200 *h)
 		for (int k = 0; k < SONDE_NTYPES; k++)
 			if (h->types[h->slot0[c] + k] != h->locked[c]) active[h->slot0[c] + k] = 0;
 	}
-	std::vector<int32_t> gchan = h->gchan_host;
-	for (auto &g : gchan)
-		if (g >= 0 && !active[g]) g = -1;
+	/* regroup the surviving virtual channels densely (same kernels, fewer CTAs); the tables were sized for the
+	 * all-active case at create, so the rebuilt ones always fit */
+	std::vector<int32_t> gchan, gtype;
+	CK(cudaStreamSynchronize(h->stream));        /* launches in flight still read the old tables and group counts */
+	build_groups(h, &active, gchan, gtype);
+	h->gchan_host = gchan;
 	/* ordered on the main stream: takes effect from the next process call on */
-	CK(cudaMemcpyAsync(h->d_group_chan, gchan.data(), gchan.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+	if (!gchan.empty()) {
+		CK(cudaMemcpyAsync(h->d_group_chan, gchan.data(), gchan.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+		CK(cudaMemcpyAsync(h->d_group_type, gtype.data(), gtype.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+	}
 	CK(cudaMemcpyAsync(h->d_active, active.data(), active.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
 	CK(cudaStreamSynchronize(h->stream));        /* the host vectors above go out of scope */
 	return SONDE_OK;
@@ -815,8 +835,8 @@ int sonde_b200_debug_stalls(sonde_b200 *h, long long *out, int cap_groups)
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->stream));
 	if (!h->d_prof) {
-		CK(cudaMalloc(&h->d_prof, (size_t)h->n_groups * 16 * sizeof(long long)));
-		CK(cudaMemset(h->d_prof, 0, (size_t)h->n_groups * 16 * sizeof(long long)));
+		CK(cudaMalloc(&h->d_prof, (size_t)h->group_capacity * 16 * sizeof(long long)));
+		CK(cudaMemset(h->d_prof, 0, (size_t)h->group_capacity * 16 * sizeof(long long)));
 		return h->n_groups;
 	}
 	const int n = h->n_groups < cap_groups ? h->n_groups : cap_groups;

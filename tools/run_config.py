@@ -22,9 +22,13 @@ for c in range(C):
     row = base[int(types[c])][c % NB]
     iq[:, c, :] = row.view(NCH, L)
 iq += 0.02 * torch.view_as_complex(torch.randn((NCH, C, L, 2), device="cuda", generator=g))
-dec = capi.BatchDecoder(types, L)
+auto = len(sys.argv) > 3 and sys.argv[3] == "auto"
+dec = capi.BatchDecoder(np.full(C, -1, np.int32) if auto else types, L)
 for i in range(3):
     dec.process_iq_device(iq[i % NCH].data_ptr(), L)
+    if auto:
+        dec.fetch_counts()                # AUTO channels lock at fetch time
+        print("call", i, "kernel ms", dec.last_kernel_ms(), "locked", int((dec.detected_types() >= 0).sum()), "of", C)
 dec.sync()
 f0, k0, _ = dec.fetch_totals()
 ext = torch.cuda.ExternalStream(dec.stream)
