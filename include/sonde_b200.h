@@ -116,7 +116,12 @@ typedef struct {
 	                             dsp::demod::FM(samplerate=bw, bandwidth=bw/2)  src/main.cpp:57 */
 	int32_t keep_soft;        /* !=0: keep soft symbols for sonde_b200_fetch_soft()  */
 	int32_t reserved;         /* bit 0: use the phase-by-phase demod kernel (cross-check only); bit 1: never stage with TMA;
-	                             bit 2: alternative warp placement of the AFSK pipeline kernel (diagnostics) */
+	                             bit 2: alternative warp placement of the AFSK pipeline kernel (diagnostics);
+	                             bit 3: AUTO pre-classifier: before an unlocked AUTO channel is demodulated for the
+	                             first time a cheap kernel looks at the run lengths between zero crossings of its discriminator
+	                             output; if they identify one modem family unambiguously only that family's decoders are tried
+	                             (instead of all seven), and all seven are restored if the channel has not locked 3 s later.
+	                             Off by default: the default is the reference's try-all (SD/decode.c:174-224). */
 } sonde_b200_config;
 
 SONDE_API int  sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg);
@@ -158,6 +163,10 @@ SONDE_API int  sonde_b200_fetch_counts(sonde_b200 *h, int32_t *frames, int32_t *
 SONDE_API int  sonde_b200_detected_types(sonde_b200 *h, int32_t *types);
 
 /* Running totals since create, per channel: framer windows, windows passing the gate, demodulated bits. */
+/* masks[C]: bit t set = decoder type t is currently run for the channel (one bit for fixed and locked channels,
+ * seven for an unlocked AUTO channel unless the pre-classifier narrowed it) */
+SONDE_API int  sonde_b200_auto_plausible(sonde_b200 *h, uint32_t *masks);
+
 SONDE_API int  sonde_b200_fetch_totals(sonde_b200 *h, int64_t *frames, int64_t *ok, int64_t *bits);
 
 /* Parity taps for the last process call.

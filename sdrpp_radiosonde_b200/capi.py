@@ -23,7 +23,7 @@ _ERR_NAMES = {ERR_ARG: "SONDE_ERR_ARG", ERR_CUDA: "SONDE_ERR_CUDA", ERR_NODEVICE
 EXPORTS = [
     "sonde_b200_create", "sonde_b200_destroy", "sonde_b200_process_iq", "sonde_b200_process_fm",
     "sonde_b200_process_iq_s16", "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
-    "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_detected_types", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
+    "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_detected_types", "sonde_b200_auto_plausible", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
     "sonde_b200_soft_stride", "sonde_b200_fetch_soft", "sonde_b200_fetch_state", "sonde_b200_modem_info",
     "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
     "sonde_b200_last_kernel_ms", "sonde_b200_launch_count", "sonde_b200_last_error", "sonde_b200_version",
@@ -94,6 +94,7 @@ def load():
         "sonde_b200_fetch_counts": (ctypes.c_int, [vp, i32p, i32p]),
         "sonde_b200_fetch_totals": (ctypes.c_int, [vp, vp, vp, vp]),
         "sonde_b200_detected_types": (ctypes.c_int, [vp, i32p]),
+        "sonde_b200_auto_plausible": (ctypes.c_int, [vp, vp]),
         "sonde_b200_bits_stride": (ctypes.c_int, [vp]),
         "sonde_b200_fetch_bits": (ctypes.c_int, [vp, vp, i32p]),
         "sonde_b200_soft_stride": (ctypes.c_int, [vp]),
@@ -167,13 +168,14 @@ class BatchDecoder:
     """
 
     def __init__(self, types, max_chunk_len, samplerate=48000, device=0, fm_gain=0.0, keep_soft=False,
-                 legacy_kernel=False, no_tma=False, afsk_layout=0):
+                 legacy_kernel=False, no_tma=False, afsk_layout=0, auto_preclassify=False):
         self.lib = load()
         self.types = np.ascontiguousarray(types, dtype=np.int32)
         self.C = int(self.types.size)
         self.max_chunk_len = int(max_chunk_len)
         cfg = Config(self.C, samplerate, self.max_chunk_len, device, _i32p(self.types), fm_gain,
-                     1 if keep_soft else 0, (1 if legacy_kernel else 0) | (2 if no_tma else 0) | (4 if afsk_layout else 0))
+                     1 if keep_soft else 0, (1 if legacy_kernel else 0) | (2 if no_tma else 0) | (4 if afsk_layout else 0) |
+                     (8 if auto_preclassify else 0))
         h = ctypes.c_void_p()
         rc = self.lib.sonde_b200_create(ctypes.byref(h), ctypes.byref(cfg))
         if rc != SONDE_OK:
@@ -248,6 +250,12 @@ class BatchDecoder:
         ok = np.zeros(self.C, dtype=np.int32)
         self._ck(self.lib.sonde_b200_fetch_counts(self.h, _i32p(frames), _i32p(ok)))
         return frames, ok
+
+    def auto_plausible(self):
+        """Bit mask of decoder types currently run per channel (see sonde_b200_auto_plausible)."""
+        m = np.zeros(self.C, dtype=np.uint32)
+        self._ck(self.lib.sonde_b200_auto_plausible(self.h, m.ctypes.data))
+        return m
 
     def detected_types(self):
         """Decoder each channel reports (-1 = AUTO channel not locked yet)."""

@@ -34,6 +34,8 @@ extern "C" cudaError_t sonde_launch_demod_pipe(const demod_params *p, int group_
 extern "C" cudaError_t sonde_launch_demod_afsk(const demod_params *p, int group_base, int n_groups,
                                                cudaStream_t stream);
 extern "C" cudaError_t sonde_launch_frames(const frame_params *p, cudaStream_t stream);
+extern "C" cudaError_t sonde_launch_auto_classify(const void *d_in, size_t row_stride, int len, int is_iq,
+                                                  const int32_t *d_rows, int n, uint32_t *d_mask, cudaStream_t stream);
 
 struct sonde_b200 {
 	sonde_b200_config cfg;
@@ -77,6 +79,14 @@ struct sonde_b200 {
 	float *d_soft = nullptr;
 	int max_frames = 0, soft_stride = 0, bits_stride = 0;
 	bool rate_registered = false;
+	/* AUTO pre-classifier (opt-in, cfg.reserved bit 3): per user channel the set of decoder types
+	 * still tried while it is unlocked, when it was narrowed, and the device scratch of the classifier */
+	std::vector<uint32_t> plausible;     /* bit t: type t is tried; all ones = the reference's try-all              */
+	std::vector<int64_t> narrowed_at;    /* samples processed when `plausible` was narrowed, -1 = not narrowed     */
+	bool classify_pending = false;       /* some unlocked AUTO channel has not been classified yet                  */
+	int64_t samples_seen = 0;
+	int32_t *d_cls_rows = nullptr;
+	uint32_t *d_cls_mask = nullptr;
 	void *d_in[2] = {nullptr, nullptr};   /* staging for the host-buffer entry points */
 	void *d_in16[2] = {nullptr, nullptr}; /* raw int16 IQ staging of sonde_b200_process_iq_s16 */
 	int32_t *h_counts = nullptr;     /* pinned */
@@ -218,6 +228,9 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 		}
 	}
 	h->locked = h->user_types;
+	h->plausible.assign(cfg->n_channels, (1u << SONDE_NTYPES) - 1u);
+	h->narrowed_at.assign(cfg->n_channels, -1);
+	h->classify_pending = h->has_auto;
 	h->cfg.n_channels = (int32_t)h->types.size();        /* device-side channel count from here on */
 	h->cfg.types = h->types.data();
 	h->device = cfg->device;
@@ -348,7 +361,7 @@ void sonde_b200_destroy(sonde_b200 *h)
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_group_chan); cudaFree(h->d_group_type); cudaFree(h->d_types);
 	cudaFree(h->d_demod); cudaFree(h->d_afsk); cudaFree(h->d_framer); cudaFree(h->d_ring);
-	cudaFree(h->d_prof); cudaFree(h->d_in_row); cudaFree(h->d_active);
+	cudaFree(h->d_prof); cudaFree(h->d_in_row); cudaFree(h->d_active); cudaFree(h->d_cls_rows); cudaFree(h->d_cls_mask);
 	for (int b = 0; b < 2; b++) {
 		cudaFree(h->d_recs[b]); cudaFree(h->d_counts[b]); cudaFree(h->d_in[b]); cudaFree(h->d_in16[b]); cudaFree(h->d_nbits[b]);
 		if (h->ev_demod[b]) cudaEventDestroy(h->ev_demod[b]);
@@ -372,6 +385,91 @@ void sonde_b200_destroy(sonde_b200 *h)
 	delete h;
 }
 
+/* which virtual channels run: a fixed channel always; an AUTO channel's locked decoder once it has locked,
+ * otherwise the decoders its `plausible` mask allows (all seven unless the pre-classifier narrowed it) */
+static void compute_active(const sonde_b200 *h, std::vector<int32_t> &active)
+{
+	active.assign(h->cfg.n_channels, 1);
+	for (int c = 0; c < h->n_user; c++) {
+		if (h->user_types[c] != SONDE_AUTO) continue;
+		for (int k = 0; k < SONDE_NTYPES; k++) {
+			const int t = h->types[h->slot0[c] + k];
+			const bool on = h->locked[c] != SONDE_AUTO ? (t == h->locked[c]) : ((h->plausible[c] >> t) & 1u);
+			active[h->slot0[c] + k] = on ? 1 : 0;
+		}
+	}
+}
+
+/* regroup the active virtual channels densely (same kernels, fewer CTAs) and publish the new tables; the tables
+ * were sized for the all-active case at create, so rebuilt ones always fit */
+static int apply_active(sonde_b200 *h)
+{
+	std::vector<int32_t> active, gchan, gtype;
+	compute_active(h, active);
+	CK(cudaStreamSynchronize(h->stream));        /* launches in flight still read the old tables and group counts */
+	build_groups(h, &active, gchan, gtype);
+	h->gchan_host = gchan;
+	if (!gchan.empty()) {
+		CK(cudaMemcpyAsync(h->d_group_chan, gchan.data(), gchan.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+		CK(cudaMemcpyAsync(h->d_group_type, gtype.data(), gtype.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+	}
+	CK(cudaMemcpyAsync(h->d_active, active.data(), active.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+	CK(cudaStreamSynchronize(h->stream));        /* the host vectors above go out of scope */
+	return SONDE_OK;
+}
+
+/* AUTO pre-classifier policy, run at the start of a process call (before the demodulators are launched):
+ *   - unlocked AUTO channels that have not been looked at yet are classified on this buffer; a channel whose
+ *     run-length histogram is unambiguous only keeps the decoders of that family, the others stay "try all";
+ *   - a channel narrowed more than FALLBACK_SECONDS of signal ago that still has not locked gets all seven back
+ *     (the reference's behaviour), so a wrong guess can only delay the lock. */
+static int auto_preclassify(sonde_b200 *h, const void *d_in, size_t len, size_t row_stride, int is_iq)
+{
+	const double FALLBACK_SECONDS = 3.0;
+	bool changed = false;
+	std::vector<int32_t> rows, users;
+	for (int c = 0; c < h->n_user; c++) {
+		if (h->user_types[c] != SONDE_AUTO || h->locked[c] != SONDE_AUTO) continue;
+		if (h->narrowed_at[c] >= 0 &&
+		    (double)(h->samples_seen - h->narrowed_at[c]) > FALLBACK_SECONDS * h->cfg.samplerate) {
+			h->plausible[c] = (1u << SONDE_NTYPES) - 1u;
+			h->narrowed_at[c] = -2;                          /* fell back: never narrowed again */
+			changed = true;
+		} else if (h->narrowed_at[c] == -1 && h->classify_pending) {
+			rows.push_back(c);                               /* input row of user channel c is c */
+			users.push_back(c);
+		}
+	}
+	if (!rows.empty()) {
+		const int n = (int)rows.size();
+		if (!h->d_cls_rows) {
+			CK(cudaMalloc(&h->d_cls_rows, (size_t)h->n_user * sizeof(int32_t)));
+			CK(cudaMalloc(&h->d_cls_mask, (size_t)h->n_user * sizeof(uint32_t)));
+		}
+		std::vector<uint32_t> mask(n);
+		CK(cudaMemcpyAsync(h->d_cls_rows, rows.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+		CK(sonde_launch_auto_classify(d_in, row_stride, (int)len, is_iq, h->d_cls_rows, n, h->d_cls_mask, h->stream));
+		h->launches++;
+		CK(cudaMemcpyAsync(mask.data(), h->d_cls_mask, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+		CK(cudaStreamSynchronize(h->stream));
+		const uint32_t all = (1u << SONDE_NTYPES) - 1u;
+		for (int i = 0; i < n; i++) {
+			const int c = users[i];
+			if (mask[i] != all && mask[i] != 0) {
+				h->plausible[c] = mask[i];
+				h->narrowed_at[c] = h->samples_seen;
+				changed = true;
+			} else if ((int)len >= 2048) {
+				h->narrowed_at[c] = -2;                      /* looked at, ambiguous: stays try-all */
+			}
+		}
+		h->classify_pending = false;
+		for (int c = 0; c < h->n_user; c++)
+			if (h->user_types[c] == SONDE_AUTO && h->locked[c] == SONDE_AUTO && h->narrowed_at[c] == -1) h->classify_pending = true;
+	}
+	return changed ? apply_active(h) : SONDE_OK;
+}
+
 static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_stride, int is_iq)
 {
 	if (!h) return SONDE_ERR_ARG;
@@ -379,6 +477,11 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	if (len > (size_t)h->cfg.max_chunk_len) return fail(h, SONDE_ERR_TOOLONG, "len > max_chunk_len");
 	if (row_stride < len) return fail(h, SONDE_ERR_ARG, "row_stride < len");
 	CK(cudaSetDevice(h->device));
+	if (h->has_auto && (h->cfg.reserved & 8)) {
+		const int rc = auto_preclassify(h, d_in, len, row_stride, is_iq);
+		if (rc != SONDE_OK) return rc;
+	}
+	h->samples_seen += (int64_t)len;
 
 	demod_params dp;
 	memset(&dp, 0, sizeof(dp));
@@ -596,7 +699,6 @@ static int pull_counts(sonde_b200 *h, int par)
 static int auto_update(sonde_b200 *h)
 {
 	bool changed = false;
-	std::vector<int32_t> active;
 	for (int c = 0; c < h->n_user; c++) {
 		if (h->user_types[c] != SONDE_AUTO || h->locked[c] != SONDE_AUTO) continue;
 		const int v0 = h->slot0[c];
@@ -608,28 +710,7 @@ static int auto_update(sonde_b200 *h)
 			}
 		}
 	}
-	if (!changed) return SONDE_OK;
-	const int V = h->cfg.n_channels;
-	active.assign(V, 1);
-	for (int c = 0; c < h->n_user; c++) {
-		if (h->user_types[c] != SONDE_AUTO || h->locked[c] == SONDE_AUTO) continue;
-		for (int k = 0; k < SONDE_NTYPES; k++)
-			if (h->types[h->slot0[c] + k] != h->locked[c]) active[h->slot0[c] + k] = 0;
-	}
-	/* regroup the surviving virtual channels densely (same kernels, fewer CTAs); the tables were sized for the
-	 * all-active case at create, so the rebuilt ones always fit */
-	std::vector<int32_t> gchan, gtype;
-	CK(cudaStreamSynchronize(h->stream));        /* launches in flight still read the old tables and group counts */
-	build_groups(h, &active, gchan, gtype);
-	h->gchan_host = gchan;
-	/* ordered on the main stream: takes effect from the next process call on */
-	if (!gchan.empty()) {
-		CK(cudaMemcpyAsync(h->d_group_chan, gchan.data(), gchan.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-		CK(cudaMemcpyAsync(h->d_group_type, gtype.data(), gtype.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-	}
-	CK(cudaMemcpyAsync(h->d_active, active.data(), active.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-	CK(cudaStreamSynchronize(h->stream));        /* the host vectors above go out of scope */
-	return SONDE_OK;
+	return changed ? apply_active(h) : SONDE_OK;
 }
 
 /* virtual channel whose results user channel c reports, -1 while an AUTO channel is undetermined */
@@ -651,6 +732,17 @@ static int fetch_counts_of(sonde_b200 *h, int par, int32_t *frames, int32_t *ok)
 		const int v = report_slot(h, c);
 		if (frames) frames[c] = v < 0 ? 0 : h->h_counts[2 * v];
 		if (ok) ok[c] = v < 0 ? 0 : h->h_counts[2 * v + 1];
+	}
+	return SONDE_OK;
+}
+
+int sonde_b200_auto_plausible(sonde_b200 *h, uint32_t *masks)
+{
+	if (!h || !masks) return SONDE_ERR_ARG;
+	for (int c = 0; c < h->n_user; c++) {
+		if (h->user_types[c] != SONDE_AUTO) masks[c] = 1u << h->user_types[c];
+		else if (h->locked[c] != SONDE_AUTO) masks[c] = 1u << h->locked[c];
+		else masks[c] = h->plausible[c];
 	}
 	return SONDE_OK;
 }

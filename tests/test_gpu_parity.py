@@ -468,3 +468,69 @@ def test_handles_of_one_device_must_share_the_sample_rate():
         a.close()
     c = capi.BatchDecoder([synth.RS41], 4096, samplerate=96000)
     c.close()
+
+
+def _run_auto(batch_chunks, n_ch, chunk, preclassify):
+    dec = capi.BatchDecoder(np.full(n_ch, -1, np.int32), chunk, auto_preclassify=preclassify)
+    hist, masks, frames = [], [], [[] for _ in range(n_ch)]
+    demod_ms = []
+    try:
+        for part in batch_chunks:
+            dec.process_fm(np.ascontiguousarray(part))
+            recs, counts = dec.fetch()
+            demod_ms.append(dec.last_kernel_ms()[0])
+            hist.append(dec.detected_types().copy())
+            masks.append(dec.auto_plausible().copy())
+            for c in range(n_ch):
+                frames[c].extend(recs[c, :counts[c]].copy())
+    finally:
+        dec.close()
+    return hist, masks, frames, demod_ms
+
+
+def test_auto_preclassifier_same_locks_less_work():
+    """with the run-length pre-classifier every AUTO channel locks to the same decoder in the
+    same buffer and reports the same records as the reference's try-all, while only the decoders of one modem family
+    run during acquisition."""
+    n, chunk = 48000 * 3, 48000
+    sig_types = [t for t in range(7) for _ in range(3)]
+    batch = np.stack([synth.make_fm(synth.default_spec(t, 70 + c), n) for c, t in enumerate(sig_types)])
+    chunks = [batch[:, p:p + chunk] for p in range(0, n, chunk)]
+    h0, m0, f0, t0 = _run_auto(chunks, len(sig_types), chunk, False)
+    h1, m1, f1, t1 = _run_auto(chunks, len(sig_types), chunk, True)
+    for a, b in zip(h0, h1):
+        assert np.array_equal(a, b)
+    assert np.array_equal(h1[-1], np.array(sig_types))
+    for c in range(len(sig_types)):
+        rb = (synth.MODEMS[sig_types[c]].frame_bits + 7) // 8
+        k1, k0 = [rec_key(r, rb) for r in f1[c]], [rec_key(r, rb) for r in f0[c]]
+        assert len(k1) == len(k0), (c, sig_types[c], len(k1), len(k0))
+        for i, (x, y) in enumerate(zip(k1, k0)):
+            assert x == y, (c, sig_types[c], i, [j for j in range(len(x)) if x[j] != y[j]], x[:6], y[:6])
+    family = {0: {0}, 2: {2}, 6: {6}, 5: {5}, 1: {1, 3, 4}, 3: {1, 3, 4}, 4: {1, 3, 4}}
+    tried = 0
+    for c, t in enumerate(sig_types):
+        # the mask reported after the first buffer is either already the lock (one bit) or the narrowed family
+        bits = {k for k in range(7) if (int(m1[0][c]) >> k) & 1}
+        assert t in bits and bits <= family[t], (c, t, bits)
+        tried += len(family[t])
+    print(f"acquisition buffer: demod kernels {t0[0]:.3f} ms try-all vs {t1[0]:.3f} ms pre-classified "
+          f"({7 * len(sig_types)} vs {tried} decoder instances)")
+    assert t1[0] < t0[0]
+
+
+def test_auto_preclassifier_wrong_guess_falls_back():
+    """A narrowing decision can only delay a lock: a channel that looks like an SRS-C50 in its first buffer and then
+    carries an RS41 gets all seven decoders back after 3 s without a lock and locks to RS41."""
+    chunk, nbuf = 48000, 9
+    c50 = synth.make_fm(synth.default_spec(synth.C50, 1), chunk)
+    rs41 = synth.make_fm(synth.default_spec(synth.RS41, 2), chunk * (nbuf - 1))
+    sig = np.concatenate([c50, rs41])[None, :]
+    chunks = [sig[:, p:p + chunk] for p in range(0, chunk * nbuf, chunk)]
+    hist, masks, frames, _ = _run_auto(chunks, 1, chunk, True)
+    assert int(hist[0][0]) in (-1, synth.C50)
+    if int(hist[0][0]) == -1:                     # not locked on the single C50 buffer: narrowed to C50, then restored
+        assert int(masks[0][0]) == 1 << synth.C50
+        assert any(int(m[0]) == 0x7F for m in masks)
+        assert int(hist[-1][0]) == synth.RS41
+        assert sum(int(r["ok"]) for r in frames[0]) > 0
