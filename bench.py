@@ -358,119 +358,130 @@ def main():
         dec2.close()
         for pb in pins:
             pb.free()
-        # the same loop through the int16 entry point (half the PCIe bytes; informational, `e2e` stays complex64)
-        pins16 = [capi.PinnedBuffer((C, L, 2), np.int16) for _ in range(nbuf)]
-        for k, pb in enumerate(pins16):
-            blk = host_iq[:, k * L:(k + 1) * L]
-            pb.array[..., 0] = np.clip(np.round(blk.real * 16384.0), -32768, 32767)
-            pb.array[..., 1] = np.clip(np.round(blk.imag * 16384.0), -32768, 32767)
-        dec4 = capi.BatchDecoder(types, L, device=local_rank)
-        for i in range(2):
-            dec4.process_s16_host_ptr(pins16[i % nbuf].ptr, L)
-            dec4.fetch()
-        barrier()
-        t0 = time.perf_counter()
-        ok16 = 0
-        dec4.process_s16_host_ptr(pins16[0].ptr, L)
-        for i in range(args.steps):
-            if i + 1 < args.steps:
-                dec4.process_s16_host_ptr(pins16[(i + 1) % nbuf].ptr, L)
-            recs, counts = dec4.fetch()
-            ok16 += int(sum(int(recs[c, j]["ok"]) for c in range(0, C, 64) for j in range(counts[c])))
-        torch.cuda.synchronize()
-        dec4.sync()
-        e2e["t16"] = time.perf_counter() - t0
-        e2e["ok16"] = ok16
-        dec4.close()
-        for pb in pins16:
-            pb.free()
+        try:
+            # the same loop through the int16 entry point (half the PCIe bytes; informational, `e2e` stays complex64)
+            pins16 = [capi.PinnedBuffer((C, L, 2), np.int16) for _ in range(nbuf)]
+            for k, pb in enumerate(pins16):
+                blk = host_iq[:, k * L:(k + 1) * L]
+                pb.array[..., 0] = np.clip(np.round(blk.real * 16384.0), -32768, 32767)
+                pb.array[..., 1] = np.clip(np.round(blk.imag * 16384.0), -32768, 32767)
+            dec4 = capi.BatchDecoder(types, L, device=local_rank)
+            for i in range(2):
+                dec4.process_s16_host_ptr(pins16[i % nbuf].ptr, L)
+                dec4.fetch()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ok16 = 0
+            dec4.process_s16_host_ptr(pins16[0].ptr, L)
+            for i in range(args.steps):
+                if i + 1 < args.steps:
+                    dec4.process_s16_host_ptr(pins16[(i + 1) % nbuf].ptr, L)
+                recs, counts = dec4.fetch()
+                ok16 += int(sum(int(recs[c, j]["ok"]) for c in range(0, C, 64) for j in range(counts[c])))
+            torch.cuda.synchronize()
+            dec4.sync()
+            e2e["t16"] = time.perf_counter() - t0
+            e2e["ok16"] = ok16
+            dec4.close()
+            for pb in pins16:
+                pb.free()
+
+        except Exception as ex:                      # informational extra: never lose the main line over it
+            e2e["t16"], e2e["ok16"], e2e["err16"] = 0.0, 0, f"{type(ex).__name__}: {ex}"
 
     # wideband front end: one host buffer of wideband IQ per step -> tcgen05 channelizer -> the same
     # C-channel decode, chained on the decoder's stream.  H2D is D*48 kS/s * 8 B instead of C*48 kS/s * 8 B.
     wide = None
     if not args.no_e2e:
-        Dw = 48
-        n_in = L * Dw
-        rngw = np.random.default_rng(7 + rank)
-        freqs = rngw.uniform(-0.45, 0.45, C) * FS * Dw
-        pinw = [capi.PinnedBuffer((n_in,), np.complex64) for _ in range(2)]
-        for pb in pinw:
-            pb.array[...] = (0.05 * (rngw.standard_normal(n_in) + 1j * rngw.standard_normal(n_in))).astype(np.complex64)
-        chz = capi.Channelizer(freqs, Dw, n_in, device=local_rank)
-        dec5 = capi.BatchDecoder(types, L, device=local_rank)
-        # the copy and the channelizer of step i+1 run on a side stream beside the decode of step i
-        side, ext5 = torch.cuda.Stream(), torch.cuda.ExternalStream(dec5.stream)
-        done = [None, None]
-        def wstep(i):
-            if done[i & 1] is not None:
-                side.wait_event(done[i & 1])          # decode(i-2) has read the output buffer this call overwrites
-            ptr, stride, m = chz.process_c64_host_ptr(pinw[i % 2].ptr, n_in, stream=side.cuda_stream)
-            ev = torch.cuda.Event()
-            ev.record(side)
-            ext5.wait_event(ev)
-            dec5.process_iq_device(ptr, m, stride)
-            done[i & 1] = torch.cuda.Event()
-            done[i & 1].record(ext5)
-        for i in range(3):
-            wstep(i)
-            dec5.fetch_counts()
-        barrier()
-        t0 = time.perf_counter()
-        wstep(0)
-        for i in range(args.steps):
-            if i + 1 < args.steps:
-                wstep(i + 1)
-            dec5.fetch_counts()
-        dec5.sync()
-        torch.cuda.synchronize()
-        wide = {"t": time.perf_counter() - t0, "gemm_ms": chz.last_kernel_ms(), "h2d": n_in * 8, "D": Dw, "taps": chz.K}
-        chz.close()
-        dec5.close()
-        for pb in pinw:
-            pb.free()
+        try:
+            Dw = 48
+            n_in = L * Dw
+            rngw = np.random.default_rng(7 + rank)
+            freqs = rngw.uniform(-0.45, 0.45, C) * FS * Dw
+            pinw = [capi.PinnedBuffer((n_in,), np.complex64) for _ in range(2)]
+            for pb in pinw:
+                pb.array[...] = (0.05 * (rngw.standard_normal(n_in) + 1j * rngw.standard_normal(n_in))).astype(np.complex64)
+            chz = capi.Channelizer(freqs, Dw, n_in, device=local_rank)
+            dec5 = capi.BatchDecoder(types, L, device=local_rank)
+            # the copy and the channelizer of step i+1 run on a side stream beside the decode of step i
+            side, ext5 = torch.cuda.Stream(), torch.cuda.ExternalStream(dec5.stream)
+            done = [None, None]
+            def wstep(i):
+                if done[i & 1] is not None:
+                    side.wait_event(done[i & 1])          # decode(i-2) has read the output buffer this call overwrites
+                ptr, stride, m = chz.process_c64_host_ptr(pinw[i % 2].ptr, n_in, stream=side.cuda_stream)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                ext5.wait_event(ev)
+                dec5.process_iq_device(ptr, m, stride)
+                done[i & 1] = torch.cuda.Event()
+                done[i & 1].record(ext5)
+            for i in range(3):
+                wstep(i)
+                dec5.fetch_counts()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            wstep(0)
+            for i in range(args.steps):
+                if i + 1 < args.steps:
+                    wstep(i + 1)
+                dec5.fetch_counts()
+            dec5.sync()
+            torch.cuda.synchronize()
+            wide = {"t": time.perf_counter() - t0, "gemm_ms": chz.last_kernel_ms(), "h2d": n_in * 8, "D": Dw, "taps": chz.K}
+            chz.close()
+            dec5.close()
+            for pb in pinw:
+                pb.free()
+        except Exception as ex:                      # informational extra
+            wide = {"error": f"{type(ex).__name__}: {ex}"}
 
     # N > 1: the one exchange step the path can have — the whole batch originates on rank 0 and is
     # scattered over NVLink chunk by chunk, double-buffered against the decode.  Reported beside the main number,
     # which is measured with every rank's shard already resident.
     scatter = None
     if world > 1 and not args.no_scatter:
-        from sdrpp_radiosonde_b200 import shard
-        n_sc = 6
-        full = [dev_iq[k].repeat(world, 1) for k in range(2)] if rank == 0 else [None, None]
-        bufs = [torch.empty((C, L), dtype=torch.complex64, device="cuda") for _ in range(2)]
-        dec3 = capi.BatchDecoder(types, L, device=local_rank)
-        shard.scatter_channels(full[0], bufs[0], world, rank)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(n_sc):
-            dec3.sync()                                   # decode(i-1) no longer reads bufs[(i+1) % 2]
-            dec3.process_iq_device(bufs[i % 2].data_ptr(), L)      # overlaps the scatter of the next chunk
-            works = shard.scatter_channels(full[(i + 1) % 2], bufs[(i + 1) % 2], world, rank, async_op=True) \
-                if i + 1 < n_sc else []
-            for w in works:
-                w.wait()
-            torch.cuda.current_stream().synchronize()
-        dec3.sync()
-        barrier()
-        t_sc = time.perf_counter() - t0
-        # scatter alone
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(n_sc):
-            shard.scatter_channels(full[i % 2], bufs[i % 2], world, rank)
-            torch.cuda.current_stream().synchronize()
-        barrier()
-        t_so = time.perf_counter() - t0
-        scatter = {"t": t_sc, "t_only": t_so, "n": n_sc}
-        dec3.close()
-        del full, bufs
+        try:
+            from sdrpp_radiosonde_b200 import shard
+            n_sc = 6
+            full = [dev_iq[k].repeat(world, 1) for k in range(2)] if rank == 0 else [None, None]
+            bufs = [torch.empty((C, L), dtype=torch.complex64, device="cuda") for _ in range(2)]
+            dec3 = capi.BatchDecoder(types, L, device=local_rank)
+            shard.scatter_channels(full[0], bufs[0], world, rank)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(n_sc):
+                dec3.sync()                                   # decode(i-1) no longer reads bufs[(i+1) % 2]
+                dec3.process_iq_device(bufs[i % 2].data_ptr(), L)      # overlaps the scatter of the next chunk
+                works = shard.scatter_channels(full[(i + 1) % 2], bufs[(i + 1) % 2], world, rank, async_op=True) \
+                    if i + 1 < n_sc else []
+                for w in works:
+                    w.wait()
+                torch.cuda.current_stream().synchronize()
+            dec3.sync()
+            barrier()
+            t_sc = time.perf_counter() - t0
+            # scatter alone
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(n_sc):
+                shard.scatter_channels(full[i % 2], bufs[i % 2], world, rank)
+                torch.cuda.current_stream().synchronize()
+            barrier()
+            t_so = time.perf_counter() - t0
+            scatter = {"t": t_sc, "t_only": t_so, "n": n_sc}
+            dec3.close()
+            del full, bufs
+        except Exception as ex:                      # informational extra
+            scatter = None
+            print(f"scatter measurement failed: {type(ex).__name__}: {ex}", file=sys.stderr)
 
     stop.set()
     th.join(timeout=2)
 
     t_all = torch.tensor([ms, (e2e["t"] * 1e3) if e2e else 0.0, scatter["t"] * 1e3 if scatter else 0.0,
                           scatter["t_only"] * 1e3 if scatter else 0.0, (e2e["t16"] * 1e3) if e2e else 0.0,
-                          (wide["t"] * 1e3) if wide else 0.0],
+                          (wide["t"] * 1e3) if wide and "t" in wide else 0.0],
                          dtype=torch.float64, device="cuda")
     tot = torch.tensor([frames, ok], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -521,12 +532,14 @@ def main():
                            "note": "bounded by the host link: every step moves C*L*8 bytes of complex64 IQ over PCIe; "
                                    "h2d_link_gbs_measured is a bare pinned-memory copy of the same buffer on rank 0"}
             t16 = float(t_all[4])
-            line["e2e_s16"] = {"value": world * args.steps * C * L / (t16 * 1e-3) / 1e6, "unit": UNIT,
+            line["e2e_s16"] = {"error": e2e["err16"]} if e2e.get("err16") or t16 <= 0 else {"value": world * args.steps * C * L / (t16 * 1e-3) / 1e6, "unit": UNIT,
                                "h2d_bytes_per_step": C * L * 4, "ms_per_step": t16 / args.steps,
                                "note": "same loop through sonde_b200_process_iq_s16 (int16 IQ quantised from the same "
                                        "signals, converted on the GPU); informational — `e2e` is the complex64 entry point",
                                "decodable_frames_sampled": e2e["ok16"]}
-        if wide:
+        if wide and "error" in wide:
+            line["e2e_wideband"] = wide
+        elif wide:
             tw = float(t_all[5])
             line["e2e_wideband"] = {"value": world * args.steps * C * L / (tw * 1e-3) / 1e6, "unit": UNIT,
                                     "ms_per_step": tw / args.steps, "h2d_bytes_per_step": wide["h2d"],
