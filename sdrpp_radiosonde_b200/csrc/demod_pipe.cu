@@ -365,7 +365,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			mbar_wait_t(&sm.yfull[ss], (k / NS2) & 1, wacc[0], prof_on);
 			const float (*y)[G][RS] = sm.y[ss];
 			const int ns = own ? n * P : 0;
-			tm_tile<P, N, SOFT, G, RS>(tr, rf, y, g, ns, center, alpha, beta, max_fdev, DELTA, ring, ring_mask, soft,
+			tm_tile<P, N, SOFT, G, RS, (P == 2 ? 8 : 0)>(tr, rf, y, g, ns, center, alpha, beta, max_fdev, DELTA, ring, ring_mask, soft,
 			                           p.soft_stride, n_rounds, n_slow, prof_on);
 			__syncwarp();
 			warp_arrive(&sm.yfree[ss], lane);
