@@ -44,7 +44,8 @@ using namespace pipe;
  * to any PW warp on their scheduler.  Two placements, picked per kernel variant from measurements
  * (tools/stalls.py):
  *   layout 0 (timing lane is the critical stage: RS41, M10): TM alone on SMSP3
- *        SMSP0: 6 PW | SMSP1: 6 PW | SMSP2: A1, A2, 4 PW | SMSP3: TM, LD (+ 3 warps that exit at once)
+ *        SMSP0: 6 PW, LD | SMSP1: 6 PW | SMSP2: A1, A2, 4 PW | SMSP3: TM (+ 5 warps that exit at once); the producer's
+ *        barrier polling next to the timing lane cost it ~2 cycles/sample
  *   layout 1 (AGC lanes are the critical stage: DFM, iMS-100, MRZ-N1): all three serial lanes on SMSP3
  *        SMSP0: 6 PW | SMSP1: 5 PW | SMSP2: 5 PW | SMSP3: TM, A1, A2, LD
  * LD is the TMA producer warp: one lane issues the bulk copies of the input tiles (it exits at once when the
@@ -53,8 +54,8 @@ template <int LAYOUT>
 struct roles;
 template <>
 struct roles<0> {
-	static constexpr int NWARPS = 23, W_TM = 3, W_A1 = 2, W_A2 = 6, W_LD = 7;
-	static __device__ __forceinline__ bool idle(int warp) { return (warp & 3) == 3 && warp != W_TM && warp != W_LD; }
+	static constexpr int NWARPS = 25, W_TM = 3, W_A1 = 2, W_A2 = 6, W_LD = 24;
+	static __device__ __forceinline__ bool idle(int warp) { return (warp & 3) == 3 && warp != W_TM; }
 	static __device__ __forceinline__ int pw_index(int warp)
 	{
 		const int q = warp >> 2, r = warp & 3;        /* ids 0,4,..,20 -> 0..5 ; 1,5,..,21 -> 6..11 ; 10,14,18,22 -> 12..15 */
@@ -71,6 +72,8 @@ struct roles<1> {
 		return r == 0 ? q : r == 1 ? 6 + q : 11 + q;
 	}
 };
+constexpr int NRAW = 3;                  /* bulk-copy ring: S1 runs two tiles ahead of S3, the copies one more */
+
 template <int P>
 struct smem_t {
 	float x[NX][G][RS];                  /* discriminator output / FM input          */
@@ -78,13 +81,13 @@ struct smem_t {
 	float v[NS2][G][RS];                 /* moving_avg before each sample's update   */
 	float a[NS2][G][AS];                 /* AGC output, [0,48) = previous tile tail  */
 	float y[NS2][P][G][RS];              /* FIR output per polyphase branch          */
-	float2 raw[2][G][T];                 /* TMA landing zone: raw IQ (or FM in .x-packed form) of two tiles */
+	float2 raw[NRAW][G][T];              /* TMA landing zone: raw IQ (or FM in .x-packed form), NRAW tiles in flight */
 	float ph[G][RS];                     /* S1 scratch: phases, [g][0] = previous    */
 	float carry[2][G];                   /* last phase of the previous tile          */
 	float2 taps[P * SONDE_FIR_TAPS];     /* each tap duplicated for the packed fp32x2 FIR */
 	int   zflag[NX];                     /* tile contains exact-zero samples         */
 	unsigned long long negzero2;         /* (-0.0f, -0.0f), read at run time so that the packed product stays an FFMA2 */
-	unsigned long long rawfull[2], rawfree[2];   /* complete_tx barriers of the bulk copies / slot released by PW */
+	unsigned long long rawfull[NRAW], rawfree[NRAW];   /* complete_tx barriers of the bulk copies / slot released by PW */
 	int chan[G], row[G];
 	unsigned long long xfull[NX], sfull[NS2], sfree[NS2], vfull[NS2], vfree[NS2], yfull[NS2], yfree[NS2];
 };
@@ -113,8 +116,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	/* ---- prologue ------------------------------------------------------------------------- */
 	if (tid == 0) {
 		sm.negzero2 = 0x8000000080000000ull;
-		mbar_init(&sm.rawfull[0], 1); mbar_init(&sm.rawfull[1], 1);
-		mbar_init(&sm.rawfree[0], NPW); mbar_init(&sm.rawfree[1], NPW);
+		for (int i = 0; i < NRAW; i++) { mbar_init(&sm.rawfull[i], 1); mbar_init(&sm.rawfree[i], NPW); }
 		for (int i = 0; i < NX; i++) { mbar_init(&sm.xfull[i], NPW); sm.zflag[i] = 0; }
 		for (int i = 0; i < NS2; i++) {
 			mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sfree[i], 1 + NPW);
@@ -136,12 +138,12 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 	if (RL::idle(warp)) return;
 	if (warp == W_LD) {
 		/* =============================== LD: TMA producer ===================================
-		 * 8 bulk copies per tile (one 2 KB row segment per channel) into sm.raw, two tiles ahead. */
+		 * 8 bulk copies per tile (one 2 KB row segment per channel) into sm.raw, up to NRAW tiles ahead. */
 		if (TMA && lane == 0) {
 			constexpr uint32_t ESZ = IQ ? 8u : 4u;
 			for (int tile = 0; tile < ntiles; tile++) {
-				const int slot = tile & 1;
-				if (tile >= 2) mbar_wait(&sm.rawfree[slot], ((tile >> 1) - 1) & 1);
+				const int slot = tile % NRAW;
+				if (tile >= NRAW) mbar_wait(&sm.rawfree[slot], ((tile / NRAW) - 1) & 1);
 				const int n = min(T, L - tile * T);
 				const uint32_t bytes = (uint32_t)n * ESZ;
 				uint32_t total = 0;
@@ -199,16 +201,16 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			float cur[CPT];
 			if (pt == 0) sm.zflag[slot] = 0;
 			if (tma) {
-				mbar_wait_t(&sm.rawfull[tile & 1], (tile >> 1) & 1, wacc[1], prof_on);
+				mbar_wait_t(&sm.rawfull[tile % NRAW], (tile / NRAW) & 1, wacc[1], prof_on);
 #pragma unroll
 				for (int c = 0; c < CPT; c++) {
 					q[c] = make_float2(0.0f, 0.0f);
 					if (t < n && ch_of[c] >= 0) {
-						if (IQ) q[c] = sm.raw[tile & 1][g0 + c][t];
-						else    q[c].x = reinterpret_cast<const float *>(&sm.raw[tile & 1][g0 + c][0])[t];
+						if (IQ) q[c] = sm.raw[tile % NRAW][g0 + c][t];
+						else    q[c].x = reinterpret_cast<const float *>(&sm.raw[tile % NRAW][g0 + c][0])[t];
 					}
 				}
-				warp_arrive(&sm.rawfree[tile & 1], lane);      /* values are in registers: the slot may be refilled */
+				warp_arrive(&sm.rawfree[tile % NRAW], lane);   /* values are in registers: the slot may be refilled */
 			}
 #pragma unroll
 			for (int c = 0; c < CPT; c++) {
@@ -238,14 +240,17 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 
 		prefetch(0);
 		stage1(0);
+		if (ntiles > 1) stage1(1);
 
 		for (int k = 0; k < ntiles; k++) {
 			const int n = min(T, L - k * T);
 			const int xs = k % NX, ss = k % NS2;
 			const uint32_t par = (k / NS2) & 1;
 
-			/* ---- S1(k+1) ---- */
-			if (k + 1 < ntiles) stage1(k + 1);
+			/* ---- S1(k+2) ---- */
+			/* two tiles ahead: the AGC lanes need about one PW iteration for a tile (A1 then A2), so with S1 only one
+			 * tile ahead S3(k) would wait for them */
+			if (k + 2 < ntiles) stage1(k + 2);
 
 			/* ---- S3(k): a = s * (5 / avg_before)  (agc.c:27,31); zero samples pass as 0 ---- */
 			mbar_wait_t(&sm.vfull[ss], par, wacc[0], prof_on);            /* implies sfull[ss] (A2 consumed it first) */
