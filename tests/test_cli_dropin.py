@@ -29,12 +29,13 @@ def run_tool(exe, flag, raw, outdir, tag):
 
 
 def normalise_kml(kml: bytes) -> bytes:
-    """The tool's final <Point> prints KMLFile.lat/lon/alt, which kml_init() never initialises (SD/io/kml.c:12-27): when
-    no track point was ever written it is whatever the stack held, which differs between two binaries.  Mask that one
-    line in that one case; everything else is compared verbatim."""
+    """The tool's closing <Placemark><Point> block prints KMLFile.lat/lon/alt — and is only written at all if they are
+    >= 0 — but kml_init() never initialises them (SD/io/kml.c:12-27,138-160): when no track point was ever written they
+    are whatever the stack held, which differs between two binaries and between runs.  In that one case the block is
+    dropped from both files; everything else is compared verbatim."""
     if re.search(rb"^-?\d+\.\d+,-?\d+\.\d+,-?\d+\.\d+$", kml, flags=re.M):
         return kml
-    return re.sub(rb"(<Point>\s*<altitudeMode>absolute</altitudeMode>\s*<coordinates>)[^<]*(</coordinates>)", rb"\1UNINIT\2", kml)
+    return re.sub(rb"<Placemark>\s*<name>[^<]*</name>\s*<Point>.*?</Point>\s*</Placemark>\s*", b"", kml, flags=re.S)
 
 
 @needs_cli
