@@ -21,9 +21,23 @@ import channelizer_oracle as orc  # noqa: E402
 
 
 def test_channelizer_symbols_exported():
+    """every symbol include/sonde_b200_channelizer.h declares is exported, and nothing else is claimed"""
+    import re
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "sonde_b200_channelizer.h")).read()
+    declared = set(re.findall(r"SONDE_API\s+[\w\s\*]+?\b(sonde_chan_\w+)\s*\(", hdr))
+    assert declared == set(capi.CHAN_EXPORTS), declared ^ set(capi.CHAN_EXPORTS)
     lib = ctypes.CDLL(capi.LIB_PATH)
-    for name in capi.CHAN_EXPORTS:
+    for name in declared:
         assert hasattr(lib, name), name
+
+
+def test_channelizer_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.SondeError) as e:
+        capi.Channelizer([0.0], 8, 8 * 100)
+    assert e.value.code == capi.ERR_NODEVICE
 
 
 def test_oracle_tone_goes_to_dc_and_bf16_rounding():
