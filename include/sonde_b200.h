@@ -196,6 +196,10 @@ SONDE_API void  sonde_b200_host_free(void *p);
  * warps, AGC bias lane, AGC level lane, timing lane.  Returns the number of CTA groups. */
 SONDE_API int  sonde_b200_debug_stalls(sonde_b200 *h, long long *out, int cap_groups);
 
+/* Diagnostics: copies the raw per-channel demodulator state (AGC, timing loop, FIR memory; 256 bytes per channel,
+ * layout of csrc/device_state.h) into out.  Returns the record size, or a negative error. */
+SONDE_API int  sonde_b200_debug_demod_state(sonde_b200 *h, void *out, size_t cap_bytes);
+
 /* The CUDA stream (cudaStream_t) all work of this handle is enqueued on. */
 SONDE_API void *sonde_b200_stream(sonde_b200 *h);
 

@@ -25,7 +25,7 @@ EXPORTS = [
     "sonde_b200_process_iq_s16", "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
     "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_detected_types", "sonde_b200_auto_plausible", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
     "sonde_b200_soft_stride", "sonde_b200_fetch_soft", "sonde_b200_fetch_state", "sonde_b200_modem_info",
-    "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
+    "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_debug_demod_state", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
     "sonde_b200_last_kernel_ms", "sonde_b200_launch_count", "sonde_b200_last_error", "sonde_b200_version",
 ]
 
@@ -105,6 +105,7 @@ def load():
         "sonde_b200_host_free": (None, [vp]),
         "sonde_b200_stream": (vp, [vp]),
         "sonde_b200_debug_stalls": (ctypes.c_int, [vp, vp, ctypes.c_int]),
+        "sonde_b200_debug_demod_state": (ctypes.c_int, [vp, vp, sz]),
         "sonde_b200_sync": (ctypes.c_int, [vp]),
         "sonde_b200_join": (ctypes.c_int, [vp]),
         "sonde_b200_last_kernel_ms": (ctypes.c_int, [vp, f32p, f32p]),
@@ -286,6 +287,13 @@ class BatchDecoder:
         st = np.zeros((self.C, 8), dtype=np.float32)
         self._ck(self.lib.sonde_b200_fetch_state(self.h, _f32p(st)))
         return st
+
+    def debug_demod_state(self):
+        """Raw demodulator state per (virtual) channel as float32 words [C][64] (diagnostics)."""
+        out = np.zeros((self.C * 8, 64), dtype=np.float32)
+        rc = self.lib.sonde_b200_debug_demod_state(self.h, out.ctypes.data, out.nbytes)
+        self._ck(rc if rc < 0 else SONDE_OK)
+        return out
 
     def debug_stalls(self):
         """First call enables the pipeline kernel's stall counters; later calls return [groups][4 roles][4]."""

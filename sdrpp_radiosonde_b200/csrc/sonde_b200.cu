@@ -50,7 +50,7 @@ struct sonde_b200 {
 	std::vector<int32_t> h_vcounts;
 	bool has_auto = false;
 	sonde_modem modems[SONDE_NTYPES_];
-	int device = 0;
+	int device = 0, n_sms = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 
@@ -146,6 +146,18 @@ void build_groups(sonde_b200 *h, const std::vector<int32_t> *active, std::vector
 	const int C = h->cfg.n_channels;
 	gchan.clear();
 	gtype.clear();
+	/* Channels per CTA.  The serial warps of a CTA cost the same for one channel as for eight and the parallel work
+	 * scales with the channel count, so the batch is spread over all SMs: the fewest waves of one CTA per SM that
+	 * hold it at <= DEMOD_G channels each, then the smallest group size that still fits in those waves
+	 * (1024 channels on 148 SMs: 147 CTAs of 7 instead of 128 of 8). */
+	int gsz = DEMOD_G;
+	{
+		int n_act = 0;
+		for (int c = 0; c < C; c++) n_act += (!active || (*active)[c]) ? 1 : 0;
+		const int sms = h->n_sms > 0 ? h->n_sms : 148;
+		const int waves = std::max(1, (n_act + sms * DEMOD_G - 1) / (sms * DEMOD_G));
+		gsz = std::min(DEMOD_G, std::max(1, (n_act + sms * waves - 1) / (sms * waves)));
+	}
 	auto add_groups = [&](auto pred) {
 		int added = 0;
 		for (int t = 0; t < SONDE_NTYPES; t++) {
@@ -153,8 +165,8 @@ void build_groups(sonde_b200 *h, const std::vector<int32_t> *active, std::vector
 			std::vector<int32_t> ch;
 			for (int c = 0; c < C; c++)
 				if (h->types[c] == t && (!active || (*active)[c])) ch.push_back(c);
-			for (size_t i = 0; i < ch.size(); i += DEMOD_G) {
-				for (int k = 0; k < DEMOD_G; k++) gchan.push_back(i + k < ch.size() ? ch[i + k] : -1);
+			for (size_t i = 0; i < ch.size(); i += gsz) {
+				for (int k = 0; k < DEMOD_G; k++) gchan.push_back(k < gsz && i + k < ch.size() ? ch[i + k] : -1);
 				gtype.push_back(t);
 				added++;
 			}
@@ -234,6 +246,7 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	h->cfg.n_channels = (int32_t)h->types.size();        /* device-side channel count from here on */
 	h->cfg.types = h->types.data();
 	h->device = cfg->device;
+	h->n_sms = prop.multiProcessorCount;
 	if (h->cfg.fm_gain == 0.0f) h->cfg.fm_gain = 0.636619747f;
 
 	auto bail = [&](int code) { sonde_b200_destroy(h); return code; };
@@ -280,7 +293,9 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	const int C = h->cfg.n_channels;
 	std::vector<int32_t> gchan, gtype;
 	build_groups(h, nullptr, gchan, gtype);
-	h->group_capacity = (int)gtype.size();
+	/* the group size shrinks when fewer channels are active (AUTO locks), so a regrouped batch can have MORE groups
+	 * than the all-active one; one group per channel is the bound */
+	h->group_capacity = std::max((int)gtype.size(), C);
 
 	/* ---- sizes ----------------------------------------------------------------------------- */
 	int bits_max = 0, frames_max = 0;
@@ -291,7 +306,9 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 		const int nb = max_new_bits(m, cfg->max_chunk_len);
 		bits_max = std::max(bits_max, nb);
 		frames_max = std::max(frames_max, nb / m.frame_bits + 2);
-		ring_need = std::max(ring_need, (uint32_t)((2 * m.frame_bits + m.sync_len + nb) / 8 + 64));
+		/* two calls are in flight on the ring: frame(i) on fstream still reads while demod(i+1) appends (only
+		 * demod(i+2) waits for frame(i), run_chunk), so the span is the framer's 2F + S backlog plus TWO calls' bits */
+		ring_need = std::max(ring_need, (uint32_t)((2 * m.frame_bits + m.sync_len + 2 * nb) / 8 + 64));
 	}
 	h->ring_bytes = next_pow2(ring_need);
 	h->max_frames = frames_max;
@@ -299,8 +316,8 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	h->bits_stride = (bits_max + 7) / 8 + 1;
 
 #define CKB(call) do { if ((call) != cudaSuccess) { h->err = #call; return bail(SONDE_ERR_CUDA); } } while (0)
-	CKB(cudaMalloc(&h->d_group_chan, gchan.size() * sizeof(int32_t)));
-	CKB(cudaMalloc(&h->d_group_type, gtype.size() * sizeof(int32_t)));
+	CKB(cudaMalloc(&h->d_group_chan, (size_t)h->group_capacity * DEMOD_G * sizeof(int32_t)));
+	CKB(cudaMalloc(&h->d_group_type, (size_t)h->group_capacity * sizeof(int32_t)));
 	CKB(cudaMalloc(&h->d_types, C * sizeof(int32_t)));
 	CKB(cudaMemcpy(h->d_group_chan, gchan.data(), gchan.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
 	CKB(cudaMemcpy(h->d_group_type, gtype.data(), gtype.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -400,8 +417,8 @@ static void compute_active(const sonde_b200 *h, std::vector<int32_t> &active)
 	}
 }
 
-/* regroup the active virtual channels densely (same kernels, fewer CTAs) and publish the new tables; the tables
- * were sized for the all-active case at create, so rebuilt ones always fit */
+/* regroup the active virtual channels (same kernels, fewer CTAs) and publish the new tables; the tables were sized
+ * at create for one group per channel, so rebuilt ones always fit */
 static int apply_active(sonde_b200 *h)
 {
 	std::vector<int32_t> active, gchan, gtype;
@@ -507,6 +524,15 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	dp.soft_stride = h->soft_stride;
 	dp.prof = h->d_prof;
 	dp.in_row = h->d_in_row;
+	{
+		/* K1 warp placement: TM = warp 0 and LD = warp 4 on SMSP0, AG = warp 1 on SMSP1, parallel-work warps on
+		 * SMSP2/3 (ids 2,3,6,7,...) plus two beside the timing lane; SONDE_PW_MASK overrides it for experiments */
+		static const uint32_t mask = [] {
+			const char *e = getenv("SONDE_PW_MASK");
+			return e ? (uint32_t)strtoul(e, nullptr, 16) : 0xDDCCu;
+		}();
+		dp.pw_mask = mask;
+	}
 
 	const int par = (int)(h->n_issued & 1);
 	dp.nbits_out = h->d_nbits[par];
@@ -934,6 +960,18 @@ int sonde_b200_debug_stalls(sonde_b200 *h, long long *out, int cap_groups)
 	const int n = h->n_groups < cap_groups ? h->n_groups : cap_groups;
 	if (out) CK(cudaMemcpy(out, h->d_prof, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
 	return n;
+}
+
+/* Diagnostics: the raw per-channel demodulator state (device_state.h demod_state, 256 bytes per virtual channel). */
+int sonde_b200_debug_demod_state(sonde_b200 *h, void *out, size_t cap_bytes)
+{
+	if (!h || !out) return SONDE_ERR_ARG;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->stream));
+	const size_t need = (size_t)h->cfg.n_channels * sizeof(demod_state);
+	if (cap_bytes < need) return fail(h, SONDE_ERR_ARG, "buffer too small");
+	CK(cudaMemcpy(out, h->d_demod, need, cudaMemcpyDeviceToHost));
+	return (int)sizeof(demod_state);
 }
 
 void *sonde_b200_stream(sonde_b200 *h) { return h ? (void *)h->stream : nullptr; }

@@ -15,13 +15,13 @@ def rec_key(r, raw_bytes):
             bytes(r.data[:n]), bytes(r.raw[:raw_bytes]))
 
 
-def run_gpu(types, batch, chunk, kind="fm", keep_soft=False, want_bits=False, legacy_kernel=False, afsk_layout=0):
+def run_gpu(types, batch, chunk, kind="fm", keep_soft=False, want_bits=False, legacy_kernel=False, afsk_layout=0, no_tma=False):
     """Feed batch[C][n] through the GPU path in buffers of `chunk` samples.
 
     Returns dict(frames=[list of record rows per channel], bits=[...], soft=[...], state=...).
     """
     C, n = batch.shape
-    dec = capi.BatchDecoder(types, min(chunk, n), keep_soft=keep_soft, legacy_kernel=legacy_kernel, afsk_layout=afsk_layout)
+    dec = capi.BatchDecoder(types, min(chunk, n), keep_soft=keep_soft, legacy_kernel=legacy_kernel, afsk_layout=afsk_layout, no_tma=no_tma)
     frames = [[] for _ in range(C)]
     bits = [[] for _ in range(C)]
     soft = [[] for _ in range(C)]

@@ -241,6 +241,33 @@ def test_pipelined_fetch_equals_sequential():
         assert [rec_key(g, rb) for g in frames[c]] == [rec_key(g, rb) for g in seq["frames"][c]]
 
 
+def test_pipelined_fetch_full_second_buffers():
+    """Two calls in flight at L = 48000: frame(i) still reads the bit ring while demod(i+1) appends to it, so the ring
+    must hold the framer's backlog plus two calls' bits (M10: 9600 bit/s, RS41: a pending sync offset of up to 4144 bits).
+    ADVICE r1: with a one-call ring demod(i+1) wrapped onto bits frame(i) had not read yet."""
+    from sdrpp_radiosonde_b200 import capi
+    types = [synth.M10, synth.RS41, synth.M10, synth.RS41]
+    n, chunk = 48000 * 6, 48000
+    batch = np.stack([synth.make_iq(synth.default_spec(t, 40 + c), n) for c, t in enumerate(types)])
+    seq = run_gpu(types, batch, chunk, kind="iq")
+    assert all(sum(int(r["ok"]) for r in seq["frames"][c]) > 0 for c in range(len(types)))
+    for rep in range(3):
+        dec = capi.BatchDecoder(types, chunk)
+        frames = [[] for _ in types]
+        chunks = [np.ascontiguousarray(batch[:, p:p + chunk]) for p in range(0, n, chunk)]
+        dec.process_iq(chunks[0])
+        for i in range(len(chunks)):
+            if i + 1 < len(chunks):
+                dec.process_iq(chunks[i + 1])
+            recs, counts = dec.fetch()
+            for c in range(len(types)):
+                frames[c].extend(recs[c, :counts[c]].copy())
+        dec.close()
+        for c, t in enumerate(types):
+            rb = (synth.MODEMS[t].frame_bits + 7) // 8
+            assert [rec_key(g, rb) for g in frames[c]] == [rec_key(g, rb) for g in seq["frames"][c]], (rep, c, t)
+
+
 def test_ragged_and_tiny_buffers():
     """Buffers of 1, 2, 7, 48, 49, 255, 256, 257 ... samples in an irregular sequence (an SDR++ stream does not
     deliver fixed sizes): every call is one reference buffer, `interm` restarts at each (gfsk.c:73)."""

@@ -4,7 +4,7 @@ sys.path.insert(0, '.'); sys.path.insert(0, '..')
 from sdrpp_radiosonde_b200 import capi, synth
 import bench
 stype = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-C, L = 256, 48000
+C, L = (int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 1024), 48000
 iq = bench.gen_batch(stype, 0, C, L, 16)
 d = torch.from_numpy(iq).cuda()
 dec = capi.BatchDecoder(np.full(C, stype, np.int32), L, no_tma=('notma' in sys.argv[2:]), afsk_layout=(1 if 'layout1' in sys.argv[2:] else 0))
@@ -13,7 +13,7 @@ dec.debug_stalls()
 dec.process_iq_device(d.data_ptr(), L); dec.sync()
 st = dec.debug_stalls().astype(np.float64)
 print("demod ms", dec.last_kernel_ms())
-names = ["PW", "A1", "BX" if stype >= 5 else "A2", "TM"]
+names = (["PW", "A1", "BX", "TM"] if stype >= 5 else ["PW first", "AG", "PW last", "TM"])
 m = st.mean(axis=0)
 for r in range(4):
     tot = m[r, 2]

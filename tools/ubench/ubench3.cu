@@ -1,0 +1,202 @@
+// the serial loops of K1 in isolation (one warp on an otherwise idle SM): cycles per sample
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../sdrpp_radiosonde_b200/csrc/strict_math.cuh"
+#include "../../sdrpp_radiosonde_b200/csrc/timing_exact.cuh"
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("err %s line %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+constexpr uint32_t ZSENT = 0x7fc5a5a5u;
+constexpr int RS = 268, G = 8, T = 256;
+
+struct agc_block {
+	float4 s0, s1, v0, v1;
+};
+
+__device__ __forceinline__ void agc_block8(const float4 xa, const float4 xb, float &bias, float &avg, agc_block &o)
+{
+	const float b1 = fsub(1.0f, 0.01f), b0 = 0.01f, g1 = fsub(1.0f, 0.001f), g0 = 0.001f;
+	o.s0.x = fsub(xa.x, bias); bias = fadd(fmul(bias, b1), fmul(o.s0.x, b0));
+	o.s0.y = fsub(xa.y, bias); bias = fadd(fmul(bias, b1), fmul(o.s0.y, b0));
+	o.s0.z = fsub(xa.z, bias); bias = fadd(fmul(bias, b1), fmul(o.s0.z, b0));
+	o.s0.w = fsub(xa.w, bias); bias = fadd(fmul(bias, b1), fmul(o.s0.w, b0));
+	o.s1.x = fsub(xb.x, bias); bias = fadd(fmul(bias, b1), fmul(o.s1.x, b0));
+	o.s1.y = fsub(xb.y, bias); bias = fadd(fmul(bias, b1), fmul(o.s1.y, b0));
+	o.s1.z = fsub(xb.z, bias); bias = fadd(fmul(bias, b1), fmul(o.s1.z, b0));
+	o.s1.w = fsub(xb.w, bias); bias = fadd(fmul(bias, b1), fmul(o.s1.w, b0));
+	o.v0.x = avg; avg = fadd(fmul(avg, g1), fmul(fabsf(o.s0.x), g0));
+	o.v0.y = avg; avg = fadd(fmul(avg, g1), fmul(fabsf(o.s0.y), g0));
+	o.v0.z = avg; avg = fadd(fmul(avg, g1), fmul(fabsf(o.s0.z), g0));
+	o.v0.w = avg; avg = fadd(fmul(avg, g1), fmul(fabsf(o.s0.w), g0));
+	o.v1.x = avg; avg = fadd(fmul(avg, g1), fmul(fabsf(o.s1.x), g0));
+	o.v1.y = avg; avg = fadd(fmul(avg, g1), fmul(fabsf(o.s1.y), g0));
+	o.v1.z = avg; avg = fadd(fmul(avg, g1), fmul(fabsf(o.s1.z), g0));
+	o.v1.w = avg; avg = fadd(fmul(avg, g1), fmul(fabsf(o.s1.w), g0));
+}
+
+__device__ __forceinline__ void agc_store8(float *__restrict__ s, float *__restrict__ v, const int i, const agc_block &o)
+{
+	*reinterpret_cast<float4 *>(s + i) = o.s0;
+	*reinterpret_cast<float4 *>(s + i + 4) = o.s1;
+	*reinterpret_cast<float4 *>(v + i) = o.v0;
+	*reinterpret_cast<float4 *>(v + i + 4) = o.v1;
+}
+
+/* `check_zero`: the tile contains exact-zero samples, which bypass the AGC and do not update its state (agc.c:23);
+ * their s is the sentinel ZSENT so that S3 can pass them as 0.  x rows have 8 floats of slack for the prefetch. */
+__device__ __forceinline__ void agc_tile(const float *__restrict__ x, float *__restrict__ s, float *__restrict__ v, const int n,
+                                         float &bias, float &avg, const bool check_zero)
+{
+	const float b1 = fsub(1.0f, 0.01f), b0 = 0.01f, g1 = fsub(1.0f, 0.001f), g0 = 0.001f;
+	int i = 0;
+	if (!check_zero) {
+		const int nb = n >> 3;                   /* whole blocks of 8 */
+		if (nb > 0) {
+			agc_block A, B, C;
+			const float4 *xp = reinterpret_cast<const float4 *>(x);
+			float4 xa = xp[0], xb = xp[1];
+			int b = 0;
+			/* prime: block 0 -> A */
+			{
+				const float4 na = xp[2], nbv = xp[3];
+				agc_block8(xa, xb, bias, avg, A);
+				xa = na; xb = nbv;
+			}
+			/* steady state, three blocks per trip: compute the next block, then store the one before it */
+			for (b = 1; b + 2 < nb; b += 3) {
+				{
+					const float4 na = xp[2 * b + 2], nbv = xp[2 * b + 3];
+					agc_block8(xa, xb, bias, avg, B);
+					agc_store8(s, v, 8 * (b - 1), A);
+					xa = na; xb = nbv;
+				}
+				{
+					const float4 na = xp[2 * b + 4], nbv = xp[2 * b + 5];
+					agc_block8(xa, xb, bias, avg, C);
+					agc_store8(s, v, 8 * b, B);
+					xa = na; xb = nbv;
+				}
+				{
+					const float4 na = xp[2 * b + 6], nbv = xp[2 * b + 7];
+					agc_block8(xa, xb, bias, avg, A);
+					agc_store8(s, v, 8 * (b + 1), C);
+					xa = na; xb = nbv;
+				}
+			}
+			/* block b-1 is in A and not stored yet; up to two more whole blocks */
+			if (b < nb) {
+				const float4 na = xp[2 * b + 2], nbv = xp[2 * b + 3];
+				agc_block8(xa, xb, bias, avg, B);
+				agc_store8(s, v, 8 * (b - 1), A);
+				xa = na; xb = nbv;
+				if (b + 1 < nb) {
+					agc_block8(xa, xb, bias, avg, C);
+					agc_store8(s, v, 8 * b, B);
+					agc_store8(s, v, 8 * (b + 1), C);
+				} else {
+					agc_store8(s, v, 8 * b, B);
+				}
+			} else {
+				agc_store8(s, v, 8 * (b - 1), A);
+			}
+			i = nb << 3;
+		}
+		for (; i < n; i++) {
+			const float o = fsub(x[i], bias);
+			bias = fadd(fmul(bias, b1), fmul(o, b0));
+			s[i] = o;
+			v[i] = avg;
+			avg = fadd(fmul(avg, g1), fmul(fabsf(o), g0));
+		}
+	} else {
+		for (; i < n; i++) {
+			const float xi = x[i];
+			v[i] = avg;
+			if (xi == 0.0f) { s[i] = __uint_as_float(ZSENT); continue; }
+			const float o = fsub(xi, bias);
+			bias = fadd(fmul(bias, b1), fmul(o, b0));
+			s[i] = o;
+			avg = fadd(fmul(avg, g1), fmul(fabsf(o), g0));
+		}
+	}
+}
+
+// MODE 0: as in the kernel (LDS.128 in, 2 x STS.128 out); 1: no stores; 2: only the bias chain, no stores
+template <int MODE>
+__global__ void ag(long long *out, int tiles, int nlanes)
+{
+	__shared__ float x[G][RS], s[G][RS], v[G][RS];
+	for (int i = threadIdx.x; i < G * RS; i += blockDim.x) (&x[0][0])[i] = 0.3f * __sinf(0.37f * i);
+	__syncthreads();
+	if (threadIdx.x >= 32) return;
+	const int g = threadIdx.x & 7;
+	float bias = 0.f, avg = 5.f;
+	long long t0 = clock64();
+	for (int k = 0; k < tiles; k++) {
+		if ((int)threadIdx.x < nlanes) {
+			if (MODE == 0) agc_tile(x[g], s[g], v[g], T, bias, avg, false);
+			else {
+				const float b1 = fsub(1.0f, 0.01f), b0 = 0.01f, g1 = fsub(1.0f, 0.001f), g0 = 0.001f;
+				for (int i = 0; i < T; i++) {
+					const float o = fsub(x[g][i], bias);
+					bias = fadd(fmul(bias, b1), fmul(o, b0));
+					if (MODE == 1) avg = fadd(fmul(avg, g1), fmul(fabsf(o), g0));
+				}
+			}
+		}
+		__syncwarp();
+	}
+	long long t1 = clock64();
+	if (bias == 12345.f || avg == 1.f || s[0][3] == 9.f || v[1][2] == 7.f) out[1] = 1;
+	if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+
+__global__ void tm(long long *out, int tiles, int nlanes, uint8_t *ringbuf)
+{
+	__shared__ float y[G][3 * T + 36];
+	for (int i = threadIdx.x; i < G * (3 * T + 36); i += blockDim.x) (&y[0][0])[i] = 5.0f * __sinf(0.31415926f * (i % 804) + 0.1f * (i / 804));
+	__syncthreads();
+	if (threadIdx.x >= 32) return;
+	const int g = threadIdx.x & 7;
+	tmx_regs tr = {};
+	tr.freq = 0.2f; tr.target = 1.0f; tr.phase = 0.01f * g;
+	const tmx_consts tc = {0.2f, 2.824e-3f, 3.99435e-6f, 0.1f / 256.0f};
+	uint8_t *ring = ringbuf + 4096 * g;
+	long long n_slow = 0, rounds = 0;
+	long long t0 = clock64();
+	for (int k = 0; k < tiles; k++) {
+		int sabs = 0, sring = 0;
+		if ((int)threadIdx.x < nlanes) {
+			while (sabs + 11 <= 3 * T) {
+				const int used = tmx_round<4, 3, 9, 3, false>(tr, y[g] + sring, tc, ring, 4095u, nullptr, 0, n_slow);
+				sabs += used; sring += used;
+				sring = (sring >= 3 * T) ? sring - 3 * T : sring;
+				rounds++;
+			}
+		}
+		__syncwarp();
+	}
+	long long t1 = clock64();
+	if (tr.phase == 12345.f) out[1] = 1;
+	if (threadIdx.x == 0) { out[0] = t1 - t0; out[2] = rounds; out[3] = n_slow; }
+}
+
+int main()
+{
+	long long *d; CK(cudaMalloc(&d, 64)); CK(cudaMemset(d, 0, 64));
+	uint8_t *ring; CK(cudaMalloc(&ring, 65536));
+	long long h[4];
+	const int tiles = 64;
+	for (int nl : {8, 32}) {
+		ag<0><<<1, 64>>>(d, tiles, nl); CK(cudaDeviceSynchronize()); CK(cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost));
+		printf("AG fused loop as in K1 (LDS.128, 2 STS.128), %2d lanes : %.2f cyc/sample\n", nl, (double)h[0] / (tiles * T));
+		ag<1><<<1, 64>>>(d, tiles, nl); CK(cudaDeviceSynchronize()); CK(cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost));
+		printf("AG both chains, scalar loads, no stores,          %2d lanes : %.2f cyc/sample\n", nl, (double)h[0] / (tiles * T));
+		ag<2><<<1, 64>>>(d, tiles, nl); CK(cudaDeviceSynchronize()); CK(cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost));
+		printf("AG bias chain only, scalar loads, no stores,      %2d lanes : %.2f cyc/sample\n", nl, (double)h[0] / (tiles * T));
+		tm<<<1, 64>>>(d, tiles, nl, ring); CK(cudaDeviceSynchronize()); CK(cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost));
+		printf("TM rounds (RS41 windows),                         %2d lanes : %.1f cyc/round (%lld rounds, %lld slow)\n", nl,
+		       (double)h[0] / ((double)h[2]), h[2], h[3]);
+	}
+	return 0;
+}
