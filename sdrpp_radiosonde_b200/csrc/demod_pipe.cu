@@ -231,11 +231,27 @@ __device__ __forceinline__ float q_load(const float2 *q, const int m)
 	return q_has_x(m) ? q[q_phys(m)].x : q[q_phys(m - 64)].y;
 }
 
+/* float offsets inside a q row of the (up to) two slots of sample lane + 32 i; QN - 1 is a spare pair nobody reads */
+struct q_offsets {
+	int x[8], y[8];
+};
+__device__ __forceinline__ q_offsets q_offsets_of(const int lane)
+{
+	q_offsets o;
+#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		const int m = SONDE_FIR_HIST + lane + 32 * i;
+		o.x[i] = q_has_x(m) ? 2 * q_phys(m) : 2 * (QN - 1);
+		o.y[i] = q_has_y(m) ? 2 * q_phys(m - 64) + 1 : 2 * (QN - 1) + 1;
+	}
+	return o;
+}
+
 /* ---- item B: gain apply + FIR of tile k, channel g -------------------------------------------------------------------- */
 template <int P>
 __device__ __forceinline__ void item_fir(smem_t<P> &sm, const demod_params &p, const int k, const int g, const int lane,
-                                         const int ntiles, const int type, const unsigned long long negzero2, long long &wacc,
-                                         const bool prof_on)
+                                         const int ntiles, const int type, const unsigned long long negzero2, const q_offsets &qoff,
+                                         long long &wacc, const bool prof_on)
 {
 	const int L = p.len;
 	const int n = min(T, L - k * T);
@@ -276,7 +292,10 @@ __device__ __forceinline__ void item_fir(smem_t<P> &sm, const demod_params &p, c
 			const int t = lane + 32 * i;
 			float o = 0.0f;
 			if (t < n && !(zs && __float_as_uint(sv[i]) == ZSENT)) o = fmul(sv[i], gn[i]);
-			q_store(q, SONDE_FIR_HIST + t, o);
+			/* q_store(q, 48 + t, o) with the two target slots precomputed per lane (qoff): a slot the sample does
+			 * not have is the row's spare pair, so both stores are unconditional */
+			reinterpret_cast<float *>(q)[qoff.x[i]] = o;
+			reinterpret_cast<float *>(q)[qoff.y[i]] = o;
 		}
 	}
 	warp_sync_hard();
@@ -605,12 +624,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 			mbar_wait_t(&sm.yfull[k % NY], (k / NY) & 1, wacc[0], prof_on);
 			const int end = (k == ntiles - 1) ? ns_total : (k + 1) * TP;
 			if (own) {
-				while (sabs + W <= end) {
-					const int used = tmx_round<KM0, NM, KS0, NS, SOFT>(tr, yrow + sring, tc, ring, ring_mask, soft, p.soft_stride, n_slow);
-					sabs += used;
-					sring += used;
-					sring = (sring >= RING) ? sring - RING : sring;
-				}
+				tmx_run<KM0, NM, KS0, NS, RING, SOFT>(tr, yrow, sabs, sring, end, tc, ring, ring_mask, soft, p.soft_stride, n_slow);
 				if (k == ntiles - 1) {
 					while (sabs < ns_total) {
 						const int used = tmx_literal_round<SOFT>(tr, yrow + sring, min(W, ns_total - sabs), tc, ring, ring_mask, soft, p.soft_stride);
@@ -638,6 +652,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 		/* =============================== PW: work queue ===================================== */
 		const unsigned long long negzero2 = *reinterpret_cast<volatile unsigned long long *>(&sm.negzero2);
 		const int total = (2 + 2 * ntiles) * gact;
+		const q_offsets qoff = q_offsets_of(lane);
 		for (;;) {
 			const int idx = queue_pull(&sm.qnext, lane);
 			if (idx >= total) break;
@@ -646,7 +661,7 @@ demod_pipe_kernel(const demod_params p, const int group_base)
 				const int k = (b < 2) ? b : (b - 2) / 2 + 2;
 				if (k < ntiles) item_disc<P, IQ, TMA>(sm, p, k, g, lane, ntiles, wacc[0], prof_on);
 			} else {
-				item_fir<P>(sm, p, (b - 3) / 2, g, lane, ntiles, type, negzero2, wacc[1], prof_on);
+				item_fir<P>(sm, p, (b - 3) / 2, g, lane, ntiles, type, negzero2, qoff, wacc[1], prof_on);
 			}
 			if (prof_on) n_rounds++;
 		}

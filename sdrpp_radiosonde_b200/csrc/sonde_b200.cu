@@ -524,16 +524,14 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	dp.soft_stride = h->soft_stride;
 	dp.prof = h->d_prof;
 	dp.in_row = h->d_in_row;
-	{
-		/* K1 warp placement: TM = warp 0 and LD = warp 4 on SMSP0, AG = warp 1 on SMSP1, parallel-work warps on
-		 * SMSP2/3 (ids 2,3,6,7,...) plus two beside the timing lane; SONDE_PW_MASK overrides it for experiments */
-		static const uint32_t mask = [] {
-			const char *e = getenv("SONDE_PW_MASK");
-			return e ? (uint32_t)strtoul(e, nullptr, 16) : 0xDDCCu;
-		}();
-		dp.pw_mask = mask;
-	}
-
+	/* K1 warp placement: TM = warp 0 and LD = warp 4 on SMSP0, AG = warp 1 on SMSP1, twelve parallel-work warps on
+	 * SMSP2/3 (ids 2,3,6,7,...) plus, per kernel variant, the measured best number of extra ones beside the serial
+	 * warps (profiles/README.md); SONDE_PW_MASK overrides it for experiments */
+	static const uint32_t mask_env = [] {
+		const char *e = getenv("SONDE_PW_MASK");
+		return e ? (uint32_t)strtoul(e, nullptr, 16) : 0u;
+	}();
+	static const uint32_t kPwMask[3] = {0xCCCFCCu /* RS41 */, 0xCCDDCCu /* DFM, iMS-100, MRZ-N1 */, 0xCCCCCCu /* M10/M20 */};
 	const int par = (int)(h->n_issued & 1);
 	dp.nbits_out = h->d_nbits[par];
 	/* the demodulator of call i+2 appends to ring positions the framer of call i may still be reading */
@@ -554,7 +552,10 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 			if (v == 3 && (h->cfg.reserved & 1)) CK(sonde_launch_demod_afsk(&dp, base, h->groups_v[v], st));
 			else if (v == 3)               CK(sonde_launch_demod_pipe_afsk(&dp, base, h->groups_v[v], (h->cfg.reserved >> 2) & 1, st));
 			else if (h->cfg.reserved & 1)  CK(sonde_launch_demod_gfsk(&dp, base, h->groups_v[v], v == 2 ? 2 : 1, st));
-			else                           CK(sonde_launch_demod_pipe(&dp, base, h->groups_v[v], v, st));
+			else {
+				dp.pw_mask = mask_env ? mask_env : kPwMask[v];
+				CK(sonde_launch_demod_pipe(&dp, base, h->groups_v[v], v, st));
+			}
 			h->launches++;
 			if (fork) {
 				CK(cudaEventRecord(h->ev_join[v], st));

@@ -48,6 +48,13 @@ __device__ __forceinline__ float max_nan(float a, float b)
 	return r;
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+	return v;
+}
+
 /* retime() + update_estimate() at a symbol hit whose phase is `ph` (timing.c:45-76) */
 __device__ __forceinline__ void tmx_retime(tmx_regs &t, const float ph, const float yv, const tmx_consts &c)
 {
@@ -103,47 +110,97 @@ __device__ __forceinline__ int tmx_literal_round(tmx_regs &t, const float *y, co
 	return maxslots;
 }
 
-/* One round of one lane starting at FIR-output pointer y (slot 0 = the lane's current slot); at least
- * W = KS0 + NS - 1 slots must be readable.  Returns the slots consumed (>= 1). */
-template <int KM0, int NM, int KS0, int NS, bool SOFT>
-__device__ __forceinline__ int tmx_round(tmx_regs &t, const float *y, const tmx_consts &c, uint8_t *ring,
-                                         const uint32_t ring_mask, float *soft, const int soft_cap, long long &n_slow)
+/* All rounds of one lane that start at slot `sabs` (ring position `sring`) and whose candidate slots end before slot
+ * `end`: W = KS0 + NS - 1 slots must be readable from the start of each round (the ring has a mirror of its first
+ * slots behind its last one).
+ *
+ * Shape of the loop (ncu on a first version that handled the two rare events inside the round showed a quarter of
+ * every round in BSSY/BSYNC reconvergence, branch resolution and predicate latency): the inner loop is straight-line
+ * code with one backward branch; a lane that meets a rare event (the round does not fit the windows -> literal round;
+ * a 32-bit word of bits is complete -> store it) leaves the inner loop, handles it and re-enters. */
+template <int KM0, int NM, int KS0, int NS, int RING, bool SOFT>
+__device__ __forceinline__ void tmx_run(tmx_regs &t, const float *yrow, int &sabs, int &sring, const int end,
+                                        const tmx_consts &c, uint8_t *ring, const uint32_t ring_mask, float *soft,
+                                        const int soft_cap, long long &n_slow)
 {
 	constexpr int W = KS0 + NS - 1;
 	static_assert(KM0 >= 1 && KM0 + NM - 1 < KS0, "the mid-symbol window must end before the symbol window starts");
-	/* candidate FIR outputs: slot k (1-based, k adds after the round's start) reads y[k - 1] */
+	int left = end - W - sabs;                   /* rounds may start while left >= 0 */
+	/* 32-bit shared-memory address of the row, taken once: left to itself the compiler rebuilt the shared window base
+	 * (S2R SR_CgaCtaId ...) in every round */
+	const uint32_t ybase = (uint32_t)__cvta_generic_to_shared(yrow);
+	/* The candidate FIR outputs of a round are fetched at the END of the round before it (as soon as its first slot is
+	 * known) and carried in registers: the loads are in flight during the loop branch, and ptxas cannot turn them into
+	 * loads predicated on this round's comparisons, which would put the shared-memory latency behind the add chain. */
 	float ymc[NM], ysc[NS];
+	auto fetch = [&](const int at) {
+		const uint32_t ya = ybase + 4u * (uint32_t)at;
 #pragma unroll
-	for (int j = 0; j < NM; j++) ymc[j] = y[KM0 - 1 + j];
+		for (int j = 0; j < NM; j++) ymc[j] = lds_f32(ya + 4u * (KM0 - 1 + j));   /* slot k (1-based) reads y[k - 1] */
 #pragma unroll
-	for (int j = 0; j < NS; j++) ysc[j] = y[KS0 - 1 + j];
-	/* the reference's chain of adds */
-	float p[W + 1];
-	p[0] = t.phase;
+		for (int j = 0; j < NS; j++) ysc[j] = lds_f32(ya + 4u * (KS0 - 1 + j));
+	};
+	/* The inner loop is a do-while with ONE conditional backward branch whose predicate (this round fits, another
+	 * round may start, no word of bits completes) is known long before the branch: a branch that has to wait for a
+	 * predicate computed just before it costs the lane ~12 cycles. */
+	if (left >= 0) {
+		fetch(sring);
+		for (;;) {
+			int ev;                                  /* 0: out of slots, 1: literal round needed, 2: word of bits complete */
+			for (;;) {
+				const bool word = ((t.nb + 1u) & 31u) == 0u;
+				/* the reference's chain of adds */
+				float p[W + 1];
+				p[0] = t.phase;
 #pragma unroll
-	for (int i = 1; i <= W; i++) p[i] = fadd(p[i - 1], t.freq);
-	bool ok = t.target == 1.0f && p[KM0 - 1] < 1.0f && p[KM0 + NM - 1] >= 1.0f && p[KS0 - 1] < 2.0f && p[W] >= 2.0f;
-	/* earliest slot at or above the threshold wins (timing.c:35) */
-	float ym = ymc[NM - 1];
+				for (int i = 1; i <= W; i++) p[i] = fadd(p[i - 1], t.freq);
+				const bool ok = t.target == 1.0f && p[KM0 - 1] < 1.0f && p[KM0 + NM - 1] >= 1.0f && p[KS0 - 1] < 2.0f &&
+				                p[W] >= 2.0f;
+				/* earliest slot at or above the threshold wins (timing.c:35) */
+				float ym = ymc[NM - 1];
 #pragma unroll
-	for (int j = NM - 2; j >= 0; j--) ym = (p[KM0 + j] >= 1.0f) ? ymc[j] : ym;
-	float ys = ysc[NS - 1], pl = p[W];
-	int ks = W;
+				for (int j = NM - 2; j >= 0; j--) ym = (p[KM0 + j] >= 1.0f) ? ymc[j] : ym;
+				float ys = ysc[NS - 1], pl = p[W];
+				int ks = W;
 #pragma unroll
-	for (int j = NS - 2; j >= 0; j--) {
-		const bool hit = p[KS0 + j] >= 2.0f;
-		ys = hit ? ysc[j] : ys;
-		pl = hit ? p[KS0 + j] : pl;
-		ks = hit ? KS0 + j : ks;
+				for (int j = NS - 2; j >= 0; j--) {
+					const bool hit = p[KS0 + j] >= 2.0f;
+					ys = hit ? ysc[j] : ys;
+					pl = hit ? p[KS0 + j] : pl;
+					ks = hit ? KS0 + j : ks;
+				}
+				if (__builtin_expect(!ok, 0)) { ev = 1; break; }
+				left -= ks;
+				sring += ks;
+				sring = (int)min((unsigned)sring, (unsigned)(sring - RING));      /* wrap without a predicate */
+				const bool again = left >= 0 && !word;
+				fetch(sring);                            /* next round's candidates (harmless if there is no next round) */
+				t.interm = ym;
+				tmx_retime(t, pl, ys, c);
+				t.acc = (t.acc << 1) | (ys > 0.0f ? 1u : 0u);
+				if (SOFT) {
+					if (soft && t.nsoft < soft_cap) soft[t.nsoft] = ys;
+				}
+				t.nsoft++;
+				t.nb++;
+				if (__builtin_expect(again, 1)) continue;
+				ev = word ? 2 : 0;
+				break;
+			}
+			if (ev == 2) {
+				*reinterpret_cast<uint32_t *>(ring + (((t.nb - 32u) >> 3) & ring_mask)) = __byte_perm(t.acc, 0, 0x0123);
+			} else if (ev == 1) {
+				n_slow++;
+				const int used = tmx_literal_round<SOFT>(t, yrow + sring, W, c, ring, ring_mask, soft, soft_cap);
+				left -= used;
+				sring += used;
+				sring = (sring >= RING) ? sring - RING : sring;
+				fetch(sring);
+			}
+			if (left < 0) break;
+		}
 	}
-	if (__builtin_expect(!ok, 0)) {
-		n_slow++;
-		return tmx_literal_round<SOFT>(t, y, W, c, ring, ring_mask, soft, soft_cap);
-	}
-	t.interm = ym;
-	tmx_retime(t, pl, ys, c);
-	tmx_emit<SOFT>(t, ys, ring, ring_mask, soft, soft_cap);
-	return ks;
+	sabs = end - W - left;
 }
 
 #endif

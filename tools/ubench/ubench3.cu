@@ -167,12 +167,8 @@ __global__ void tm(long long *out, int tiles, int nlanes, uint8_t *ringbuf)
 	for (int k = 0; k < tiles; k++) {
 		int sabs = 0, sring = 0;
 		if ((int)threadIdx.x < nlanes) {
-			while (sabs + 11 <= 3 * T) {
-				const int used = tmx_round<4, 3, 9, 3, false>(tr, y[g] + sring, tc, ring, 4095u, nullptr, 0, n_slow);
-				sabs += used; sring += used;
-				sring = (sring >= 3 * T) ? sring - 3 * T : sring;
-				rounds++;
-			}
+			tmx_run<4, 3, 9, 3, 3 * T, false>(tr, y[g], sabs, sring, 3 * T, tc, ring, 4095u, nullptr, 0, n_slow);
+			rounds = tr.nsoft;
 		}
 		__syncwarp();
 	}
@@ -186,7 +182,7 @@ int main()
 	long long *d; CK(cudaMalloc(&d, 64)); CK(cudaMemset(d, 0, 64));
 	uint8_t *ring; CK(cudaMalloc(&ring, 65536));
 	long long h[4];
-	const int tiles = 64;
+	const int tiles = 4000;
 	for (int nl : {8, 32}) {
 		ag<0><<<1, 64>>>(d, tiles, nl); CK(cudaDeviceSynchronize()); CK(cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost));
 		printf("AG fused loop as in K1 (LDS.128, 2 STS.128), %2d lanes : %.2f cyc/sample\n", nl, (double)h[0] / (tiles * T));
