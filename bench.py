@@ -4,7 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
     python bench.py --impl reference ...                      (the reference's own CPU path, host cores)
 
-Workload (BASELINE.json configs[1], per GPU): 1024 RS41 channels, 48 kS/s synthetic GFSK complex64 IQ with
+    python bench.py --config {2,3,4,5} ...                    (the other BASELINE configs, same JSON contract)
+
+Workload (default --config 2 = BASELINE.json configs[1], per GPU): 1024 RS41 channels, 48 kS/s synthetic GFSK complex64 IQ with
 per-channel CFO / timing offset / clock error / AWGN, 10 s per channel, processed in
 chunks of L = 48000 samples (1 s).  One "step" = one process call = one chunk of every channel
 (49.15 M samples, 393 MB of IQ > L2, so every step streams from HBM; steps cycle through the 10 chunks).
@@ -32,6 +34,26 @@ sys.path.insert(0, ROOT)
 from sdrpp_radiosonde_b200 import synth  # noqa: E402
 
 FS = 48000
+
+# BASELINE.json configs[1..4] (1-based 2..5): sonde mix, channels per GPU, what the workload string says
+CONFIGS = {
+    2: dict(mix=[synth.RS41], channels=1024, seconds=10, auto=False,
+            name="RS41 4800-baud GFSK + RS(255,231)", ref="BASELINE configs[1]"),
+    3: dict(mix=[synth.DFM09, synth.M10], channels=2048, seconds=4, auto=False,
+            name="DFM06/09/17 Manchester-FSK + M10/M20 mixed (alternating channels)", ref="BASELINE configs[2]"),
+    4: dict(mix=[synth.IMS100], channels=1024, seconds=4, auto=False,
+            name="iMS-100/RS-11G Manchester-FSK + 12 x BCH(63,51)", ref="BASELINE configs[3], per-GPU share of 4096 over 4 GPUs"),
+    5: dict(mix=[synth.RS41, synth.DFM09, synth.M10, synth.IMS100, synth.MRZN1, synth.IMET4, synth.C50], channels=1024,
+            seconds=3, auto=True, name="all seven decoders (9 sonde types), every channel AUTO (preamble autodetect)",
+            ref="BASELINE configs[4], per-GPU share of 8192 over 8 GPUs"),
+}
+
+
+def config_types(cfg, n_ch, ch0=0):
+    mix = CONFIGS[cfg]["mix"]
+    return np.array([mix[(ch0 + c) % len(mix)] for c in range(n_ch)], dtype=np.int32)
+
+
 METRIC = "IQ Msamples/s (decoded frames/s in config) across N channels vs reference CPU"
 UNIT = "Msamples/s"
 
@@ -42,9 +64,10 @@ def _gen_channel(args):
 
 
 def gen_batch(stype, ch0, n_ch, n, procs):
-    """[n_ch][n] complex64, channel c seeded 0xB200 + ch0 + c."""
+    """[n_ch][n] complex64, channel c seeded 0xB200 + ch0 + c; stype: one type or one per channel."""
     import multiprocessing as mp
-    jobs = [(stype, ch0 + c, n) for c in range(n_ch)]
+    tl = [int(stype)] * n_ch if np.isscalar(stype) else [int(t) for t in stype]
+    jobs = [(tl[c], ch0 + c, n) for c in range(n_ch)]
     if procs <= 1 or n_ch < 4:
         rows = [_gen_channel(j) for j in jobs]
     else:
@@ -77,12 +100,14 @@ class CpuPath:
             self.ref.ref_decode_count.restype = ctypes.c_int
 
     def run(self, stype, iq, chunk, threads):
-        """iq [C][n] complex64 -> (seconds, framer windows, frames with fields != 0 / passing the gate)."""
+        """iq [C][n] complex64 -> (seconds, framer windows, frames with fields != 0 / passing the gate).
+        stype: one decoder type or one per channel."""
         C, n = iq.shape
         fp = ctypes.POINTER(ctypes.c_float)
         flat = np.ascontiguousarray(iq).view(np.float32).reshape(C, 2 * n)
+        tl = np.full(C, stype, dtype=np.int32) if np.isscalar(stype) else np.asarray(stype, dtype=np.int32)
         if self.ref is None:
-            types = np.full(C, stype, dtype=np.int32)
+            types = tl
             frames = np.zeros(C, dtype=np.int32)
             ok = np.zeros(C, dtype=np.int32)
             t0 = time.perf_counter()
@@ -104,7 +129,7 @@ class CpuPath:
                 self.orc.orc_discriminate(flat[c].ctypes.data_as(fp), n, ctypes.c_float(0.636619747),
                                           ctypes.byref(prev), fm.ctypes.data_as(fp))
                 nf = ctypes.c_int(0)
-                frames[c] = self.ref.ref_decode_count(stype, FS, fm.ctypes.data_as(fp), n, chunk, ctypes.byref(nf))
+                frames[c] = self.ref.ref_decode_count(int(tl[c]), FS, fm.ctypes.data_as(fp), n, chunk, ctypes.byref(nf))
                 ok[c] = nf.value
 
         ths = [threading.Thread(target=work, args=(C * i // threads, C * (i + 1) // threads)) for i in range(threads)]
@@ -116,8 +141,8 @@ class CpuPath:
         return time.perf_counter() - t0, sum(frames), sum(ok)
 
 
-def cpu_sample(n_ch, n, procs):
-    return gen_batch(synth.RS41, 0, n_ch, n, procs)
+def cpu_sample(cfg, n_ch, n, procs):
+    return gen_batch(config_types(cfg, n_ch), 0, n_ch, n, procs)
 
 
 # ------------------------------------------------------------------------------------------
@@ -170,9 +195,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--channels", type=int, default=1024, help="channels per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE config (1-based); 2 = the headline")
+    ap.add_argument("--channels", type=int, default=0, help="channels per GPU (default: the config's)")
     ap.add_argument("--chunk", type=int, default=48000)
-    ap.add_argument("--seconds", type=int, default=10, help="seconds of signal per channel")
+    ap.add_argument("--seconds", type=int, default=0, help="seconds of signal per channel (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-scatter", action="store_true", help="N > 1: skip the rank-0 -> all scatter measurement")
@@ -200,12 +226,15 @@ def main():
                 numa_note = f"rank pinned to {len(cpus)} GPU-local cores"
         except Exception as e:                               # affinity is an optimisation, never a requirement
             numa_note = f"no GPU-local affinity ({type(e).__name__})"
-    L, C = args.chunk, args.channels
-    n_chunks = max(1, args.seconds * FS // L)
+    cfg = CONFIGS[args.config]
+    L, C = args.chunk, args.channels or cfg["channels"]
+    n_chunks = max(1, (args.seconds or cfg["seconds"]) * FS // L)
     n_total = n_chunks * L
-    config = {"workload": f"RS41 4800-baud GFSK + RS(255,231), {C} channels/GPU, 48 kS/s complex64 IQ, "
-                          f"chunk L={L}, {n_chunks} distinct chunks/channel (BASELINE configs[1])",
-              "channels_per_gpu": C, "chunk_len": L, "cache": "each step reads a different 393 MB chunk (> 126 MB L2)"}
+    # `config` is the static description of the workload, identical in both arms; measured by-products go to `result`
+    config = {"workload": f"{cfg['name']}, {C} channels/GPU, 48 kS/s complex64 IQ, chunk L={L}, "
+                          f"{n_chunks} distinct chunks/channel ({cfg['ref']})",
+              "baseline_config": args.config, "channels_per_gpu": C, "chunk_len": L,
+              "cache": f"each step reads a different {C * L * 8 / 1e6:.0f} MB chunk (> 126 MB L2)"}
 
     # ---------------------------------------------------------------- reference arm (CPU only)
     if args.impl == "reference":
@@ -213,23 +242,30 @@ def main():
             return
         cpu = CpuPath()
         n_ch = 2 * ncores
-        sample = cpu_sample(n_ch, n_total, ncores)
+        n_ref = min(n_total, 4 * L) if args.config != 2 else n_total
+        ctypes_ = config_types(args.config, n_ch)
+        sample = cpu_sample(args.config, n_ch, n_ref, ncores)
         for _ in range(min(args.warmup, 1)):
-            cpu.run(synth.RS41, sample[:ncores, :L * 2], L, ncores)
+            cpu.run(ctypes_[:ncores], sample[:ncores, :L * 2], L, ncores)
         t = 0.0
         frames = ok = 0
         for _ in range(args.steps):
-            dt, f, k = cpu.run(synth.RS41, sample, L, ncores)
+            dt, f, k = cpu.run(ctypes_, sample, L, ncores)
             t += dt
             frames += f
             ok += k
-        samples = args.steps * n_ch * n_total
+        samples = args.steps * n_ch * n_ref
         val = samples / t / 1e6
-        desc = f"{n_ch} channels x {n_total} samples per step (first {n_ch} channels of the workload)"
+        desc = (f"a bounded sample of the workload: its first {n_ch} channels x {n_ref} samples per step on {ncores} host "
+                f"threads (the CPU path is one independent decoder per channel, so samples/s does not depend on the "
+                f"channel count); discriminator = this repo's restated polynomial atan2 (SDR++ is not vendored), "
+                f"everything after it the unmodified reference")
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, frames_per_s=frames / t, ok_frames_per_s=ok / t),
+                "config": config,
+                "result": {"frames_per_s": frames / t, "ok_frames_per_s": ok / t, "channels_run": n_ch,
+                           "samples_per_channel": n_ref},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": cpu.kind, "sample": desc},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -238,7 +274,8 @@ def main():
     # ---------------------------------------------------------------- B200 arm
     procs = max(1, ncores // max(1, world))
     t_gen = time.time()
-    host_iq = gen_batch(synth.RS41, rank * C, C, n_total, procs)          # before CUDA init (fork pool)
+    sig_types = config_types(args.config, C, rank * C)
+    host_iq = gen_batch(sig_types, rank * C, C, n_total, procs)           # before CUDA init (fork pool)
     t_gen = time.time() - t_gen
 
     import torch
@@ -264,9 +301,20 @@ def main():
         dev_iq[k].copy_(torch.from_numpy(np.ascontiguousarray(host_iq[:, k * L:(k + 1) * L])))
     torch.cuda.synchronize()
 
-    types = np.full(C, synth.RS41, dtype=np.int32)
+    # config 5: every channel is created as AUTO (SD/decode.c:174-224) and locks at the first fetch after a frame
+    types = np.full(C, -1, dtype=np.int32) if cfg["auto"] else sig_types
     dec = capi.BatchDecoder(types, L, device=local_rank)
     ext = torch.cuda.ExternalStream(dec.stream)
+    auto_info = None
+    if cfg["auto"]:
+        # acquisition: buffers with all seven decoders on every channel until the channels have locked
+        acq = []
+        for i in range(min(n_chunks, 3)):
+            dec.process_iq_device(dev_iq[i % n_chunks].data_ptr(), L)
+            dec.fetch_counts()
+            acq.append((float(dec.last_kernel_ms()[0]), int((dec.detected_types() >= 0).sum())))
+        auto_info = {"acquisition_buffers": [{"demod_kernel_ms": a, "channels_locked_after": b} for a, b in acq],
+                     "channels": C, "note": "the timed steps below are the locked steady state"}
 
     def barrier():
         torch.cuda.synchronize()
@@ -321,7 +369,7 @@ def main():
         pins = [capi.PinnedBuffer((C, L), np.complex64) for _ in range(nbuf)]
         for k, pb in enumerate(pins):
             pb.array[...] = host_iq[:, k * L:(k + 1) * L]
-        dec2 = capi.BatchDecoder(types, L, device=local_rank)
+        dec2 = capi.BatchDecoder(sig_types, L, device=local_rank)
         for i in range(2):
             dec2.process_host_ptr(pins[i % nbuf].ptr, L, is_iq=True)
             dec2.fetch()
@@ -365,7 +413,7 @@ def main():
                 blk = host_iq[:, k * L:(k + 1) * L]
                 pb.array[..., 0] = np.clip(np.round(blk.real * 16384.0), -32768, 32767)
                 pb.array[..., 1] = np.clip(np.round(blk.imag * 16384.0), -32768, 32767)
-            dec4 = capi.BatchDecoder(types, L, device=local_rank)
+            dec4 = capi.BatchDecoder(sig_types, L, device=local_rank)
             for i in range(2):
                 dec4.process_s16_host_ptr(pins16[i % nbuf].ptr, L)
                 dec4.fetch()
@@ -402,7 +450,7 @@ def main():
             for pb in pinw:
                 pb.array[...] = (0.05 * (rngw.standard_normal(n_in) + 1j * rngw.standard_normal(n_in))).astype(np.complex64)
             chz = capi.Channelizer(freqs, Dw, n_in, device=local_rank)
-            dec5 = capi.BatchDecoder(types, L, device=local_rank)
+            dec5 = capi.BatchDecoder(sig_types, L, device=local_rank)
             # the copy and the channelizer of step i+1 run on a side stream beside the decode of step i
             side, ext5 = torch.cuda.Stream(), torch.cuda.ExternalStream(dec5.stream)
             done = [None, None]
@@ -446,7 +494,7 @@ def main():
             n_sc = 6
             full = [dev_iq[k].repeat(world, 1) for k in range(2)] if rank == 0 else [None, None]
             bufs = [torch.empty((C, L), dtype=torch.complex64, device="cuda") for _ in range(2)]
-            dec3 = capi.BatchDecoder(types, L, device=local_rank)
+            dec3 = capi.BatchDecoder(sig_types, L, device=local_rank)
             shard.scatter_channels(full[0], bufs[0], world, rank)
             barrier()
             t0 = time.perf_counter()
@@ -511,13 +559,16 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config, frames_per_s=frames / (ms_max * 1e-3), ok_frames_per_s=ok / (ms_max * 1e-3),
+            "config": config,
+            "result": dict(frames_per_s=frames / (ms_max * 1e-3), ok_frames_per_s=ok / (ms_max * 1e-3),
                            realtime_channels_equiv=value * 1e6 / FS, gen_seconds=round(t_gen, 1),
+                           **({"auto": auto_info} if auto_info else {}),
                            **({"host_affinity": numa_note} if numa_note else {})),
             "gpu_launches": launches,
             "clocks": summarize_clocks(samples),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "demod_pipe_kernel<1,12,true>", "kernel_ms": dem,
+                         "traffic": traffic, "kernel": "demod_pipe_kernel (+ demod_pipe_afsk_kernel for AFSK channels): all demod "
+                         "kernels of one step, forked on streams", "kernel_ms": dem,
                          "frame_kernel_ms": float(np.mean(frm_ms)),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "note": "8 B per complex sample; the chain is serial per channel (AGC IIR + Gardner NCO), "
@@ -556,16 +607,17 @@ def main():
                                "rank0_egress_gbs": (world - 1) * C * L * 8 / (so_ms * 1e-3) / 1e9}
         if not args.no_cpu_baseline and world == 1:
             cpu = CpuPath()
-            n_ch = 2 * ncores
-            t, f, k = cpu.run(synth.RS41, host_iq[:n_ch], L, ncores)
+            n_ch = min(C, 2 * ncores)
+            t, f, k = cpu.run(sig_types[:n_ch], host_iq[:n_ch], L, ncores)
             reps = 1
             while t < 8.0 and reps < 64:                      # ~10 s of CPU work
-                dt, _, _ = cpu.run(synth.RS41, host_iq[:n_ch], L, ncores)
+                dt, _, _ = cpu.run(sig_types[:n_ch], host_iq[:n_ch], L, ncores)
                 t += dt
                 reps += 1
             line["cpu_baseline"] = {"value": reps * n_ch * n_total / t / 1e6, "unit": UNIT, "cores": ncores,
                                     "kind": cpu.kind,
-                                    "sample": f"first {n_ch} channels x {n_total} samples, {reps} passes",
+                                    "sample": f"first {n_ch} channels of the workload x {n_total} samples, {reps} passes; "
+                                              "discriminator = this repo's restated polynomial atan2 (SDR++ is not vendored)",
                                     "ok_frames_per_s": k * reps / t}
         emit(line)
 

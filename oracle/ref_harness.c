@@ -423,6 +423,82 @@ ref_gfsk_soft(int samplerate, int baud, const float *fm, size_t n, size_t chunk,
 	return (long)count;
 }
 
+/*
+ * Soft symbols of the reference's AFSK chain (SD/demod/afsk.c:104-151): its own AFSKDemod state and its own
+ * agc_apply / filter_fwd_sample / filter_get / advance_timeslot / retime, with the per-sample mixer + boxcar statements
+ * between them written out exactly as afsk.c has them (same expression types, this container's libm cexpf / cabsf /
+ * fmod), because afsk_demod() does not export the symbol values.  The mirror is validated in tests/test_oracle.py: its
+ * hard decisions equal afsk_demod()'s bits.  One entry = one afsk_demod() call sequence over a buffer of `chunk`
+ * samples (interm = 0 at every buffer start, afsk.c:94).
+ * type: SONDE_IMET4 or SONDE_C50 (mark / space / baud of the protocol headers).
+ */
+EXPORT long
+ref_afsk_soft(int type, int samplerate, const float *fm, size_t n, size_t chunk, float *soft, size_t soft_cap,
+              float *state_out)
+{
+	AFSKDemod d;
+	size_t pos, i, len, count = 0;
+	int phase, rc;
+	float symbol, interm, sym;
+	float p_mark, p_space;
+	float complex out, mark_sum, space_sum;
+
+	if (type == 5) rc = afsk_init(&d, samplerate, IMET4_BAUDRATE, IMET4_MARK_FREQ, IMET4_SPACE_FREQ);
+	else if (type == 6) rc = afsk_init(&d, samplerate, C50_BAUDRATE, C50_MARK_FREQ, C50_SPACE_FREQ);
+	else return -1;
+	if (rc) return -1;
+	p_mark = d.p_mark; p_space = d.p_space;
+	mark_sum = d.mark_sum; space_sum = d.space_sum;
+	for (pos = 0; pos < n; pos += chunk) {
+		len = (n - pos < chunk) ? n - pos : chunk;
+		interm = 0;
+		for (i = 0; i < len; i++) {
+			symbol = fm[pos + i];
+			symbol = agc_apply(&d.agc, symbol) / d.len * 2;
+
+			out = symbol * cexpf(-I * p_mark);
+			mark_sum += out - d.mark_history[d.idx];
+			d.mark_history[d.idx] = out;
+
+			out = symbol * cexpf(-I * p_space);
+			space_sum += out - d.space_history[d.idx];
+			d.space_history[d.idx] = out;
+
+			symbol = cabsf(mark_sum) - cabsf(space_sum);
+			d.idx = (d.idx + 1) % d.len;
+			p_mark = fmod(p_mark + d.f_mark, 2*M_PI);
+			p_space = fmod(p_space + d.f_space, 2*M_PI);
+			filter_fwd_sample(&d.lpf, symbol);
+
+			for (phase = 0; phase < d.lpf.num_phases; phase++) {
+				switch (advance_timeslot(&d.timing)) {
+				case 1:
+					interm = filter_get(&d.lpf, phase);
+					break;
+				case 2:
+					sym = filter_get(&d.lpf, phase);
+					retime(&d.timing, interm, sym);
+					if (count < soft_cap) soft[count] = sym;
+					count++;
+					break;
+				default:
+					break;
+				}
+			}
+		}
+	}
+	if (state_out) {
+		state_out[0] = d.agc.bias;
+		state_out[1] = d.agc.moving_avg;
+		state_out[2] = d.timing.phase;
+		state_out[3] = d.timing.freq;
+		state_out[4] = d.timing.prev;
+		state_out[5] = (float)d.timing.state;
+	}
+	afsk_deinit(&d);
+	return (long)count;
+}
+
 /* FIR taps exactly as the reference computes them (SD/demod/dsp/filter.c:10-32). */
 EXPORT int
 ref_gfsk_taps(int samplerate, int baud, float *taps, int cap)

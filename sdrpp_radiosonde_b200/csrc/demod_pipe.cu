@@ -322,17 +322,19 @@ __device__ __forceinline__ void item_fir(smem_t<P> &sm, const demod_params &p, c
 	if (k >= NY) flag_wait(&sm.tm_rel, k - NY + 1, wacc, prof_on);
 	{
 		const int j0 = 128 * ((lane >> 2) & 1) + 16 * (lane >> 3) + 4 * (lane & 3);
-		unsigned long long w[SONDE_FIR_HIST + 4];
 		const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(q + q_phys(j0));
-#pragma unroll
-		for (int i = 0; i < (SONDE_FIR_HIST + 4) / 2; i++) {
-			const ulonglong2 t = src[i];
-			w[2 * i] = t.x;
-			w[2 * i + 1] = t.y;
-		}
 		float *yrow = sm.y[g] + ys * (T * P);
-#pragma unroll
+#pragma unroll 1
 		for (int br = 0; br < P; br++) {
+			/* the window is (re)loaded per polyphase branch: 52 packed operands are 104 registers, which do not
+			 * survive two unrolled 49-tap passes without spilling */
+			unsigned long long w[SONDE_FIR_HIST + 4];
+#pragma unroll
+			for (int i = 0; i < (SONDE_FIR_HIST + 4) / 2; i++) {
+				const ulonglong2 t = src[i];
+				w[2 * i] = t.x;
+				w[2 * i + 1] = t.y;
+			}
 			unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};                  /* (+0, +0) */
 			const unsigned long long *tp = reinterpret_cast<const unsigned long long *>(c_taps2[type] + br * SONDE_FIR_TAPS);
 #pragma unroll
@@ -497,7 +499,7 @@ __device__ __forceinline__ void agc_tile(const float *__restrict__ x, float *__r
 }
 
 template <int P, int KM0, int NM, int KS0, int NS, bool IQ, bool SOFT, bool TMA>
-__global__ void __launch_bounds__(768, 1)
+__global__ void __maxnreg__(64)
 demod_pipe_kernel(const demod_params p, const int group_base)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];

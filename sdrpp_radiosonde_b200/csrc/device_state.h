@@ -116,6 +116,10 @@ static inline cudaError_t sonde_ensure_dynamic_smem(Kernel kernel, int bytes, st
 	if (e != cudaSuccess) return e;
 	if (dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
 	e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	/* keep the SM's L1 / shared split at its shared-memory maximum so that small CTAs of other kernels (the framer of
+	 * the previous call) can be resident beside a demodulator CTA */
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e == cudaSuccess && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
 	return e;
 }

@@ -37,7 +37,7 @@ extern "C" cudaError_t sonde_upload_modems_frame(const sonde_modem *m)
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 4;
+constexpr int WARPS_PER_CTA = 2;    /* 64 threads x 128 registers: small enough to sit beside a K1 CTA (768 x 72) on the same SM */
 constexpr int WIN_WORDS = 264;            /* >= 2 * 4144 / 32 + 4 : the framer buffer holds up to 2F bits */
 constexpr int WORK_BYTES = 1024;
 constexpr unsigned FULL = 0xffffffffu;

@@ -581,12 +581,14 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	fp.chunk_index = h->chunk_index;
 	fp.counts = h->d_counts[par];
 	fp.active = h->d_active;
-	CK(cudaStreamWaitEvent(h->fstream, h->ev_demod[par], 0));
-	CK(cudaEventRecord(h->evf[0], h->fstream));
-	CK(sonde_launch_frames(&fp, h->fstream));
+	static const bool frame_serial = getenv("SONDE_FRAME_SERIAL") != nullptr;      /* experiment switch */
+	cudaStream_t fs_ = frame_serial ? h->stream : h->fstream;
+	CK(cudaStreamWaitEvent(fs_, h->ev_demod[par], 0));
+	CK(cudaEventRecord(h->evf[0], fs_));
+	CK(sonde_launch_frames(&fp, fs_));
 	h->launches++;
-	CK(cudaEventRecord(h->evf[1], h->fstream));
-	CK(cudaEventRecord(h->ev_done[par], h->fstream));
+	CK(cudaEventRecord(h->evf[1], fs_));
+	CK(cudaEventRecord(h->ev_done[par], fs_));
 	h->have_timing = true;
 	h->chunk_index++;
 	h->n_issued++;

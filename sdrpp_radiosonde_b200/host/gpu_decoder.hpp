@@ -23,8 +23,10 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sonde_b200.h"
@@ -73,6 +75,9 @@ inline void merge_fragment(SondeFullData &d, const SondeData &f)
 		snprintf(buf, sizeof(buf), "O3=%.2fmPa", f.o3_mpa);
 		d.auxData = buf;
 	}
+	/* decoder.hpp:108-110: after every fragment, a sonde (or a frame) without a pressure sensor reports the
+	 * barometric estimate of its altitude */
+	if (d.pressure <= 0) d.pressure = tl::altitude_to_pressure(d.alt);
 }
 
 /* C channels, one input stream each, one GPU call per buffer. */
@@ -107,8 +112,11 @@ public:
 		m_data.resize(in.size());
 		m_tele.clear();
 		for (size_t c = 0; c < in.size(); c++) m_tele.emplace_back(types[c]);
-		m_stage = (float *)sonde_b200_host_alloc((size_t)in.size() * max_chunk * 2 * sizeof(float));
-		if (!m_stage) throw std::runtime_error("pinned staging allocation failed");
+		m_backlog.assign(in.size(), {});
+		for (auto &st : m_stage) {
+			st = (float *)sonde_b200_host_alloc((size_t)in.size() * max_chunk * 2 * sizeof(float));
+			if (!st) throw std::runtime_error("pinned staging allocation failed");
+		}
 		for (auto *s : m_in) dsp::block::registerInput(s);
 		dsp::block::_block_init = true;
 	}
@@ -121,48 +129,98 @@ public:
 		dsp::block::stop();
 		for (auto *s : m_in) dsp::block::unregisterInput(s);
 		dsp::block::_block_init = false;
-		if (m_stage) sonde_b200_host_free(m_stage);
-		m_stage = nullptr;
+		for (auto &st : m_stage) {
+			if (st) sonde_b200_host_free(st);
+			st = nullptr;
+		}
 		sonde_b200_destroy(m_h);
 		m_h = nullptr;
 	}
 
+	/* One pass: take what every input stream delivers, decode as much as ALL channels have, keep the rest.
+	 *
+	 * The reference block consumes its whole buffer (decoder.hpp:59-117).  A bank has C streams that need not deliver
+	 * the same count, and a dsp::stream buffer may carry more than max_chunk samples, so nothing may be cut off:
+	 * every stream's samples are appended to a per-channel backlog, the common prefix is decoded in sub-chunks of at
+	 * most max_chunk, and what one channel has beyond the others waits for the next pass.  Sub-chunks are pipelined
+	 * two deep through the C ABI (process(k+1) is issued before fetch(k), sonde_b200.h), from two pinned staging
+	 * buffers that the channels are copied into by a few threads. */
 	int run() override
 	{
 		const size_t C = m_in.size();
-		int count = -1;
 		for (size_t c = 0; c < C; c++) {
 			const int n = m_in[c]->read();
 			if (n < 0) return -1;
-			if (count < 0 || n < count) count = n;          /* channels are fed in lock step */
+			m_backlog[c].insert(m_backlog[c].end(), m_in[c]->readBuf, m_in[c]->readBuf + n);
+			m_in[c]->flush();
 		}
-		if (count > m_max_chunk) count = m_max_chunk;
-		for (size_t c = 0; c < C; c++)
-			memcpy(m_stage + c * (size_t)count * 2, m_in[c]->readBuf, (size_t)count * sizeof(dsp::complex_t));
+		size_t avail = m_backlog[0].size();
+		for (size_t c = 1; c < C; c++) avail = std::min(avail, m_backlog[c].size());
 
-		if (count > 0) {
-			if (sonde_b200_process_iq(m_h, m_stage, (size_t)count) != SONDE_OK ||
-			    sonde_b200_fetch(m_h, m_recs.data(), m_counts.data()) != SONDE_OK)
+		size_t done = 0;
+		int in_flight = 0;                               /* sub-chunks processed but not fetched yet (0 or 1) */
+		int slot = 0;
+		while (done < avail) {
+			const size_t count = std::min(avail - done, (size_t)m_max_chunk);
+			stage(slot, done, count);
+			if (sonde_b200_process_iq(m_h, m_stage[slot], count) != SONDE_OK)
 				throw std::runtime_error(std::string("sonde_b200: ") + sonde_b200_last_error(m_h));
-			for (size_t c = 0; c < C; c++) {
-				for (int k = 0; k < m_counts[c]; k++) {
-					const sonde_frame_rec &r = m_recs[c * m_max_frames + k];
-					if (m_fcb) m_fcb((int)c, &r, m_fctx);
-					SondeData fragment;
-					m_tele[c].parse(r, &fragment);
-					merge_fragment(m_data[c], fragment);
-					if (fragment.fields && m_cb) m_cb(&m_data[c], m_ctx);
-				}
-			}
+			if (in_flight) deliver();                    /* records of the sub-chunk before this one */
+			in_flight = 1;
+			done += count;
+			slot ^= 1;
 		}
-		for (auto *s : m_in) s->flush();
+		if (in_flight) deliver();
+		if (done)
+			for (size_t c = 0; c < C; c++) m_backlog[c].erase(m_backlog[c].begin(), m_backlog[c].begin() + done);
 		return 0;
 	}
+
+	/* samples waiting because another channel's stream has delivered less so far */
+	size_t backlog(size_t channel) const { return m_backlog[channel].size(); }
 
 	sonde_b200 *handle() { return m_h; }
 
 private:
+	/* copy [first, first + count) of every channel's backlog into staging buffer `slot`, [C][count] row-major */
+	void stage(int slot, size_t first, size_t count)
+	{
+		const size_t C = m_in.size();
+		const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t)8, C, (size_t)std::thread::hardware_concurrency()}));
+		auto work = [&](size_t t) {
+			for (size_t c = t; c < C; c += nthreads)
+				memcpy(m_stage[slot] + c * count * 2, m_backlog[c].data() + first, count * sizeof(dsp::complex_t));
+		};
+		if (nthreads == 1 || C * count < (size_t)1 << 16) {
+			for (size_t t = 0; t < nthreads; t++) work(t);
+			return;
+		}
+		std::vector<std::thread> pool;
+		for (size_t t = 1; t < nthreads; t++) pool.emplace_back(work, t);
+		work(0);
+		for (auto &th : pool) th.join();
+	}
+
+	/* fetch the oldest unfetched call and fire the callbacks, in record order per channel */
+	void deliver()
+	{
+		const size_t C = m_in.size();
+		if (sonde_b200_fetch(m_h, m_recs.data(), m_counts.data()) != SONDE_OK)
+			throw std::runtime_error(std::string("sonde_b200: ") + sonde_b200_last_error(m_h));
+		for (size_t c = 0; c < C; c++) {
+			for (int k = 0; k < m_counts[c]; k++) {
+				const sonde_frame_rec &r = m_recs[c * m_max_frames + k];
+				if (m_fcb) m_fcb((int)c, &r, m_fctx);
+				SondeData fragment;
+				m_tele[c].parse(r, &fragment);
+				merge_fragment(m_data[c], fragment);
+				if (fragment.fields && m_cb) m_cb(&m_data[c], m_ctx);
+			}
+		}
+	}
+
 	std::vector<dsp::stream<dsp::complex_t> *> m_in;
+	std::vector<std::vector<dsp::complex_t>> m_backlog;
 	std::vector<int32_t> m_types;
 	SondeCallback m_cb = nullptr;
 	FrameCallback m_fcb = nullptr;
@@ -173,7 +231,7 @@ private:
 	std::vector<int32_t> m_counts;
 	std::vector<SondeFullData> m_data;
 	std::vector<Telemetry> m_tele;
-	float *m_stage = nullptr;
+	float *m_stage[2] = {nullptr, nullptr};
 };
 
 /* One channel: the drop-in for one plugin instance (src/main.hpp:33-42). */

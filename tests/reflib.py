@@ -100,6 +100,20 @@ class _FrameRunner:
         assert 0 <= n <= cap
         return soft[:n].copy(), state
 
+    def afsk_soft(self, stype, fm, chunk, samplerate=48000):
+        """Soft symbols + final loop state of the reference's AFSK chain (compiled reference only)."""
+        fm = np.ascontiguousarray(fm, dtype=np.float32)
+        cap = fm.size // 8 + 64
+        soft = np.zeros(cap, dtype=np.float32)
+        state = np.zeros(8, dtype=np.float32)
+        fn = getattr(self.lib, self.prefix + "_afsk_soft")
+        fn.restype = ctypes.c_long
+        fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_size_t, ctypes.c_size_t,
+                       ctypes.POINTER(ctypes.c_float), ctypes.c_size_t, ctypes.POINTER(ctypes.c_float)]
+        n = fn(int(stype), samplerate, _fptr(fm), fm.size, chunk, _fptr(soft), cap, _fptr(state))
+        assert 0 <= n <= cap
+        return soft[:n].copy(), state
+
     def gfsk_taps(self, baud, samplerate=48000):
         taps = np.zeros(256, dtype=np.float32)
         fn = getattr(self.lib, self.prefix + "_gfsk_taps")
@@ -206,6 +220,22 @@ def _frames_run_iq(self, stype, iq, chunk, samplerate=48000, gain=0.0, max_recs=
 
 
 OracleLib.frames_run_iq = _frames_run_iq
+
+
+def _discriminate(self, iq, gain=0.636619747, libm=False):
+    """The restated FM discriminator over one channel's IQ (prev phase 0 at the start): float FM stream.
+    libm=True: the glibc atan2f variant kept to report how far an upstream-like discriminator drifts."""
+    iq = np.ascontiguousarray(iq, dtype=np.complex64)
+    out = np.zeros(iq.size, dtype=np.float32)
+    prev = ctypes.c_float(0.0)
+    fn = self.lib.orc_discriminate_libm if libm else self.lib.orc_discriminate
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float, ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]
+    fn(iq.ctypes.data, iq.size, ctypes.c_float(gain), ctypes.byref(prev), out.ctypes.data)
+    return out
+
+
+OracleLib.discriminate = _discriminate
 
 
 def _frames_run_ragged(self, stype, fm, chunks, samplerate=48000, max_recs=None):

@@ -221,3 +221,48 @@ def test_nco_wrap_identity():
     assert np.all(a.astype(np.float64) == xs.astype(np.float64) - np.float64(hi))      # Sterbenz: exact
     got = (a + dl).astype(np.float32)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("stype", [synth.IMET4, synth.C50])
+def test_ref_afsk_soft_mirror_reproduces_afsk_demod(stype):
+    """ref_afsk_soft() (oracle/ref_harness.c) restates the per-sample statements of SD/demod/afsk.c:104-151 around the
+    reference's own primitives to expose the symbol VALUES; its hard decisions must be afsk_demod()'s bits."""
+    if not reflib.have_ref():
+        pytest.skip("compiled reference not built")
+    ref = reflib.RefLib()
+    n = 48000 * 3
+    fm = synth.make_fm(synth.default_spec(stype, 7), n)
+    for chunk in (1024, 48000):
+        soft, _ = ref.afsk_soft(stype, fm, chunk)
+        bits = ref.demod_bits(stype, fm, chunk)
+        assert soft.size == bits.size and soft.size > 1000
+        assert np.array_equal((soft > 0).astype(np.uint8), bits), (stype, chunk)
+
+
+def test_discriminator_drift_vs_libm_atan2f():
+    """"Parity unpinned" stage (SDR++'s dsp::demod::FM is not under /root/reference): the report SURVEY.md §8c asks for.
+    The polynomial discriminator of this repo vs a glibc atan2f one on the same IQ: per-sample difference of the FM
+    stream, and what it does downstream in the UNMODIFIED reference chain (soft symbols, frames)."""
+    if not (reflib.have_ref() and reflib.have_oracle()):
+        pytest.skip("needs oracle/_ref and oracle/_build")
+    ref, orc = reflib.RefLib(), reflib.OracleLib()
+    n = 48000 * 4
+    iq = synth.make_iq(synth.default_spec(synth.RS41, 3), n)
+    fm_poly, fm_libm = orc.discriminate(iq), orc.discriminate(iq, libm=True)
+    d = np.abs(fm_poly.astype(np.float64) - fm_libm)
+    rms = float(np.sqrt(np.mean(fm_libm.astype(np.float64) ** 2)))
+    print(f"discriminator: max |poly - atan2f| = {d.max():.3e} ({d.max() / rms:.2e} of the FM rms), "
+          f"{np.count_nonzero(fm_poly != fm_libm)} of {n} samples differ in the last bits")
+    assert d.max() < 1e-6 * max(1.0, rms * 10)            # 2.4 ulp polynomial vs libm: ~1e-7 of full scale
+    sp, _ = ref.gfsk_soft(4800, fm_poly, 48000)
+    sl, _ = ref.gfsk_soft(4800, fm_libm, 48000)
+    m = min(sp.size, sl.size)
+    srms = float(np.sqrt(np.mean(sl[:m].astype(np.float64) ** 2)))
+    rel = np.abs(sp[:m].astype(np.float64) - sl[:m]) / srms
+    print(f"downstream soft symbols: {np.count_nonzero(sp[:m] != sl[:m])} of {m} differ, "
+          f"{np.count_nonzero(rel > 1e-5)} by more than 1e-5 of the rms, max {rel.max():.2e}; "
+          f"hard decisions differing: {np.count_nonzero((sp[:m] > 0) != (sl[:m] > 0))}")
+    fp = ref.frames_run(synth.RS41, fm_poly, 48000)
+    fl = ref.frames_run(synth.RS41, fm_libm, 48000)
+    assert [int(r.ok) for r in fp] == [int(r.ok) for r in fl] and sum(int(r.ok) for r in fp) >= 3
+    assert [bytes(r.data[:320]) for r in fp if r.ok] == [bytes(r.data[:320]) for r in fl if r.ok]
