@@ -484,51 +484,127 @@ def main():
         except Exception as ex:                      # informational extra
             wide = {"error": f"{type(ex).__name__}: {ex}"}
 
-    # N > 1: the one exchange step the path can have — the whole batch originates on rank 0 and is
-    # scattered over NVLink chunk by chunk, double-buffered against the decode.  Reported beside the main number,
-    # which is measured with every rank's shard already resident.
+    # N > 1: the one exchange step the path can have — the whole batch originates on rank 0 (one front
+    # end feeding the box).  Two forms, both reported beside the main number (which has every shard resident):
+    #  (a) pre-channelised complex64: every rank PULLS its [C][L] block out of rank 0's buffer with the copy engine
+    #      (CUDA IPC + sonde_b200_process_iq_peer = cudaMemcpyPeerAsync: no SMs, so the pull of chunk i+1 runs beside
+    #      the decode of chunk i); rank 0's NVLink egress is (N-1) * C * L * 8 bytes per step — the physical bound
+    #  (b) wideband: rank 0 broadcasts the 18 MB wideband buffer (NCCL) and every rank channelises its own block
     scatter = None
+    wide_src = None
     if world > 1 and not args.no_scatter:
         try:
-            from sdrpp_radiosonde_b200 import shard
-            n_sc = 6
-            full = [dev_iq[k].repeat(world, 1) for k in range(2)] if rank == 0 else [None, None]
-            bufs = [torch.empty((C, L), dtype=torch.complex64, device="cuda") for _ in range(2)]
+            from cuda.bindings import runtime as cudart
+
+            def ck(r):
+                if isinstance(r, tuple):
+                    err, rest = r[0], r[1:]
+                else:
+                    err, rest = r, ()
+                if int(err) != 0:
+                    raise RuntimeError(f"cudart error {err}")
+                return rest[0] if len(rest) == 1 else rest
+
+            n_sc = 8
+            blk = C * L * 8
+            handles = [None, None]
+            srcs = [0, 0]
+            if rank == 0:
+                for j in range(2):
+                    srcs[j] = int(ck(cudart.cudaMalloc(world * blk)))
+                    for r in range(world):
+                        ck(cudart.cudaMemcpy(srcs[j] + r * blk, dev_iq[j % n_chunks].data_ptr(), blk,
+                                             cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice))
+                    handles[j] = bytes(ck(cudart.cudaIpcGetMemHandle(srcs[j])).reserved)
+            dist.broadcast_object_list(handles, src=0)
+            if rank != 0:
+                for j in range(2):
+                    hnd = cudart.cudaIpcMemHandle_t()
+                    hnd.reserved = handles[j]
+                    srcs[j] = int(ck(cudart.cudaIpcOpenMemHandle(hnd, cudart.cudaIpcMemLazyEnablePeerAccess)))
             dec3 = capi.BatchDecoder(sig_types, L, device=local_rank)
-            shard.scatter_channels(full[0], bufs[0], world, rank)
+
+            def pull(i):
+                ptr = srcs[i % 2] + rank * blk
+                if rank == 0:
+                    dec3.process_iq_device(ptr, L)
+                else:
+                    dec3.process_iq_peer(0, ptr, L)
+            for i in range(2):
+                pull(i)
+                dec3.fetch_counts()
             barrier()
             t0 = time.perf_counter()
+            pull(0)
             for i in range(n_sc):
-                dec3.sync()                                   # decode(i-1) no longer reads bufs[(i+1) % 2]
-                dec3.process_iq_device(bufs[i % 2].data_ptr(), L)      # overlaps the scatter of the next chunk
-                works = shard.scatter_channels(full[(i + 1) % 2], bufs[(i + 1) % 2], world, rank, async_op=True) \
-                    if i + 1 < n_sc else []
-                for w in works:
-                    w.wait()
-                torch.cuda.current_stream().synchronize()
+                if i + 1 < n_sc:
+                    pull(i + 1)
+                dec3.fetch_counts()
             dec3.sync()
             barrier()
             t_sc = time.perf_counter() - t0
-            # scatter alone
-            barrier()
-            t0 = time.perf_counter()
-            for i in range(n_sc):
-                shard.scatter_channels(full[i % 2], bufs[i % 2], world, rank)
-                torch.cuda.current_stream().synchronize()
-            barrier()
-            t_so = time.perf_counter() - t0
-            scatter = {"t": t_sc, "t_only": t_so, "n": n_sc}
+            scatter = {"t": t_sc, "n": n_sc}
             dec3.close()
-            del full, bufs
+            if rank != 0:
+                for j in range(2):
+                    cudart.cudaIpcCloseMemHandle(srcs[j])
+            barrier()
+            if rank == 0:
+                for j in range(2):
+                    cudart.cudaFree(srcs[j])
         except Exception as ex:                      # informational extra
             scatter = None
             print(f"scatter measurement failed: {type(ex).__name__}: {ex}", file=sys.stderr)
+        try:
+            Dw = 48
+            n_in = L * Dw
+            rngw = np.random.default_rng(7)
+            freqs = np.random.default_rng(11 + rank).uniform(-0.45, 0.45, C) * FS * Dw
+            wbuf = [torch.empty((n_in,), dtype=torch.complex64, device="cuda") for _ in range(2)]
+            if rank == 0:
+                for wb in wbuf:
+                    wb.copy_(torch.from_numpy((0.05 * (rngw.standard_normal(n_in) + 1j * rngw.standard_normal(n_in))).astype(np.complex64)))
+            chz = capi.Channelizer(freqs, Dw, n_in, device=local_rank)
+            dec6 = capi.BatchDecoder(sig_types, L, device=local_rank)
+            ext6 = torch.cuda.ExternalStream(dec6.stream)
+            cur = torch.cuda.current_stream()
+            done6 = [None, None]
+
+            def wstep6(i):
+                if done6[i & 1] is not None:
+                    cur.wait_event(done6[i & 1])
+                dist.broadcast(torch.view_as_real(wbuf[i & 1]), src=0)          # 18 MB over NVLink (NCCL)
+                ptr, stride, m = chz.process_c64_device(wbuf[i & 1].data_ptr(), n_in, stream=cur.cuda_stream)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                ext6.wait_event(ev)
+                dec6.process_iq_device(ptr, m, stride)
+                done6[i & 1] = torch.cuda.Event()
+                done6[i & 1].record(ext6)
+            for i in range(3):
+                wstep6(i)
+                dec6.fetch_counts()
+            barrier()
+            t0 = time.perf_counter()
+            wstep6(0)
+            for i in range(args.steps):
+                if i + 1 < args.steps:
+                    wstep6(i + 1)
+                dec6.fetch_counts()
+            dec6.sync()
+            barrier()
+            wide_src = {"t": time.perf_counter() - t0, "bytes": n_in * 8, "D": Dw}
+            chz.close()
+            dec6.close()
+        except Exception as ex:                      # informational extra
+            wide_src = None
+            print(f"wideband single-source measurement failed: {type(ex).__name__}: {ex}", file=sys.stderr)
 
     stop.set()
     th.join(timeout=2)
 
     t_all = torch.tensor([ms, (e2e["t"] * 1e3) if e2e else 0.0, scatter["t"] * 1e3 if scatter else 0.0,
-                          scatter["t_only"] * 1e3 if scatter else 0.0, (e2e["t16"] * 1e3) if e2e else 0.0,
+                          wide_src["t"] * 1e3 if wide_src else 0.0, (e2e["t16"] * 1e3) if e2e else 0.0,
                           (wide["t"] * 1e3) if wide and "t" in wide else 0.0],
                          dtype=torch.float64, device="cuda")
     tot = torch.tensor([frames, ok], dtype=torch.float64, device="cuda")
@@ -599,12 +675,21 @@ def main():
                                             f"({wide['taps']} taps, {C} channel centres) -> the same {C}-channel decode, per step; "
                                             "channel samples per second; informational (SURVEY §8 f-2)"}
         if scatter:
-            sc_ms, so_ms = float(t_all[2]) / scatter["n"], float(t_all[3]) / scatter["n"]
-            line["scatter"] = {"what": "batch resident on rank 0, NCCL send/recv of each rank's [C][L] complex64 block per chunk, "
-                                       "double-buffered against the decode",
+            sc_ms = float(t_all[2]) / scatter["n"]
+            line["scatter"] = {"what": "batch resident on rank 0; every rank pulls its [C][L] complex64 block over NVLink with the "
+                                       "copy engine (CUDA IPC + cudaMemcpyPeerAsync, sonde_b200_process_iq_peer), the pull of "
+                                       "chunk i+1 beside the decode of chunk i",
                                "ms_per_step_with_scatter": sc_ms, "value_with_scatter": world * C * L / (sc_ms * 1e-3) / 1e6,
-                               "scatter_only_ms": so_ms,
-                               "rank0_egress_gbs": (world - 1) * C * L * 8 / (so_ms * 1e-3) / 1e9}
+                               "rank0_egress_bytes_per_step": (world - 1) * C * L * 8,
+                               "rank0_egress_gbs": (world - 1) * C * L * 8 / (sc_ms * 1e-3) / 1e9,
+                               "note": "bounded by rank 0's NVLink egress: (N-1) x 393 MB per step"}
+        if wide_src:
+            tw6 = float(t_all[3])
+            line["single_source_wideband"] = {
+                "what": f"rank 0 holds the wideband complex64 IQ ({wide_src['D']} x 48 kS/s, {wide_src['bytes'] / 1e6:.1f} MB per step); NCCL "
+                        "broadcast, then every rank channelises (tcgen05 GEMM) and decodes its own channel block",
+                "value": world * args.steps * C * L / (tw6 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": tw6 / args.steps,
+                "broadcast_bytes_per_step": wide_src["bytes"]}
         if not args.no_cpu_baseline and world == 1:
             cpu = CpuPath()
             n_ch = min(C, 2 * ncores)

@@ -142,6 +142,12 @@ SONDE_API int  sonde_b200_process_iq_s16(sonde_b200 *h, const int16_t *iq /*[C][
 SONDE_API int  sonde_b200_process_iq_device(sonde_b200 *h, const void *d_iq, size_t len, size_t row_stride);
 SONDE_API int  sonde_b200_process_fm_device(sonde_b200 *h, const void *d_fm, size_t len, size_t row_stride);
 
+/* Input resident on ANOTHER GPU of the box (a front-end GPU feeding its peers; SURVEY.md §8e, the north_star's
+ * "scatter the channel batch"): this handle's [C][len] complex64 block is pulled from device `src_device` over NVLink
+ * by the copy engine (cudaMemcpyPeerAsync, no SMs involved) and decoded.  Double buffered like the host entry points:
+ * process_iq_peer(i+1) may be issued before fetch(i). */
+SONDE_API int  sonde_b200_process_iq_peer(sonde_b200 *h, int src_device, const void *d_iq_src, size_t len, size_t row_stride);
+
 /* Capacity (records per channel per process call) of the fetch arrays. */
 SONDE_API int  sonde_b200_max_frames(const sonde_b200 *h);
 

@@ -25,7 +25,7 @@ EXPORTS = [
     "sonde_b200_process_iq_s16", "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
     "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_detected_types", "sonde_b200_auto_plausible", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
     "sonde_b200_soft_stride", "sonde_b200_fetch_soft", "sonde_b200_fetch_state", "sonde_b200_modem_info",
-    "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_debug_demod_state", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
+    "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_debug_demod_state", "sonde_b200_process_iq_peer", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
     "sonde_b200_last_kernel_ms", "sonde_b200_launch_count", "sonde_b200_last_error", "sonde_b200_version",
 ]
 
@@ -106,6 +106,7 @@ def load():
         "sonde_b200_stream": (vp, [vp]),
         "sonde_b200_debug_stalls": (ctypes.c_int, [vp, vp, ctypes.c_int]),
         "sonde_b200_debug_demod_state": (ctypes.c_int, [vp, vp, sz]),
+        "sonde_b200_process_iq_peer": (ctypes.c_int, [vp, ctypes.c_int, vp, sz, sz]),
         "sonde_b200_sync": (ctypes.c_int, [vp]),
         "sonde_b200_join": (ctypes.c_int, [vp]),
         "sonde_b200_last_kernel_ms": (ctypes.c_int, [vp, f32p, f32p]),
@@ -287,6 +288,11 @@ class BatchDecoder:
         st = np.zeros((self.C, 8), dtype=np.float32)
         self._ck(self.lib.sonde_b200_fetch_state(self.h, _f32p(st)))
         return st
+
+    def process_iq_peer(self, src_device, dev_ptr, length, row_stride=None):
+        """[C][length] complex64 resident on GPU `src_device`: pulled by the copy engine, then decoded."""
+        self._ck(self.lib.sonde_b200_process_iq_peer(self.h, int(src_device), ctypes.c_void_p(dev_ptr), length,
+                                                     length if row_stride is None else row_stride))
 
     def debug_demod_state(self):
         """Raw demodulator state per (virtual) channel as float32 words [C][64] (diagnostics)."""

@@ -51,6 +51,9 @@ struct sonde_b200 {
 	bool has_auto = false;
 	sonde_modem modems[SONDE_NTYPES_];
 	int device = 0, n_sms = 0;
+	cudaStream_t pstream[3] = {nullptr, nullptr, nullptr};   /* extra copy streams of sonde_b200_process_iq_peer */
+	cudaEvent_t ev_piece[3] = {nullptr, nullptr, nullptr};
+	unsigned long long peers_enabled = 0;  /* devices this handle's device has been given peer access to */
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 
@@ -98,6 +101,8 @@ struct sonde_b200 {
 	bool have_timing = false;
 	std::string err;
 };
+
+#define SONDE_PEER_STREAMS 4
 
 namespace {
 
@@ -391,6 +396,10 @@ void sonde_b200_destroy(sonde_b200 *h)
 	if (h->dstream) cudaStreamDestroy(h->dstream);
 	if (h->fstream) cudaStreamDestroy(h->fstream);
 	if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+	for (int i = 0; i < 3; i++) {
+		if (h->pstream[i]) cudaStreamDestroy(h->pstream[i]);
+		if (h->ev_piece[i]) cudaEventDestroy(h->ev_piece[i]);
+	}
 	for (int v = 0; v < 4; v++) {
 		if (h->vstream[v]) cudaStreamDestroy(h->vstream[v]);
 		if (h->ev_join[v]) cudaEventDestroy(h->ev_join[v]);
@@ -666,6 +675,74 @@ int sonde_b200_process_iq_s16(sonde_b200 *h, const int16_t *iq, size_t len, floa
 		static_cast<const short2 *>(h->d_in16[par]) + 4 * n4, static_cast<float2 *>(h->d_in[par]) + 4 * n4, n_tail, scale);
 	CK(cudaGetLastError());
 	h->launches++;
+	CK(cudaEventRecord(h->ev_copied[par], h->cstream));
+	CK(cudaStreamWaitEvent(h->stream, h->ev_copied[par], 0));
+	return run_chunk(h, h->d_in[par], len, len, 1);
+}
+
+/* The channel block of this handle lives on ANOTHER GPU of the box (one front-end GPU feeding its peers, SURVEY.md
+ * §8e): pull it over NVLink with the copy engine (cudaMemcpyPeerAsync on this handle's copy stream: no SMs, nothing
+ * that competes with the demodulator for CTAs), then decode it.  Same double-buffered protocol as the host entry
+ * points: the pull of call i+1 overlaps the kernels of call i. */
+int sonde_b200_process_iq_peer(sonde_b200 *h, int src_device, const void *d_iq_src, size_t len, size_t row_stride)
+{
+	if (!h) return SONDE_ERR_ARG;
+	if (!d_iq_src || len == 0) return fail(h, SONDE_ERR_ARG, "null input or zero length");
+	if (len > (size_t)h->cfg.max_chunk_len) return fail(h, SONDE_ERR_TOOLONG, "len > max_chunk_len");
+	if (row_stride < len) return fail(h, SONDE_ERR_ARG, "row_stride < len");
+	CK(cudaSetDevice(h->device));
+	if (src_device != h->device && !((h->peers_enabled >> src_device) & 1ull)) {
+		int can = 0;
+		CK(cudaDeviceCanAccessPeer(&can, h->device, src_device));
+		if (can) {
+			const cudaError_t e = cudaDeviceEnablePeerAccess(src_device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(h, SONDE_ERR_CUDA, "cudaDeviceEnablePeerAccess", e);
+			(void)cudaGetLastError();
+		}
+		if (src_device >= 0 && src_device < 64) h->peers_enabled |= 1ull << src_device;      /* without P2P the copy is staged by the driver */
+	}
+	const size_t need = (size_t)h->n_user * h->cfg.max_chunk_len * 2 * sizeof(float);
+	const int par = (int)(h->n_issued & 1);
+	if (!h->d_in[par]) CK(cudaMalloc(&h->d_in[par], need));
+	if (h->n_issued >= 2) CK(cudaStreamWaitEvent(h->cstream, h->ev_done[par], 0));
+	const size_t esz = 2 * sizeof(float);
+	if (row_stride == len) {
+		/* one copy stream drives one copy engine, which moved ~245 GB/s of the link's ~750 GB/s on the B200 box; the
+		 * block is therefore pulled as up to PEER_STREAMS pieces on as many streams */
+		const size_t total = (size_t)h->n_user * len * esz;
+		const int pieces = total >= ((size_t)8 << 20) ? SONDE_PEER_STREAMS : 1;
+		const size_t step = ((total / pieces) + 255) & ~(size_t)255;
+		if (pieces > 1) CK(cudaEventRecord(h->ev_fork, h->cstream));
+		for (int i = 0; i < pieces; i++) {
+			const size_t off = (size_t)i * step;
+			if (off >= total) break;
+			const size_t nbytes = std::min(step, total - off);
+			cudaStream_t st = i == 0 ? h->cstream : h->pstream[i - 1];
+			if (i > 0) {
+				if (!st) {
+					CK(cudaStreamCreateWithFlags(&h->pstream[i - 1], cudaStreamNonBlocking));
+					CK(cudaEventCreateWithFlags(&h->ev_piece[i - 1], cudaEventDisableTiming));
+					st = h->pstream[i - 1];
+				}
+				CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+			}
+			CK(cudaMemcpyPeerAsync(static_cast<char *>(h->d_in[par]) + off, h->device, static_cast<const char *>(d_iq_src) + off,
+			                       src_device, nbytes, st));
+			if (i > 0) {
+				CK(cudaEventRecord(h->ev_piece[i - 1], st));
+				CK(cudaStreamWaitEvent(h->cstream, h->ev_piece[i - 1], 0));
+			}
+		}
+	} else {
+		cudaMemcpy3DPeerParms pp;
+		memset(&pp, 0, sizeof(pp));
+		pp.srcDevice = src_device;
+		pp.dstDevice = h->device;
+		pp.srcPtr = make_cudaPitchedPtr(const_cast<void *>(d_iq_src), row_stride * esz, len * esz, (size_t)h->n_user);
+		pp.dstPtr = make_cudaPitchedPtr(h->d_in[par], len * esz, len * esz, (size_t)h->n_user);
+		pp.extent = make_cudaExtent(len * esz, (size_t)h->n_user, 1);
+		CK(cudaMemcpy3DPeerAsync(&pp, h->cstream));
+	}
 	CK(cudaEventRecord(h->ev_copied[par], h->cstream));
 	CK(cudaStreamWaitEvent(h->stream, h->ev_copied[par], 0));
 	return run_chunk(h, h->d_in[par], len, len, 1);

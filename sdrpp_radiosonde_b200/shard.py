@@ -44,6 +44,31 @@ def gather_counts(local_counts: np.ndarray, n_channels: int, world: int, rank: i
     return np.concatenate([o[: sizes[r]].cpu().numpy() for r, o in enumerate(out)])
 
 
+def gather_records(local_recs: np.ndarray, local_counts: np.ndarray, n_channels: int, world: int, rank: int):
+    """All ranks' frame records in global channel order with ONE all_gather (the output side of the
+    multi-GPU path; records are fixed-size, a few MB per rank).  local_recs: [C_rank][max_frames] structured array
+    (capi.REC_DTYPE), local_counts: [C_rank].  Returns (recs[C][max_frames], counts[C]) on every rank."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local_recs, np.asarray(local_counts)
+    sizes = [shard_range(n_channels, world, r)[1] - shard_range(n_channels, world, r)[0] for r in range(world)]
+    cap, mf, isz = max(sizes), local_recs.shape[1], local_recs.dtype.itemsize
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    # one message per rank: [cap] int32 counts (as bytes) followed by [cap][max_frames] records
+    msg = np.zeros(cap * 4 + cap * mf * isz, dtype=np.uint8)
+    msg[: 4 * len(local_counts)] = np.asarray(local_counts, dtype=np.int32).view(np.uint8)
+    msg[cap * 4: cap * 4 + local_recs.size * isz] = np.ascontiguousarray(local_recs).view(np.uint8).ravel()
+    mine = torch.from_numpy(msg).to(dev)
+    out = torch.empty(world * msg.size, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, mine)
+    buf = out.cpu().numpy().reshape(world, msg.size)
+    counts = np.concatenate([buf[r, : 4 * sizes[r]].view(np.int32) for r in range(world)])
+    recs = np.concatenate([buf[r, cap * 4: cap * 4 + sizes[r] * mf * isz].view(local_recs.dtype).reshape(sizes[r], mf)
+                           for r in range(world)])
+    return recs, counts
+
+
 def scatter_channels(full, out, world: int, rank: int, src: int = 0, async_op: bool = False):
     """Scatter the channel batch `full[C][L]` held by rank `src` so that every rank gets its shard_range()
     block in `out[(hi-lo)][L]` (torch tensors on the backend's device; complex64 is sent as float pairs).

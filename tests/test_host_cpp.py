@@ -182,3 +182,45 @@ def test_channel_bank_unequal_streams_lose_nothing(tmp_path):
         assert abs(int(ch[c]["frames"]) - want_frames[c]) <= 1, (c, ch[c], want_frames[c])
         assert int(ch[c]["ok"]) >= want_ok[c] - 1 and want_ok[c] >= 3, (c, ch[c], want_ok[c])
         assert int(ch[c]["callbacks"]) >= 1 and ch[c]["pressure_ok"] == "1", (c, ch[c])
+
+
+MEXE = os.path.join(ROOT, "build", "host_multibank_test")
+
+
+def build_multibank_exe():
+    os.makedirs(os.path.dirname(MEXE), exist_ok=True)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-O2", "-std=c++17", f"-I{ROOT}/include", f"-I{cuda}/include", f"{ROOT}/tests/cpp/host_multibank_test.cpp",
+           "-o", MEXE, f"-L{ROOT}/sdrpp_radiosonde_b200", "-lsonde_b200", f"-L{cuda}/lib64", "-lcudart",
+           "-Wl,-rpath," + os.path.join(ROOT, "sdrpp_radiosonde_b200"), "-lpthread"]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+
+
+def test_multibank_compiles_and_fails_loudly_without_gpu(tmp_path):
+    import torch
+    build_multibank_exe()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    (tmp_path / "iq").write_bytes(np.zeros(2048, np.complex64).tobytes())
+    r = subprocess.run([MEXE, "1", "2048", "1024", "2", "0", str(tmp_path / "iq")], capture_output=True, text=True)
+    assert r.returncode == 3 and "NOGPU" in r.stdout and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_multibank_shards_equal_single_handle(tmp_path):
+    """radiosonde::GpuMultiBank (C++ host, one process): 9 channels of four types in 4 shards over the devices of the
+    box (all on device 0 when there is one GPU), fed from a host buffer and from a buffer on device 0 that the shards
+    pull with the copy engine (sonde_b200_process_iq_peer), two buffers in flight: the gathered records are
+    byte-identical to one handle decoding everything."""
+    build_multibank_exe()
+    types = [synth.RS41, synth.M10, synth.DFM09, synth.RS41, synth.C50, synth.IMS100, synth.RS41, synth.M10, synth.MRZN1]
+    n, chunk = 48000 * 3, 12000
+    args = [MEXE, str(len(types)), str(n), str(chunk), "4"]
+    for c, t in enumerate(types):
+        (tmp_path / f"iq{c}").write_bytes(synth.make_iq(synth.default_spec(t, 80 + c), n).tobytes())
+        args += [str(t), str(tmp_path / f"iq{c}")]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = dict(kv.split("=") for kv in r.stdout.strip().splitlines()[-1].split()[1:])
+    assert out["host_equal"] == "1" and out["peer_equal"] == "1", r.stdout
+    assert int(out["frames"]) >= int(out["ok"]) >= 20, r.stdout

@@ -45,6 +45,22 @@ def _worker(rank, world, port, C, q):
     for w in works:
         w.wait()
     assert torch.equal(mine_iq, want_iq)
+    # frame records of every rank in global channel order with one all_gather
+    from sdrpp_radiosonde_b200 import capi
+    mf = 3
+    recs = np.zeros((hi - lo, mf), dtype=capi.REC_DTYPE)
+    cnt = np.array([(c % mf) + 1 for c in range(lo, hi)], dtype=np.int32)
+    for i, c in enumerate(range(lo, hi)):
+        for k in range(cnt[i]):
+            recs[i, k]["chunk"] = 1000 * c + k
+            recs[i, k]["ok"] = (c + k) & 1
+            recs[i, k]["data"][:4] = [c, k, 0xB2, 0x00]
+    allr, allcnt = shard.gather_records(recs, cnt, C, world, rank)
+    assert allr.shape == (C, mf) and allcnt.tolist() == [(c % mf) + 1 for c in range(C)]
+    for c in range(C):
+        for k in range(allcnt[c]):
+            assert int(allr[c, k]["chunk"]) == 1000 * c + k and int(allr[c, k]["ok"]) == ((c + k) & 1)
+            assert allr[c, k]["data"][:4].tolist() == [c, k, 0xB2, 0x00]
     q.put((rank, allc.tolist()))
     dist.barrier()
     dist.destroy_process_group()
