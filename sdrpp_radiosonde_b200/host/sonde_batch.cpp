@@ -1,0 +1,242 @@
+/*
+ * sonde_batch.cpp — sonde_b200_batch: a batch command-line runner on the batch C ABI (include/sonde_b200.h).
+ *
+ * The reference's CLI (SD/main.c:96-366) decodes ONE recording per process: read 1024 samples, decode(), print,
+ * append to CSV/GPX/KML.  This runner decodes MANY recordings at once — every input file is one channel of one GPU
+ * batch — and writes, per channel, the same CSV the reference's `-c` option writes (SD/io/csv.c:8-60) from the same
+ * aggregation of decoder fragments (SD/decode.c:278-376 append_data_point: fields accumulate in one `printable`
+ * record per channel, pressure falls back to the barometric formula, one row per fragment that carried data).
+ *
+ *   sonde_b200_batch [-t type] [-b buflen] [-c csv_prefix] [-i] [-q] file0 [file1 ...]
+ *     -t, --type     auto|c50|dfm|imet4|ims100|m10|mrzn1|rs41 (the reference's names, SD/main.c:66; default auto),
+ *                    or a comma-separated list, one per file
+ *     -b, --buflen   samples per channel per GPU call (default 1024 = the reference's BUFLEN, SD/main.c:32)
+ *     -c, --csv      write <prefix><channel>.csv per channel
+ *     -i, --iq       the files are raw complex64 IQ at 48 kS/s instead of raw float32 FM audio (SD/main.c:257-262)
+ *     -q, --quiet    no per-point lines on stdout
+ * stdout (unless -q): one line per data point  "<channel> <serial> <seq> <lat> <lon> <alt> <temp>"
+ * and always one summary line per channel     "CH <channel> type=<decoder> frames=<n> ok=<n> points=<n>".
+ * Exit code 3 when the CUDA path is unavailable: there is no CPU fallback.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <vector>
+
+#include "../../include/sonde_b200.h"
+#include "sonde_data.hpp"
+#include "telemetry.hpp"
+
+namespace {
+
+const char *kNames[] = {"auto", "c50", "dfm", "imet4", "ims100", "m10", "mrzn1", "rs41"};
+const int kTypes[] = {SONDE_AUTO, SONDE_C50, SONDE_DFM09, SONDE_IMET4, SONDE_IMS100, SONDE_M10, SONDE_MRZN1, SONDE_RS41};
+
+int type_of(const std::string &s)
+{
+	for (size_t i = 0; i < sizeof(kNames) / sizeof(*kNames); i++)
+		if (s == kNames[i]) return kTypes[i];
+	fprintf(stderr, "unknown sonde type '%s'\n", s.c_str());
+	exit(2);
+}
+const char *name_of(int type)
+{
+	for (size_t i = 0; i < sizeof(kNames) / sizeof(*kNames); i++)
+		if (kTypes[i] == type) return kNames[i];
+	return "?";
+}
+
+/* SD/decode.c:278-376: fold one fragment into the channel's accumulated record; true if it carried data */
+bool append_data_point(SondeData &printable, const SondeData &d)
+{
+	if (!d.fields) return false;
+	if (d.fields & DATA_PTU) {
+		printable.fields |= DATA_PTU;
+		printable.temp = d.temp; printable.rh = d.rh; printable.pressure = d.pressure;
+		printable.calib_percent = d.calib_percent;
+	}
+	if (d.fields & DATA_TIME) { printable.fields |= DATA_TIME; printable.time = d.time; }
+	if (d.fields & DATA_POS) { printable.fields |= DATA_POS; printable.lat = d.lat; printable.lon = d.lon; printable.alt = d.alt; }
+	if (d.fields & DATA_SPEED) {
+		printable.fields |= DATA_SPEED;
+		printable.speed = d.speed; printable.heading = d.heading; printable.climb = d.climb;
+	}
+	if (d.fields & DATA_SERIAL) {
+		printable.fields |= DATA_SERIAL;
+		strncpy(printable.serial, d.serial, sizeof(printable.serial) - 1);
+		printable.serial[sizeof(printable.serial) - 1] = 0;
+	}
+	if (d.fields & DATA_OZONE) { printable.fields |= DATA_OZONE; printable.o3_mpa = d.o3_mpa; }
+	if (d.fields & DATA_SHUTDOWN) { printable.fields |= DATA_SHUTDOWN; printable.shutdown = d.shutdown; }
+	if (d.fields & DATA_SEQ) { printable.fields |= DATA_SEQ; printable.seq = d.seq; }
+	if (!(printable.pressure > 0)) printable.pressure = radiosonde::tl::altitude_to_pressure(printable.alt);
+	return true;
+}
+
+/* SD/io/csv.c:26-60 */
+void csv_add_point(FILE *f, const SondeData &d)
+{
+	char timestr[sizeof("YYYY-MM-DDThh:mm:ssZ") + 1];
+	if (d.fields & DATA_TIME) {
+		strftime(timestr, sizeof(timestr), "%Y-%m-%dT%H:%M:%SZ", gmtime(&d.time));
+		fprintf(f, "%s,", timestr);
+	} else {
+		fprintf(f, ",");
+	}
+	if (d.fields & DATA_PTU) fprintf(f, "%f,%f,%f,", d.temp, d.rh, d.pressure); else fprintf(f, ",,,");
+	if (d.fields & DATA_POS) fprintf(f, "%f,%f,%f,", d.lat, d.lon, d.alt); else fprintf(f, ",,,");
+	if (d.fields & DATA_SPEED) fprintf(f, "%f,%f,%f,", d.speed, d.heading, d.climb); else fprintf(f, ",,,");
+	if (d.fields & DATA_OZONE) fprintf(f, "O3=%fmPa", d.o3_mpa);
+	fprintf(f, "\n");
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+	std::string type_arg = "auto", csv_prefix;
+	size_t buflen = 1024;
+	bool iq = false, quiet = false;
+	std::vector<std::string> files;
+	for (int i = 1; i < argc; i++) {
+		const std::string a = argv[i];
+		auto need = [&](const char *what) { if (i + 1 >= argc) { fprintf(stderr, "%s needs an argument\n", what); exit(2); } return std::string(argv[++i]); };
+		if (a == "-t" || a == "--type") type_arg = need("-t");
+		else if (a == "-b" || a == "--buflen") buflen = strtoul(need("-b").c_str(), nullptr, 10);
+		else if (a == "-c" || a == "--csv") csv_prefix = need("-c");
+		else if (a == "-i" || a == "--iq") iq = true;
+		else if (a == "-q" || a == "--quiet") quiet = true;
+		else if (a == "-h" || a == "--help") { printf("usage: %s [-t type[,type...]] [-b buflen] [-c csv_prefix] [-i] [-q] file...\n", argv[0]); return 0; }
+		else files.push_back(a);
+	}
+	const size_t C = files.size();
+	if (!C || !buflen) { fprintf(stderr, "no input files\n"); return 2; }
+	std::vector<int32_t> types;
+	{
+		size_t pos = 0;
+		while (pos <= type_arg.size()) {
+			const size_t c = type_arg.find(',', pos);
+			types.push_back(type_of(type_arg.substr(pos, c == std::string::npos ? std::string::npos : c - pos)));
+			if (c == std::string::npos) break;
+			pos = c + 1;
+		}
+		if (types.size() == 1) types.assign(C, types[0]);
+		if (types.size() != C) { fprintf(stderr, "%zu types for %zu files\n", types.size(), C); return 2; }
+	}
+
+	const size_t esz = iq ? 8 : 4;
+	std::vector<FILE *> in(C, nullptr);
+	for (size_t c = 0; c < C; c++)
+		if (!(in[c] = fopen(files[c].c_str(), "rb"))) { fprintf(stderr, "cannot open %s\n", files[c].c_str()); return 2; }
+
+	sonde_b200_config cfg = {};
+	cfg.n_channels = (int32_t)C;
+	cfg.samplerate = 48000;
+	cfg.max_chunk_len = (int32_t)buflen;
+	cfg.types = types.data();
+	sonde_b200 *h = nullptr;
+	const int rc = sonde_b200_create(&h, &cfg);
+	if (rc != SONDE_OK) {
+		printf("NOGPU sonde_b200_create failed (%d): the CUDA path is required, there is no CPU fallback\n", rc);
+		return 3;
+	}
+	const int max_frames = sonde_b200_max_frames(h);
+	std::vector<sonde_frame_rec> recs(C * (size_t)max_frames);
+	std::vector<int32_t> counts(C), locked(types);
+	std::vector<radiosonde::Telemetry> tele;
+	std::vector<SondeData> printable(C), fragment(C);
+	std::vector<FILE *> csv(C, nullptr);
+	std::vector<long> n_frames(C, 0), n_ok(C, 0), n_points(C, 0);
+	for (size_t c = 0; c < C; c++) {
+		tele.emplace_back(types[c] == SONDE_AUTO ? SONDE_RS41 : types[c]);
+		memset(&printable[c], 0, sizeof(SondeData));
+		memset(&fragment[c], 0, sizeof(SondeData));
+		if (!csv_prefix.empty()) {
+			const std::string name = csv_prefix + std::to_string(c) + ".csv";
+			if (!(csv[c] = fopen(name.c_str(), "wb"))) { fprintf(stderr, "cannot create %s\n", name.c_str()); return 2; }
+			fprintf(csv[c], "Time,Temperature,RH,Pressure,Latitude,Longitude,Altitude,Speed,Heading,Climb,XDATA\n");
+		}
+	}
+	/* two pinned staging buffers: buffer k+1 is read and submitted while buffer k decodes (sonde_b200.h, fetch()) */
+	char *stage[2] = {(char *)sonde_b200_host_alloc(C * buflen * esz), (char *)sonde_b200_host_alloc(C * buflen * esz)};
+	if (!stage[0] || !stage[1]) { fprintf(stderr, "pinned allocation failed\n"); return 2; }
+
+	long n_submitted = 0, n_delivered = 0;
+	std::vector<long> last_call(C, -1);          /* the reference stops decoding a recording at its end: records that
+	                                                later (all-zero) buffers complete for it are not reported */
+	auto submit = [&](int slot) -> bool {
+		/* The reference's loop (SD/main.c:328-333, raw_read_wrapper :400-405): a read that returns at least one sample
+		 * is followed by decode() over the WHOLE 1024-sample buffer, so a short last read is decoded together with the
+		 * tail the previous read left in the buffer; a read of zero samples ends the recording.  Here a recording that
+		 * has ended contributes exact zeros (which the AGC passes through untouched, agc.c:23) until all have ended. */
+		bool any = false;
+		for (size_t c = 0; c < C; c++) {
+			char *row = stage[slot] + c * buflen * esz;
+			const size_t got = in[c] ? fread(row, esz, buflen, in[c]) : 0;
+			if (got == 0) {
+				memset(row, 0, buflen * esz);
+				if (in[c]) { fclose(in[c]); in[c] = nullptr; }
+			} else {
+				any = true;
+				last_call[c] = n_submitted;          /* this call still carries samples of recording c */
+				if (got < buflen) {
+					if (n_submitted) memcpy(row + got * esz, stage[slot ^ 1] + c * buflen * esz + got * esz, (buflen - got) * esz);
+					else memset(row + got * esz, 0, (buflen - got) * esz);
+				}
+			}
+		}
+		if (!any) return false;
+		const int r = iq ? sonde_b200_process_iq(h, (const float *)stage[slot], buflen) : sonde_b200_process_fm(h, (const float *)stage[slot], buflen);
+		if (r != SONDE_OK) { fprintf(stderr, "sonde_b200: %s\n", sonde_b200_last_error(h)); exit(1); }
+		n_submitted++;
+		return true;
+	};
+	auto deliver = [&]() {
+		if (sonde_b200_fetch(h, recs.data(), counts.data()) != SONDE_OK) { fprintf(stderr, "sonde_b200: %s\n", sonde_b200_last_error(h)); exit(1); }
+		sonde_b200_detected_types(h, locked.data());
+		const long call = n_delivered++;
+		for (size_t c = 0; c < C; c++) {
+			if (call > last_call[c]) continue;
+			for (int k = 0; k < counts[c]; k++) {
+				const sonde_frame_rec &r = recs[c * max_frames + k];
+				if (types[c] == SONDE_AUTO && tele[c].type() != r.type) {
+					/* the channel locked: SD/decode.c:242-251 set_active_decoder() clears the accumulated record */
+					tele[c].reset(r.type);
+					memset(&printable[c], 0, sizeof(SondeData));
+				}
+				n_frames[c]++;
+				n_ok[c] += r.ok;
+				/* The reference's decode() keeps its SondeData in one stack slot that every call reuses without clearing
+				 * it (SD/decode.c:128), and decoders such as the DFM's write only the members a subframe carries: a
+				 * fragment therefore shows the values the previous ones left behind.  One persistent fragment per
+				 * channel reproduces that (it starts zeroed; the reference's first fragments show stack garbage in
+				 * members no subframe has delivered yet). */
+				SondeData &frag = fragment[c];
+				tele[c].parse(r, &frag);
+				if (!append_data_point(printable[c], frag)) continue;
+				n_points[c]++;
+				const SondeData &d = printable[c];
+				if (!quiet) printf("%zu %s %d %.5f %.5f %.1f %.1f\n", c, d.serial, d.seq, d.lat, d.lon, d.alt, d.temp);
+				if (csv[c]) csv_add_point(csv[c], d);
+			}
+		}
+	};
+	int slot = 0, in_flight = 0;
+	while (submit(slot)) {
+		if (in_flight) deliver();
+		in_flight = 1;
+		slot ^= 1;
+	}
+	if (in_flight) deliver();
+	for (size_t c = 0; c < C; c++) {
+		printf("CH %zu type=%s frames=%ld ok=%ld points=%ld\n", c, name_of(locked[c]), n_frames[c], n_ok[c], n_points[c]);
+		if (csv[c]) fclose(csv[c]);
+		if (in[c]) fclose(in[c]);
+	}
+	sonde_b200_host_free(stage[0]);
+	sonde_b200_host_free(stage[1]);
+	sonde_b200_destroy(h);
+	return 0;
+}

@@ -214,6 +214,7 @@ inline float meteomodem_ntc(float beta, unsigned adc_val, unsigned range)
 class Telemetry {
 public:
 	explicit Telemetry(int type = SONDE_RS41) { reset(type); }
+	int type() const { return m_type; }
 
 	void reset(int type)
 	{
