@@ -100,6 +100,7 @@ struct frame_params {
 	int32_t        chunk_index;
 	int32_t       *counts;        /* [C][2] frames / ok of this call                 */
 	const int32_t *active;        /* [C] 0 = channel switched off (AUTO loser)        */
+	int32_t        skip_warps;    /* idle warps in front of the working ones of each CTA (SMSP placement, frame.cu) */
 };
 
 

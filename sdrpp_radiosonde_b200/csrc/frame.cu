@@ -38,6 +38,7 @@ extern "C" cudaError_t sonde_upload_modems_frame(const sonde_modem *m)
 namespace {
 
 constexpr int WARPS_PER_CTA = 2;    /* 64 threads x 128 registers: small enough to sit beside a K1 CTA (768 x 72) on the same SM */
+constexpr int MAX_SKIP_WARPS = 2;   /* optional idle warps 0..1: the working warps then sit on SMSP 2 and 3 (warp id % 4) */
 constexpr int WIN_WORDS = 264;            /* >= 2 * 4144 / 32 + 4 : the framer buffer holds up to 2F bits */
 constexpr int WORK_BYTES = 1024;
 constexpr unsigned FULL = 0xffffffffu;
@@ -640,13 +641,14 @@ __device__ void deframe_c50(warp_smem &ws, int lane, int &status)
 
 /* ---- the framer walk ------------------------------------------------------------------------ */
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__((WARPS_PER_CTA + MAX_SKIP_WARPS) * 32)
 frame_kernel(const frame_params p)
 {
 	__shared__ cta_smem sm;
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5) - p.skip_warps;
 	load_gf_tables(sm.gf, threadIdx.x, blockDim.x);
 	__syncthreads();
+	if (wid < 0) return;
 
 	const int ch = blockIdx.x * WARPS_PER_CTA + wid;
 	if (ch >= p.n_channels) return;
@@ -863,6 +865,7 @@ extern "C" cudaError_t sonde_upload_gf_tables(void)
 extern "C" cudaError_t sonde_launch_frames(const frame_params *p, cudaStream_t stream)
 {
 	const int ctas = (p->n_channels + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-	frame_kernel<<<ctas, WARPS_PER_CTA * 32, 0, stream>>>(*p);
+	if (p->skip_warps < 0 || p->skip_warps > MAX_SKIP_WARPS) return cudaErrorInvalidValue;
+	frame_kernel<<<ctas, (WARPS_PER_CTA + p->skip_warps) * 32, 0, stream>>>(*p);
 	return cudaGetLastError();
 }

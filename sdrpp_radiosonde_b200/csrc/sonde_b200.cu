@@ -78,7 +78,7 @@ struct sonde_b200 {
 	cudaEvent_t ev_demod[2] = {nullptr, nullptr}, evf[2] = {nullptr, nullptr};
 	uint64_t *d_nbits[2] = {nullptr, nullptr};
 	cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-	long n_issued = 0, n_fetched = 0;
+	long n_issued = 0, n_fetched = 0, n_truncated = 0;
 	float *d_soft = nullptr;
 	int max_frames = 0, soft_stride = 0, bits_stride = 0;
 	bool rate_registered = false;
@@ -274,13 +274,24 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	if (sonde_upload_modems_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_afsk_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_gf_tables() != cudaSuccess) return bail(SONDE_ERR_CUDA);
-	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	/* Stream priorities: frame(i) (fstream) and demod(i+1) (stream) become runnable at the same moment, when demod(i)
+	 * retires.  The demodulator is the critical path and needs one large CTA on every SM; if the framer's small CTAs are
+	 * placed first, several of them land on each SM and the demodulator's CTA has to wait until they have finished
+	 * (measured: the step cost demod + frame although the two overlap).  With the demodulator streams at the highest
+	 * priority its CTAs are placed first and the framer fills what is left beside them. */
+	int prio_lo = 0, prio_hi = 0;
+	if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	{
+		const char *e = getenv("SONDE_STREAM_PRIO");              /* experiment switch: 0 = all streams equal */
+		if (e && atoi(e) == 0) prio_lo = prio_hi = 0;
+	}
+	if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&h->dstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
-	if (cudaStreamCreateWithFlags(&h->fstream, cudaStreamNonBlocking) != cudaSuccess) return bail(SONDE_ERR_CUDA);
+	if (cudaStreamCreateWithPriority(&h->fstream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	for (int v = 0; v < 4; v++)
-		if (cudaStreamCreateWithFlags(&h->vstream[v], cudaStreamNonBlocking) != cudaSuccess ||
+		if (cudaStreamCreateWithPriority(&h->vstream[v], cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
 		    cudaEventCreateWithFlags(&h->ev_join[v], cudaEventDisableTiming) != cudaSuccess)
 			return bail(SONDE_ERR_CUDA);
 	for (int b = 0; b < 2; b++)
@@ -310,7 +321,10 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 		const sonde_modem &m = h->modems[t];
 		const int nb = max_new_bits(m, cfg->max_chunk_len);
 		bits_max = std::max(bits_max, nb);
-		frames_max = std::max(frames_max, nb / m.frame_bits + 2);
+		/* a window normally consumes a whole frame; iMet-4's framer_adjust (imet4.c:91-117) advances by as little as one
+		 * 5-byte subframe of 10-bit characters, so a garbled stream can yield a record every ~50 bits */
+		const int min_advance = (t == SONDE_IMET4) ? 50 : m.frame_bits;
+		frames_max = std::max(frames_max, nb / min_advance + 2);
 		/* two calls are in flight on the ring: frame(i) on fstream still reads while demod(i+1) appends (only
 		 * demod(i+2) waits for frame(i), run_chunk), so the span is the framer's 2F + S backlog plus TWO calls' bits */
 		ring_need = std::max(ring_need, (uint32_t)((2 * m.frame_bits + m.sync_len + 2 * nb) / 8 + 64));
@@ -551,7 +565,8 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	 * variants (sonde mixes) forks them onto their own streams so that they share the GPU. */
 	int n_variants = 0;
 	for (int v = 0; v < 4; v++) n_variants += h->groups_v[v] > 0;
-	const bool fork = n_variants > 1;
+	static const bool no_fork = getenv("SONDE_NO_FORK") != nullptr;                /* experiment switch */
+	const bool fork = n_variants > 1 && !no_fork;
 	if (fork) CK(cudaEventRecord(h->ev_fork, h->stream));
 	int base = 0;
 	for (int v = 0; v < 4; v++) {
@@ -591,7 +606,13 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	fp.counts = h->d_counts[par];
 	fp.active = h->d_active;
 	static const bool frame_serial = getenv("SONDE_FRAME_SERIAL") != nullptr;      /* experiment switch */
-	cudaStream_t fs_ = frame_serial ? h->stream : h->fstream;
+	static const int frame_skip = getenv("SONDE_FRAME_SKIP") ? atoi(getenv("SONDE_FRAME_SKIP")) : 0;
+	fp.skip_warps = frame_skip;
+	/* Several kernel variants forked over the SMs: the framer then runs in order behind them.  Measured (tools/timeline.py,
+	 * BASELINE config 5): beside the forked demodulators of the next call its CTAs are placed first and hold back theirs,
+	 * 2.16 ms per step against 1.74 ms in order; with one variant the two orders cost the same (K1 is latency-bound and
+	 * loses to the framer's warps what the overlap gains). */
+	cudaStream_t fs_ = (frame_serial || fork) ? h->stream : h->fstream;
 	CK(cudaStreamWaitEvent(fs_, h->ev_demod[par], 0));
 	CK(cudaEventRecord(h->evf[0], fs_));
 	CK(sonde_launch_frames(&fp, fs_));
@@ -902,8 +923,15 @@ int sonde_b200_fetch(sonde_b200 *h, sonde_frame_rec *recs, int32_t *counts)
 	int rc = fetch_counts_of(h, par, counts, nullptr);
 	if (rc) return rc;
 	const int V = h->cfg.n_channels;
-	for (int v = 0; v < V; v++)
-		if (h->h_counts[2 * v] > h->max_frames) return fail(h, SONDE_ERR_STATE, "frame record overflow");
+	/* The framer walks every window but only the first max_frames records of a channel are stored (frame.cu).  A channel
+	 * that produced more (cannot happen for a well-formed stream, see max_frames) is reported truncated: one channel's
+	 * garbage must not fail the batch. */
+	for (int c = 0; c < h->n_user; c++)
+		if (counts[c] > h->max_frames) {
+			counts[c] = h->max_frames;
+			h->n_truncated++;
+			h->err = "frame records of a channel truncated to max_frames";
+		}
 	if (!h->has_auto) {
 		CK(cudaMemcpyAsync(recs, h->d_recs[par], (size_t)V * h->max_frames * sizeof(sonde_frame_rec),
 		                   cudaMemcpyDeviceToHost, h->dstream));
