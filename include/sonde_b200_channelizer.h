@@ -41,7 +41,7 @@ typedef struct sonde_chan sonde_chan;   /* opaque */
 
 typedef struct {
 	int32_t n_channels;        /* C                                                                     */
-	int32_t decim;             /* D = fs_in / fs_out >= 2.  Multiples of 4 run at full speed; even D costs 2x, odd D 4x
+	int32_t decim;             /* D = fs_in / fs_out >= 2 (M of L/M with sonde_chan_options.interp).  Multiples of 4 run at full speed; even D costs 2x, odd D 4x
 	                              the tensor work (zero slots keep the TMA window pitch 16-byte aligned)             */
 	int32_t fs_out;            /* output rate per channel, 48000                                        */
 	int32_t taps_per_phase;    /* prototype low-pass length K = taps_per_phase * D; 0 -> 8              */
@@ -51,8 +51,34 @@ typedef struct {
 	const double *freq_hz;     /* [C] channel centre offsets from the wideband centre, |f| < fs_in / 2 */
 } sonde_chan_config;
 
+/* Optional settings of sonde_chan_create_ex (all zero = sonde_chan_create):
+ *
+ *  precision   SONDE_CHAN_BF16: samples and weights are rounded to bfloat16 (8 significant bits, a noise floor ~57 dB
+ *              below the signal), one tensor pass.  SONDE_CHAN_SPLIT_BF16: every operand is carried as hi + lo bfloat16
+ *              (16 significant bits) and the GEMM runs three passes into the same fp32 accumulator
+ *              (hi*hi + hi*lo + lo*hi): within ~1e-5 rms of the exact formula, i.e. the fp32 grade of the SDR++ chain
+ *              it replaces, for 3x the tensor work.
+ *  interp      L of a rational resampler, fs_out = fs_in * L / decim (1 <= L <= 16, gcd(L, decim) = 1) — sources whose
+ *              rate is not an integer multiple of 48 kS/s (src/main.cpp:60 uses a RationalResampler for the same
+ *              reason): 2.048 MS/s -> L/M = 3/128, 2.5 MS/s -> 12/625, 10 MS/s -> 3/625.  The prototype g then has
+ *              L * K taps at the rate L * fs_in and
+ *                  y_c[m] = sum_n g[m*decim + decim-1 - n*L] * x[n] * exp(-j w_c n)
+ *              (L = 1 is the formula at the top).  A call with n_in input samples yields n_in / decim * L outputs.
+ *  cutoff_hz   [C] per-channel -6 dB point of the channel filter, e.g. half the VFO bandwidth the plugin uses for the
+ *              channel's sonde type (src/main.hpp:45-51: 10 / 15 / 20 / 50 / 20 / 20 / 20 kHz); NULL or a non-positive
+ *              entry -> sonde_chan_config.cutoff_hz. */
+#define SONDE_CHAN_BF16        0
+#define SONDE_CHAN_SPLIT_BF16  1
+typedef struct {
+	int32_t precision;
+	int32_t interp;
+	const float *cutoff_hz;
+	int32_t reserved[4];
+} sonde_chan_options;
+
 /* Errors: the SONDE_ERR_* codes of sonde_b200.h. */
 SONDE_API int  sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg);
+SONDE_API int  sonde_chan_create_ex(sonde_chan **out, const sonde_chan_config *cfg, const sonde_chan_options *opt);
 SONDE_API void sonde_chan_destroy(sonde_chan *h);
 
 /* One chunk of wideband IQ: n_in complex samples (a multiple of D; at least K - D except for the very first
@@ -77,8 +103,9 @@ SONDE_API int  sonde_chan_process_u8(sonde_chan *h, const uint8_t *wide_iq /* ho
 
 /* Parameters the oracle needs (they are inputs of the algorithm, not results): the K prototype taps, the
  * quantised oscillator steps (w_c = 2 pi step_c / 2^32), K itself. */
-SONDE_API int  sonde_chan_num_taps(const sonde_chan *h);
-SONDE_API int  sonde_chan_taps(const sonde_chan *h, double *taps, int cap);
+SONDE_API int  sonde_chan_num_taps(const sonde_chan *h);                       /* L * K */
+SONDE_API int  sonde_chan_taps(const sonde_chan *h, double *taps, int cap);   /* channel 0's prototype */
+SONDE_API int  sonde_chan_taps_of(const sonde_chan *h, int channel, double *taps, int cap);
 SONDE_API int  sonde_chan_steps(const sonde_chan *h, uint32_t *steps, int cap);
 /* duration of the last GEMM kernel in ms (CUDA events on `stream`), < 0 if none */
 SONDE_API int  sonde_chan_last_kernel_ms(sonde_chan *h, float *gemm_ms);

@@ -27,12 +27,22 @@ def to_bf16(a):
     return r.astype(np.uint32).view(np.float32)
 
 
-def channelize(x, taps, steps, decim, n_start=0, history=None, bf16=False):
+def channelize(x, taps, steps, decim, n_start=0, history=None, bf16=False, interp=1, taps_per_channel=None):
     """x: complex wideband chunk (len multiple of decim), history: the samples before it (zeros if None).
 
-    Returns y[C][len(x) // decim] complex128."""
+    General form (include/sonde_b200_channelizer.h, sonde_chan_options.interp = L, decim = M):
+
+        y_c[m] = sum_n g[m M + M-1 - n L] x[n] exp(-j w_c n)
+
+    with g the L*K-tap prototype at the rate L fs_in (`taps`; `taps_per_channel[c]` overrides it per channel).  For
+    output m = L q + r that is branch r of the polyphase filter: h_r[k] = g[phi_r + k L] over the window ending at the
+    input sample n0 = q M + e_r,  e_r = (r M + M - 1) div L,  phi_r = (r M + M - 1) mod L.  L = 1: h = g, n0 = mM + M-1.
+    Returns y[C][len(x) // decim * interp] complex128."""
     x = np.asarray(x)
-    K, D = len(taps), int(decim)
+    M_, L = int(decim), int(interp)
+    Kg = len(taps)
+    K = Kg // L
+    assert K * L == Kg
     hist = np.zeros(K, dtype=np.complex128) if history is None else np.asarray(history, dtype=np.complex128)[-K:]
     if len(hist) < K:
         hist = np.concatenate([np.zeros(K - len(hist), dtype=np.complex128), hist])
@@ -41,20 +51,24 @@ def channelize(x, taps, steps, decim, n_start=0, history=None, bf16=False):
         xr, xi = to_bf16(xr), to_bf16(xi)
         hist = to_bf16(np.real(hist).astype(np.float32)) + 1j * to_bf16(np.imag(hist).astype(np.float32))
     full = np.concatenate([hist, xr.astype(np.float64) + 1j * xi.astype(np.float64)])
-    M = len(x) // D
-    # windows[m][k] = x[mD + D-1 - k]  (index into `full` shifted by K)
-    idx = (np.arange(M)[:, None] * D + D - 1 + K) - np.arange(K)[None, :]
-    win = full[idx]                                                   # [M][K]
+    Q = len(x) // M_
     k = np.arange(K, dtype=np.uint64)
-    out = np.empty((len(steps), M), dtype=np.complex128)
-    for c, st in enumerate(np.asarray(steps, dtype=np.uint64)):
-        ph = (st * k) & 0xFFFFFFFF
-        a = 2.0 * np.pi * ph.astype(np.int64).astype(np.uint32).view(np.int32).astype(np.float64) / 4294967296.0
-        w = np.asarray(taps, dtype=np.float64) * np.exp(1j * a)       # h[k] e^{+j w k}
-        if bf16:
-            w = to_bf16(np.real(w).astype(np.float32)).astype(np.float64) + 1j * to_bf16(np.imag(w).astype(np.float32)).astype(np.float64)
-        n0 = (np.uint64(n_start) + np.arange(M, dtype=np.uint64) * np.uint64(D) + np.uint64(D - 1))
-        p0 = (st * n0) & 0xFFFFFFFF
-        a0 = 2.0 * np.pi * p0.astype(np.uint32).view(np.int32).astype(np.float64) / 4294967296.0
-        out[c] = (win @ w) * np.exp(-1j * a0)
+    out = np.empty((len(steps), Q * L), dtype=np.complex128)
+    for r in range(L):
+        T = r * M_ + M_ - 1
+        e, phi = T // L, T % L
+        # windows[q][k] = x[qM + e - k]  (index into `full` shifted by K)
+        idx = (np.arange(Q)[:, None] * M_ + e + K) - np.arange(K)[None, :]
+        win = full[idx]                                               # [Q][K]
+        n0 = (np.uint64(n_start) + np.arange(Q, dtype=np.uint64) * np.uint64(M_) + np.uint64(e))
+        for c, st in enumerate(np.asarray(steps, dtype=np.uint64)):
+            g = np.asarray(taps if taps_per_channel is None else taps_per_channel[c], dtype=np.float64)
+            ph = (st * k) & 0xFFFFFFFF
+            a = 2.0 * np.pi * ph.astype(np.int64).astype(np.uint32).view(np.int32).astype(np.float64) / 4294967296.0
+            w = g[phi::L] * np.exp(1j * a)                            # h_r[k] e^{+j w k}
+            if bf16:
+                w = to_bf16(np.real(w).astype(np.float32)).astype(np.float64) + 1j * to_bf16(np.imag(w).astype(np.float32)).astype(np.float64)
+            p0 = (st * n0) & 0xFFFFFFFF
+            a0 = 2.0 * np.pi * p0.astype(np.uint32).view(np.int32).astype(np.float64) / 4294967296.0
+            out[c, r::L] = (win @ w) * np.exp(-1j * a0)
     return out

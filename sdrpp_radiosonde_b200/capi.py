@@ -334,7 +334,7 @@ class BatchDecoder:
 # ------------------------------------------------------------------------------------------------
 # wideband channelizer (include/sonde_b200_channelizer.h)
 CHAN_EXPORTS = [
-    "sonde_chan_create", "sonde_chan_destroy", "sonde_chan_process_c64", "sonde_chan_process_c64_device",
+    "sonde_chan_create", "sonde_chan_create_ex", "sonde_chan_taps_of", "sonde_chan_destroy", "sonde_chan_process_c64", "sonde_chan_process_c64_device",
     "sonde_chan_process_s16", "sonde_chan_process_u8", "sonde_chan_num_taps", "sonde_chan_taps", "sonde_chan_steps",
     "sonde_chan_last_kernel_ms", "sonde_chan_last_error",
 ]
@@ -347,6 +347,12 @@ class ChanConfig(ctypes.Structure):
                 ("device", ctypes.c_int32), ("freq_hz", ctypes.POINTER(ctypes.c_double))]
 
 
+class ChanOptions(ctypes.Structure):
+    """sonde_chan_options"""
+    _fields_ = [("precision", ctypes.c_int32), ("interp", ctypes.c_int32), ("cutoff_hz", ctypes.POINTER(ctypes.c_float)),
+                ("reserved", ctypes.c_int32 * 4)]
+
+
 def _chan_lib():
     lib = load()
     if getattr(lib, "_chan_ready", False):
@@ -355,6 +361,8 @@ def _chan_lib():
     pvp, psz = ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)
     sig = {
         "sonde_chan_create": (ctypes.c_int, [pvp, ctypes.POINTER(ChanConfig)]),
+        "sonde_chan_create_ex": (ctypes.c_int, [pvp, ctypes.POINTER(ChanConfig), ctypes.POINTER(ChanOptions)]),
+        "sonde_chan_taps_of": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int]),
         "sonde_chan_destroy": (None, [vp]),
         "sonde_chan_process_c64": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
         "sonde_chan_process_c64_device": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
@@ -391,16 +399,22 @@ class Channelizer:
     process_*() return (device pointer, row stride in samples, samples per channel); feed them to
     BatchDecoder.process_iq_device().  `stream` is a raw cudaStream_t (int), e.g. BatchDecoder.stream."""
 
-    def __init__(self, freq_hz, decim, max_in_len, fs_out=48000, taps_per_phase=0, cutoff_hz=0.0, device=0):
+    def __init__(self, freq_hz, decim, max_in_len, fs_out=48000, taps_per_phase=0, cutoff_hz=0.0, device=0,
+                 precision=0, interp=1, cutoffs=None):
+        """precision: 0 = bf16 operands, 1 = split bf16 (hi + lo, three tensor passes); interp: L of the rational
+        resampler fs_out = fs_in * L / decim; cutoffs: per-channel -6 dB points in Hz (sonde_chan_options)"""
         self.lib = _chan_lib()
         self.freq = np.ascontiguousarray(freq_hz, dtype=np.float64)
-        self.C, self.D = int(self.freq.size), int(decim)
+        self.C, self.D, self.L = int(self.freq.size), int(decim), int(interp)
         cfg = ChanConfig(self.C, self.D, fs_out, taps_per_phase, cutoff_hz, int(max_in_len), device,
                          self.freq.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        self._cut = None if cutoffs is None else np.ascontiguousarray(cutoffs, dtype=np.float32)
+        opt = ChanOptions(int(precision), self.L,
+                          None if self._cut is None else self._cut.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
         h = ctypes.c_void_p()
-        rc = self.lib.sonde_chan_create(ctypes.byref(h), ctypes.byref(cfg))
+        rc = self.lib.sonde_chan_create_ex(ctypes.byref(h), ctypes.byref(cfg), ctypes.byref(opt))
         if rc != SONDE_OK:
-            raise SondeError(rc, "sonde_chan_create")
+            raise SondeError(rc, "sonde_chan_create_ex")
         self.h = h
         self.K = self.lib.sonde_chan_num_taps(h)
         self.taps = np.zeros(self.K, dtype=np.float64)
@@ -415,7 +429,12 @@ class Channelizer:
     def _run(self, fn, ptr, n_in, stream, *extra):
         out, stride = ctypes.c_void_p(), ctypes.c_size_t()
         self._ck(fn(self.h, ptr, n_in, *extra, ctypes.c_void_p(stream or 0), ctypes.byref(out), ctypes.byref(stride)), fn.__name__)
-        return out.value, int(stride.value), n_in // self.D
+        return out.value, int(stride.value), n_in // self.D * self.L
+
+    def taps_of(self, channel):
+        t = np.zeros(self.K, dtype=np.float64)
+        self.lib.sonde_chan_taps_of(self.h, int(channel), t.ctypes.data, self.K)
+        return t
 
     def process_c64(self, wide: np.ndarray, stream=0):
         wide = np.ascontiguousarray(wide, dtype=np.complex64)

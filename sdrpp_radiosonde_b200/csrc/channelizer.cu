@@ -25,6 +25,16 @@
  *                 (lanes = consecutive m: 256-byte coalesced rows)
  *
  * Roofline: 2 * M * 2C * 2Kp flops per chunk on the tensor cores; 8 B per output sample written to HBM.
+ *
+ * Options (sonde_chan_create_ex):
+ *   precision 1  "split bf16": every operand is the sum of two bf16 numbers (hi + lo, 16 significant bits); the GEMM
+ *                runs three passes into the same TMEM accumulator (x_hi w_hi + x_hi w_lo + x_lo w_hi, the dropped
+ *                x_lo w_lo term is 2^-18 relative) — fp32-grade results for 3x the tensor work.
+ *   interp L     rational resampling fs_out = fs_in L / M.  Output m = L q + r is branch r of a polyphase filter: the
+ *                same overlapping-window GEMM with the window shifted by (e_r - e_0) samples (a TMA coordinate) and its
+ *                own weight rows, y[Lq + r] = sum_k g[phi_r + k L] x[qM + e_r - k] e^{-j w (qM + e_r - k)},
+ *                e_r = (rM + M - 1) div L, phi_r = (rM + M - 1) mod L.
+ *   cutoff_hz[c] per-channel prototype (the per-type VFO bandwidths of src/main.hpp:45-51) — only the weight rows differ.
  */
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -49,15 +59,38 @@ constexpr int CHUNKS_PER_WARP = (BN / 32) / (N_EPI_WARPS / 4);     /* 32-column 
 constexpr int NTHREADS = (FIRST_EPI_WARP + N_EPI_WARPS) * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
+constexpr int MAX_INTERP = 16;
+
 struct gemm_params {
 	float2 *out;               /* [C][out_stride] */
 	size_t out_stride;
 	const uint32_t *step;      /* [C] */
 	int n_channels;
-	int m_out;                 /* output samples this call */
-	int n_mt, n_nt, n_kb;
-	int decim;
-	uint32_t n0_base;          /* low 32 bits of (absolute index of the chunk's first input sample + D - 1) */
+	int m_rows;                /* output samples per polyphase branch this call (n_in / M) */
+	int n_mt, n_nt, n_kb;      /* n_kb: K blocks of one pass */
+	int npass;                 /* 1: bf16 operands; 3: split bf16 (hi hi + hi lo + lo hi) */
+	int np;                    /* rows of one weight matrix (padded 2C) */
+	int decim, interp;
+	uint32_t n0_base;          /* low 32 bits of the absolute index of the chunk's first input sample */
+	int e_abs[MAX_INTERP];     /* branch r: newest input sample of output L q + r is q M + e_abs[r]          */
+	int e_rel[MAX_INTERP];     /* branch r: window shift in elements inside its sample-stream copy (a multiple of 8:
+	                              TMA box rows must start on 16-byte boundaries)                              */
+	int copy_of[MAX_INTERP];   /* branch r: which shifted copy of the sample stream it reads                   */
+};
+
+/* The window of polyphase branch r starts S (e_r - e_0) slots into a row; TMA needs that start 16-byte aligned
+ * (4 slots), so the sample stream is kept in up to four copies shifted by 0..3 slots and a branch reads the copy that
+ * makes its shift a multiple of four.  L = 1 needs one copy. */
+constexpr int MAX_COPIES = 4;
+struct chan_maps {
+	CUtensorMap a[MAX_COPIES];      /* samples (hi part)          */
+	CUtensorMap alo[MAX_COPIES];    /* split precision: residuals */
+};
+struct copy_ptrs {
+	__nv_bfloat162 *hi[MAX_COPIES];
+	__nv_bfloat162 *lo[MAX_COPIES];    /* nullptr without split precision */
+	int shift[MAX_COPIES];
+	int n;
 };
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,7 +160,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const gemm_params p)
+chan_gemm_kernel(const __grid_constant__ chan_maps maps, const __grid_constant__ CUtensorMap tmB, const gemm_params p)
 {
 	extern __shared__ unsigned char smem_raw[];
 	const uint32_t base = (s32(smem_raw) + 1023u) & ~1023u;            /* swizzle atoms need 1024-byte alignment */
@@ -140,7 +173,8 @@ chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int n_tiles = p.n_mt * p.n_nt;
+	const int tiles_per_branch = p.n_mt * p.n_nt;
+	const int n_tiles = tiles_per_branch * p.interp;
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < STAGES; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
@@ -163,14 +197,20 @@ chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			int stage = 0;
 			uint32_t phase = 0;
 			for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-				const int mt = tile / p.n_nt, nt = tile % p.n_nt;
-				for (int kb = 0; kb < p.n_kb; kb++) {
-					mbar_wait(empty(stage), phase ^ 1);
-					mbar_expect_tx(full(stage), STAGE_BYTES);
-					const uint32_t sa = base + stage * STAGE_BYTES;
-					tma_load_2d(sa, &tmA, kb * BK, mt * BM, full(stage));
-					tma_load_2d(sa + A_BYTES, &tmB, kb * BK, nt * BN, full(stage));
-					if (++stage == STAGES) { stage = 0; phase ^= 1; }
+				const int r = tile / tiles_per_branch, rem = tile - r * tiles_per_branch;
+				const int mt = rem / p.n_nt, nt = rem % p.n_nt;
+				for (int pass = 0; pass < p.npass; pass++) {
+					/* pass 0: x_hi w_hi, 1: x_hi w_lo, 2: x_lo w_hi; weight rows: [hi | lo][branch][np] */
+					const CUtensorMap *ma = (pass == 2) ? &maps.alo[p.copy_of[r]] : &maps.a[p.copy_of[r]];
+					const int brow = ((pass == 1 ? p.interp : 0) + r) * p.np + nt * BN;
+					for (int kb = 0; kb < p.n_kb; kb++) {
+						mbar_wait(empty(stage), phase ^ 1);
+						mbar_expect_tx(full(stage), STAGE_BYTES);
+						const uint32_t sa = base + stage * STAGE_BYTES;
+						tma_load_2d(sa, ma, kb * BK + p.e_rel[r], mt * BM, full(stage));
+						tma_load_2d(sa + A_BYTES, &tmB, kb * BK, brow, full(stage));
+						if (++stage == STAGES) { stage = 0; phase ^= 1; }
+					}
 				}
 			}
 		}
@@ -183,7 +223,8 @@ chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				mbar_wait(tempty(as), aphase ^ 1);              /* epilogue drained this accumulator */
 				tc_fence_after();
 				const uint32_t d = tmem_base + (uint32_t)as * BN;
-				for (int kb = 0; kb < p.n_kb; kb++) {
+				const int n_kb_all = p.n_kb * p.npass;
+				for (int kb = 0; kb < n_kb_all; kb++) {
 					mbar_wait(full(stage), phase);
 					tc_fence_after();
 					const uint32_t sa = base + stage * STAGE_BYTES;
@@ -206,11 +247,13 @@ chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		uint32_t aphase = 0;
 		const float k_ang = 3.14159265358979323846f / 2147483648.0f;
 		for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-			const int mt = tile / p.n_nt, nt = tile % p.n_nt;
+			const int r = tile / tiles_per_branch, rem = tile - r * tiles_per_branch;
+			const int mt = rem / p.n_nt, nt = rem % p.n_nt;
 			mbar_wait(tfull(as), aphase);
 			tc_fence_after();
-			const int m = mt * BM + q * 32 + lane;
-			const uint32_t n0 = p.n0_base + (uint32_t)m * (uint32_t)p.decim;
+			const int row = mt * BM + q * 32 + lane;                /* output sample L row + r of the call */
+			const int m = row * p.interp + r;
+			const uint32_t n0 = p.n0_base + (uint32_t)row * (uint32_t)p.decim + (uint32_t)p.e_abs[r];
 			const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * BN;
 #pragma unroll 1
 			for (int ck = part * CHUNKS_PER_WARP; ck < (part + 1) * CHUNKS_PER_WARP; ck++) {
@@ -220,7 +263,7 @@ chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
 				for (int i = 0; i < 16; i++) {
 					const int c = c0 + i;
-					if (c < p.n_channels && m < p.m_out) {
+					if (c < p.n_channels && row < p.m_rows) {
 						const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
 						const uint32_t ph = __ldg(p.step + c) * n0;             /* phase mod 2^32: exact */
 						float sn, cs;
@@ -247,27 +290,37 @@ chan_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 /* ---- input conversion into the persistent bf16 sample buffer -------------------------------- */
 /* `stride`: complex samples are stored every `stride`-th slot of the sample buffer (the slots in between stay zero),
  * which makes the window pitch a multiple of 16 bytes for decimations that are not multiples of 4 (see create). */
-__global__ void __launch_bounds__(256) to_bf16_c64_kernel(const float2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n, int stride)
+/* x -> bf16(x) and, for the split-precision mode (lo != nullptr), the residual bf16(x - hi), into every shifted copy */
+__device__ __forceinline__ void put_sample(const copy_ptrs &cp, size_t slot, float2 v)
+{
+	const __nv_bfloat162 h = __float22bfloat162_rn(v);
+	const float2 hf = __bfloat1622float2(h);
+	const __nv_bfloat162 l = __float22bfloat162_rn(make_float2(v.x - hf.x, v.y - hf.y));
+	for (int c = 0; c < cp.n; c++) {
+		cp.hi[c][slot - cp.shift[c]] = h;
+		if (cp.lo[c]) cp.lo[c][slot - cp.shift[c]] = l;
+	}
+}
+__global__ void __launch_bounds__(256) to_bf16_c64_kernel(const float2 *__restrict__ in, const copy_ptrs cp, size_t n, int stride)
 {
 	const size_t step = (size_t)gridDim.x * blockDim.x;
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
-		out[i * stride] = __float22bfloat162_rn(__ldg(in + i));
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) put_sample(cp, i * stride, __ldg(in + i));
 }
-__global__ void __launch_bounds__(256) to_bf16_s16_kernel(const short2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n, int stride, float scale)
+__global__ void __launch_bounds__(256) to_bf16_s16_kernel(const short2 *__restrict__ in, const copy_ptrs cp, size_t n, int stride, float scale)
 {
 	const size_t step = (size_t)gridDim.x * blockDim.x;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
 		const short2 a = __ldg(in + i);
-		out[i * stride] = __float22bfloat162_rn(make_float2((float)a.x * scale, (float)a.y * scale));
+		put_sample(cp, i * stride, make_float2((float)a.x * scale, (float)a.y * scale));
 	}
 }
-/* offset-binary 8-bit IQ (RTL-SDR): sample = (u8 - 127.5) / 128 */
-__global__ void __launch_bounds__(256) to_bf16_u8_kernel(const uchar2 *__restrict__ in, __nv_bfloat162 *__restrict__ out, size_t n, int stride)
+/* offset-binary 8-bit IQ (RTL-SDR): sample = (u8 - 127.5) / 128 (exact in bf16: the residual is zero) */
+__global__ void __launch_bounds__(256) to_bf16_u8_kernel(const uchar2 *__restrict__ in, const copy_ptrs cp, size_t n, int stride)
 {
 	const size_t step = (size_t)gridDim.x * blockDim.x;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
 		const uchar2 a = __ldg(in + i);
-		out[i * stride] = __float22bfloat162_rn(make_float2(((float)a.x - 127.5f) * 0.0078125f, ((float)a.y - 127.5f) * 0.0078125f));
+		put_sample(cp, i * stride, make_float2(((float)a.x - 127.5f) * 0.0078125f, ((float)a.y - 127.5f) * 0.0078125f));
 	}
 }
 
@@ -279,18 +332,29 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 struct sonde_chan {
 	sonde_chan_config cfg;
-	int C = 0, D = 0, S = 1, K = 0, Kp = 0, H = 0, Np = 0;   /* S: slot stride of the sample buffer; Kp, H in slots */
+	int C = 0, D = 0, L = 1, S = 1, K = 0, Kp = 0, H = 0, Np = 0;   /* D: decimation M; L: interpolation; S: slot stride of
+	                                                                 the sample buffer; K: taps per branch; Kp, H in slots */
+	int npass = 1;
 	int max_out = 0;
-	std::vector<double> taps;
+	int e_abs[MAX_INTERP] = {0}, e_rel[MAX_INTERP] = {0}, copy_of[MAX_INTERP] = {0};
+	int n_copies = 1, copy_shift[MAX_COPIES] = {0};
+	size_t nx = 0;                      /* slots per copy (without the 4 slots of front padding) */
+	std::vector<float> cutoffs;                 /* [C] */
+	std::vector<std::vector<double>> protos;    /* distinct prototypes g (L K taps at rate L fs_in) */
+	std::vector<int> proto_of;                  /* [C] index into protos */
 	std::vector<uint32_t> steps;
-	__nv_bfloat162 *d_x = nullptr;      /* [H + max_in] complex bf16: history then the chunk */
+	/* sample stream, complex bf16, [H history | chunk]; copy c is the stream shifted by copy_shift[c] slots (slot s of
+	 * the stream is d_x[c][4 + s - shift]); d_xlo: the residuals of the split-precision mode, same layout */
+	__nv_bfloat162 *d_x[MAX_COPIES] = {nullptr, nullptr, nullptr, nullptr};
+	__nv_bfloat162 *d_xlo[MAX_COPIES] = {nullptr, nullptr, nullptr, nullptr};
 	__nv_bfloat162 *d_tail = nullptr;   /* [H] */
-	__nv_bfloat16 *d_w = nullptr;       /* [Np][2 Kp] */
+	__nv_bfloat16 *d_w = nullptr;       /* [hi | lo][L][Np][2 Kp] */
 	uint32_t *d_step = nullptr;
 	float2 *d_out[2] = {nullptr, nullptr};
 	void *d_in = nullptr;               /* staging of the host entry points */
 	size_t out_stride = 0;
-	CUtensorMap tmA, tmB;
+	chan_maps maps;
+	CUtensorMap tmB;
 	uint64_t n_consumed = 0;            /* wideband samples consumed so far */
 	long n_calls = 0;
 	cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -306,22 +370,52 @@ static int cfail(sonde_chan *h, int code, const char *msg)
 }
 #define CCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (h) h->err = std::string(#x) + ": " + cudaGetErrorString(e_); return SONDE_ERR_CUDA; } } while (0)
 
-static uint16_t bf16_bits(double v)
+static uint16_t bf16_bits(float v)
 {
-	const __nv_bfloat16 b = __float2bfloat16_rn((float)v);
+	const __nv_bfloat16 b = __float2bfloat16_rn(v);
 	uint16_t u;
 	memcpy(&u, &b, 2);
 	return u;
 }
+static float bf16_value(uint16_t u)
+{
+	const uint32_t w = (uint32_t)u << 16;
+	float f;
+	memcpy(&f, &w, 4);
+	return f;
+}
+
+static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
+
+/* prototype low-pass at the up-sampled rate L fs_in: Hamming-windowed sinc, -6 dB at fc, gain L (unit DC gain per
+ * polyphase branch) */
+static std::vector<double> make_prototype(int n, double fc, double fs_up, int L)
+{
+	std::vector<double> g(n);
+	double sum = 0;
+	for (int k = 0; k < n; k++) {
+		const double t = k - 0.5 * (n - 1);
+		const double x = 2.0 * fc / fs_up * t;
+		const double sinc = fabs(x) < 1e-12 ? 1.0 : sin(M_PI * x) / (M_PI * x);
+		const double w = 0.54 - 0.46 * cos(2.0 * M_PI * k / (n - 1));
+		g[k] = sinc * w;
+		sum += g[k];
+	}
+	for (double &v : g) v *= (double)L / sum;
+	return g;
+}
 
 extern "C" {
 
-int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
+int sonde_chan_create_ex(sonde_chan **out, const sonde_chan_config *cfg, const sonde_chan_options *opt)
 {
 	if (!out || !cfg || !cfg->freq_hz) return SONDE_ERR_ARG;
 	*out = nullptr;
 	if (cfg->n_channels <= 0 || cfg->decim < 2 || cfg->fs_out <= 0 || cfg->max_in_len <= 0 || cfg->max_in_len % cfg->decim)
 		return SONDE_ERR_ARG;
+	const int L = (opt && opt->interp > 0) ? opt->interp : 1;
+	if (L > MAX_INTERP || L >= cfg->decim || gcd_int(L, cfg->decim) != 1) return SONDE_ERR_ARG;
+	if (opt && (opt->precision < 0 || opt->precision > 1)) return SONDE_ERR_ARG;
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return SONDE_ERR_NODEVICE;
 	cudaDeviceProp prop;
@@ -333,63 +427,100 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 	h->cfg.freq_hz = nullptr;
 	h->C = cfg->n_channels;
 	h->D = cfg->decim;
+	h->L = L;
+	h->npass = (opt && opt->precision == 1) ? 3 : 1;
 	const int tpp = cfg->taps_per_phase > 0 ? cfg->taps_per_phase : 8;
-	h->K = tpp * h->D;
+	h->K = (tpp * h->D + L - 1) / L;                 /* taps per branch: tpp output samples of input */
 	/* The TMA window view needs a row pitch of 4 D S bytes that is a multiple of 16.  D % 4 == 0: S = 1.  Otherwise the
 	 * samples are stored every 2nd (even D) or 4th slot with zero slots in between and the weight rows carry zeros at
 	 * those positions: the same GEMM over a 2x / 4x longer K dimension (2x / 4x the tensor work, still exact). */
 	h->S = (h->D % 4 == 0) ? 1 : (h->D % 2 == 0) ? 2 : 4;
 	h->Kp = (h->K * h->S + 31) / 32 * 32;            /* window length in slots; 2 Kp a multiple of the 64-element K block */
-	h->H = h->Kp - h->D * h->S;                      /* history slots in front of the chunk */
+	for (int r = 0; r < L; r++) h->e_abs[r] = (r * h->D + h->D - 1) / L;
+	for (int r = 0; r < L; r++) {
+		const int delta = h->S * (h->e_abs[r] - h->e_abs[0]), j = delta % 4;       /* window shift of the branch in slots */
+		int ci = -1;
+		for (int c = 0; c < h->n_copies && ci < 0; c++)
+			if (h->copy_shift[c] == j) ci = c;
+		if (ci < 0) { ci = h->n_copies++; h->copy_shift[ci] = j; }                 /* copy 0 has shift 0 (branch 0) */
+		h->copy_of[r] = ci;
+		h->e_rel[r] = 2 * (delta - j);
+	}
+	h->H = h->Kp - h->S * (1 + h->e_abs[0]);         /* history slots in front of the chunk (L = 1: Kp - D S) */
 	h->Np = (2 * h->C + BN - 1) / BN * BN;
-	h->max_out = cfg->max_in_len / h->D;
+	h->max_out = cfg->max_in_len / h->D * L;
 	h->out_stride = ((size_t)h->max_out + 3) & ~(size_t)3;
 	h->n_sms = prop.multiProcessorCount;
-	const double fs_in = (double)cfg->fs_out * h->D;
-	const double fc = cfg->cutoff_hz > 0 ? cfg->cutoff_hz : 0.42 * cfg->fs_out;
+	const double fs_in = (double)cfg->fs_out * h->D / L;
 
-	/* prototype low-pass: Hamming-windowed sinc, -6 dB at fc, unit DC gain */
-	h->taps.resize(h->K);
-	double sum = 0;
-	for (int k = 0; k < h->K; k++) {
-		const double t = k - 0.5 * (h->K - 1);
-		const double x = 2.0 * fc / fs_in * t;
-		const double sinc = fabs(x) < 1e-12 ? 1.0 : sin(M_PI * x) / (M_PI * x);
-		const double w = 0.54 - 0.46 * cos(2.0 * M_PI * k / (h->K - 1));
-		h->taps[k] = sinc * w;
-		sum += h->taps[k];
+	/* prototypes: one per distinct cut-off (the per-type channel bandwidths) */
+	h->cutoffs.resize(h->C);
+	h->proto_of.resize(h->C);
+	for (int c = 0; c < h->C; c++) {
+		float fc = (opt && opt->cutoff_hz && opt->cutoff_hz[c] > 0) ? opt->cutoff_hz[c] : cfg->cutoff_hz;
+		if (!(fc > 0)) fc = 0.42f * cfg->fs_out;
+		h->cutoffs[c] = fc;
+		int found = -1;
+		for (int d = 0; d < c && found < 0; d++)
+			if (h->cutoffs[d] == fc) found = h->proto_of[d];
+		if (found < 0) {
+			found = (int)h->protos.size();
+			h->protos.push_back(make_prototype(h->K * L, fc, fs_in * L, L));
+		}
+		h->proto_of[c] = found;
 	}
-	for (double &v : h->taps) v /= sum;
 
-	/* oscillator steps and the weight matrix B[n][j] (see the header comment) */
+	/* oscillator steps and the weight matrices B[pass][r][n][j] (see the header comment) */
 	h->steps.resize(h->C);
-	std::vector<uint16_t> w((size_t)h->Np * 2 * h->Kp, 0);
+	const size_t wmat = (size_t)h->Np * 2 * h->Kp;
+	std::vector<uint16_t> w((size_t)(h->npass > 1 ? 2 : 1) * L * wmat, 0);
 	for (int c = 0; c < h->C; c++) {
 		const double f = cfg->freq_hz[c] / fs_in;             /* cycles per input sample */
 		if (!(fabs(f) < 0.5)) { delete h; return SONDE_ERR_ARG; }
 		const long long st = llround(f * 4294967296.0);
 		h->steps[c] = (uint32_t)st;
-		uint16_t *row_re = &w[(size_t)(2 * c) * 2 * h->Kp], *row_im = &w[(size_t)(2 * c + 1) * 2 * h->Kp];
-		for (int kk = 0; kk < h->Kp; kk++) {
-			if ((h->Kp - 1 - kk) % h->S) continue;            /* a zero slot between samples     */
-			const int k = (h->Kp - 1 - kk) / h->S;            /* tap index of window position kk */
-			if (k >= h->K) continue;                          /* zero padding (oldest samples)   */
-			/* phase reduced before the trig call: w_c k mod 2 pi via the integer step */
-			const uint32_t ph = h->steps[c] * (uint32_t)k;
-			const double a = 2.0 * M_PI * (double)(int32_t)ph / 4294967296.0;
-			const double wr = h->taps[k] * cos(a), wi = h->taps[k] * sin(a);
-			row_re[2 * kk] = bf16_bits(wr);  row_re[2 * kk + 1] = bf16_bits(-wi);
-			row_im[2 * kk] = bf16_bits(wi);  row_im[2 * kk + 1] = bf16_bits(wr);
+		const std::vector<double> &g = h->protos[h->proto_of[c]];
+		for (int r = 0; r < L; r++) {
+			const int phi = (r * h->D + h->D - 1) % L;
+			uint16_t *row_re = &w[(size_t)r * wmat + (size_t)(2 * c) * 2 * h->Kp], *row_im = row_re + 2 * h->Kp;
+			uint16_t *lo_re = h->npass > 1 ? row_re + (size_t)L * wmat : nullptr, *lo_im = lo_re ? lo_re + 2 * h->Kp : nullptr;
+			for (int kk = 0; kk < h->Kp; kk++) {
+				if ((h->Kp - 1 - kk) % h->S) continue;            /* a zero slot between samples     */
+				const int k = (h->Kp - 1 - kk) / h->S;            /* tap index of window position kk */
+				if (k >= h->K) continue;                          /* zero padding (oldest samples)   */
+				/* phase reduced before the trig call: w_c k mod 2 pi via the integer step */
+				const uint32_t ph = h->steps[c] * (uint32_t)k;
+				const double a = 2.0 * M_PI * (double)(int32_t)ph / 4294967296.0;
+				const double tap = g[phi + (size_t)k * L];
+				const float v[4] = {(float)(tap * cos(a)), (float)(-tap * sin(a)), (float)(tap * sin(a)), (float)(tap * cos(a))};
+				uint16_t hi[4];
+				for (int i = 0; i < 4; i++) hi[i] = bf16_bits(v[i]);
+				row_re[2 * kk] = hi[0];  row_re[2 * kk + 1] = hi[1];
+				row_im[2 * kk] = hi[2];  row_im[2 * kk + 1] = hi[3];
+				if (lo_re) {
+					lo_re[2 * kk] = bf16_bits(v[0] - bf16_value(hi[0]));  lo_re[2 * kk + 1] = bf16_bits(v[1] - bf16_value(hi[1]));
+					lo_im[2 * kk] = bf16_bits(v[2] - bf16_value(hi[2]));  lo_im[2 * kk + 1] = bf16_bits(v[3] - bf16_value(hi[3]));
+				}
+			}
 		}
 	}
 
 	auto bail = [&](int code, const char *msg) { h->err = msg; sonde_chan_destroy(h); return code; };
 	/* the tensor map has at least one full tile of rows, so the buffer covers BM windows even for tiny max_in_len */
-	const size_t rows_dim = h->max_out > BM ? (size_t)h->max_out : (size_t)BM;
-	const size_t nx = (size_t)h->H + rows_dim * h->D * h->S + 2 * BK;      /* + slack */
-	if (cudaMalloc(&h->d_x, nx * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
-	if (cudaMemset(h->d_x, 0, nx * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMemset");
-	if (cudaMalloc(&h->d_tail, (size_t)h->H * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
+	const size_t rows = (size_t)(cfg->max_in_len / h->D);
+	const size_t rows_dim = rows > BM ? rows : (size_t)BM;
+	const size_t row_len = (size_t)h->Kp + (size_t)h->S * h->D;             /* window + the largest branch shift, in slots */
+	const size_t nx = rows_dim * h->D * h->S + row_len + 2 * BK;            /* + slack */
+	h->nx = nx;
+	for (int c = 0; c < h->n_copies; c++) {
+		if (cudaMalloc(&h->d_x[c], (nx + 4) * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
+		if (cudaMemset(h->d_x[c], 0, (nx + 4) * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMemset");
+		if (h->npass > 1) {
+			if (cudaMalloc(&h->d_xlo[c], (nx + 4) * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
+			if (cudaMemset(h->d_xlo[c], 0, (nx + 4) * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMemset");
+		}
+	}
+	if (cudaMalloc(&h->d_tail, ((size_t)h->H + 1) * sizeof(__nv_bfloat162)) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
 	if (cudaMalloc(&h->d_w, w.size() * 2) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
 	if (cudaMemcpy(h->d_w, w.data(), w.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMemcpy");
 	if (cudaMalloc(&h->d_step, (size_t)h->C * 4) != cudaSuccess) return bail(SONDE_ERR_CUDA, "cudaMalloc");
@@ -405,14 +536,24 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 	if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode)
 		return bail(SONDE_ERR_CUDA, "cuTensorMapEncodeTiled not available");
 	{
-		/* A: rows = output samples (pitch 2D elements), columns = 2 Kp interleaved re/im of the window */
-		const cuuint64_t gdim[2] = {(cuuint64_t)(2 * h->Kp), (cuuint64_t)rows_dim};      /* rows past it: zero fill, no access */
+		/* A: rows = output samples of one branch (pitch 2 D S elements), columns = the interleaved re/im of the window plus
+		 * the branch shifts */
+		const cuuint64_t gdim[2] = {(cuuint64_t)(2 * row_len), (cuuint64_t)rows_dim};      /* rows past it: zero fill, no access */
 		const cuuint64_t gstr[1] = {(cuuint64_t)(2 * h->D * h->S) * 2};
 		const cuuint32_t box[2] = {BK, BM}, estr[2] = {1, 1};
-		if (encode(&h->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-		           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-			return bail(SONDE_ERR_CUDA, "tensor map A");
-		const cuuint64_t gdimb[2] = {(cuuint64_t)(2 * h->Kp), (cuuint64_t)h->Np};
+		memset(&h->maps, 0, sizeof(h->maps));
+		for (int c = 0; c < h->n_copies; c++) {
+			if (encode(&h->maps.a[c], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_x[c] + 4, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+				return bail(SONDE_ERR_CUDA, "tensor map A");
+			h->maps.alo[c] = h->maps.a[c];
+			if (h->d_xlo[c] &&
+			    encode(&h->maps.alo[c], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_xlo[c] + 4, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+				return bail(SONDE_ERR_CUDA, "tensor map A (residuals)");
+		}
+		for (int c = h->n_copies; c < MAX_COPIES; c++) { h->maps.a[c] = h->maps.a[0]; h->maps.alo[c] = h->maps.alo[0]; }
+		const cuuint64_t gdimb[2] = {(cuuint64_t)(2 * h->Kp), (cuuint64_t)((h->npass > 1 ? 2 : 1) * L * h->Np)};
 		const cuuint64_t gstrb[1] = {(cuuint64_t)(2 * h->Kp) * 2};
 		const cuuint32_t boxb[2] = {BK, BN};
 		if (encode(&h->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_w, gdimb, gstrb, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -425,12 +566,14 @@ int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg)
 	return SONDE_OK;
 }
 
+int sonde_chan_create(sonde_chan **out, const sonde_chan_config *cfg) { return sonde_chan_create_ex(out, cfg, nullptr); }
+
 void sonde_chan_destroy(sonde_chan *h)
 {
 	if (!h) return;
 	cudaSetDevice(h->cfg.device);
 	cudaDeviceSynchronize();
-	cudaFree(h->d_x); cudaFree(h->d_tail); cudaFree(h->d_w); cudaFree(h->d_step); cudaFree(h->d_in);
+	for (int c = 0; c < MAX_COPIES; c++) { cudaFree(h->d_x[c]); cudaFree(h->d_xlo[c]); } cudaFree(h->d_tail); cudaFree(h->d_w); cudaFree(h->d_step); cudaFree(h->d_in);
 	for (int b = 0; b < 2; b++) { cudaFree(h->d_out[b]); if (h->ev[b]) cudaEventDestroy(h->ev[b]); }
 	delete h;
 }
@@ -445,16 +588,23 @@ static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float
 	CCK(cudaSetDevice(h->cfg.device));
 	cudaStream_t st = (cudaStream_t)stream_;
 	const int blocks = h->n_sms * 4;
-	__nv_bfloat162 *dst = h->d_x + h->H + (h->S - 1);          /* sample i lives in slot H + S i + (S - 1) */
+	copy_ptrs cp;                                               /* sample i lives in slot H + S i + (S - 1) of the stream */
+	memset(&cp, 0, sizeof(cp));
+	cp.n = h->n_copies;
+	for (int c = 0; c < h->n_copies; c++) {
+		cp.hi[c] = h->d_x[c] + 4 + h->H + (h->S - 1);
+		cp.lo[c] = h->d_xlo[c] ? h->d_xlo[c] + 4 + h->H + (h->S - 1) : nullptr;
+		cp.shift[c] = h->copy_shift[c];
+	}
 	if (kind == 0) {
-		to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(src), dst, n_in, h->S);
+		to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(src), cp, n_in, h->S);
 	} else {
 		const size_t esz = kind == 1 ? sizeof(float2) : kind == 2 ? sizeof(short2) : sizeof(uchar2);
 		if (!h->d_in) CCK(cudaMalloc(&h->d_in, (size_t)h->cfg.max_in_len * sizeof(float2)));
 		CCK(cudaMemcpyAsync(h->d_in, src, n_in * esz, cudaMemcpyHostToDevice, st));
-		if (kind == 1)      to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(h->d_in), dst, n_in, h->S);
-		else if (kind == 2) to_bf16_s16_kernel<<<blocks, 256, 0, st>>>(static_cast<const short2 *>(h->d_in), dst, n_in, h->S, scale);
-		else                to_bf16_u8_kernel<<<blocks, 256, 0, st>>>(static_cast<const uchar2 *>(h->d_in), dst, n_in, h->S);
+		if (kind == 1)      to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(h->d_in), cp, n_in, h->S);
+		else if (kind == 2) to_bf16_s16_kernel<<<blocks, 256, 0, st>>>(static_cast<const short2 *>(h->d_in), cp, n_in, h->S, scale);
+		else                to_bf16_u8_kernel<<<blocks, 256, 0, st>>>(static_cast<const uchar2 *>(h->d_in), cp, n_in, h->S);
 	}
 	CCK(cudaGetLastError());
 
@@ -464,22 +614,33 @@ static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float
 	gp.out_stride = h->out_stride;
 	gp.step = h->d_step;
 	gp.n_channels = h->C;
-	gp.m_out = (int)(n_in / h->D);
-	gp.n_mt = (gp.m_out + BM - 1) / BM;
+	gp.m_rows = (int)(n_in / h->D);
+	gp.n_mt = (gp.m_rows + BM - 1) / BM;
 	gp.n_nt = h->Np / BN;
 	gp.n_kb = 2 * h->Kp / BK;
+	gp.npass = h->npass;
+	gp.np = h->Np;
 	gp.decim = h->D;
-	gp.n0_base = (uint32_t)(h->n_consumed + (uint64_t)h->D - 1);
-	const int n_tiles = gp.n_mt * gp.n_nt;
+	gp.interp = h->L;
+	gp.n0_base = (uint32_t)h->n_consumed;
+	for (int r = 0; r < MAX_INTERP; r++) { gp.e_abs[r] = h->e_abs[r]; gp.e_rel[r] = h->e_rel[r]; gp.copy_of[r] = h->copy_of[r]; }
+	const int n_tiles = gp.n_mt * gp.n_nt * h->L;
 	const int grid = n_tiles < h->n_sms ? n_tiles : h->n_sms;
 	CCK(cudaEventRecord(h->ev[0], st));
-	chan_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(h->tmA, h->tmB, gp);
+	chan_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(h->maps, h->tmB, gp);
 	CCK(cudaGetLastError());
 	CCK(cudaEventRecord(h->ev[1], st));
 	h->have_timing = true;
 	/* carry the last H samples to the front for the next call (through a side buffer: the ranges may overlap) */
-	CCK(cudaMemcpyAsync(h->d_tail, h->d_x + n_in * h->S, (size_t)h->H * sizeof(__nv_bfloat162), cudaMemcpyDeviceToDevice, st));
-	CCK(cudaMemcpyAsync(h->d_x, h->d_tail, (size_t)h->H * sizeof(__nv_bfloat162), cudaMemcpyDeviceToDevice, st));
+	/* every copy is the same stream at its own shift: slots [n_in S, n_in S + H) of the stream move to [0, H); the few
+	 * slots in front of a shifted copy's origin belong to samples older than any window and are never read */
+	for (int c = 0; c < h->n_copies && h->H > 0; c++) {
+		for (__nv_bfloat162 *buf : {h->d_x[c], h->d_xlo[c]}) {
+			if (!buf) continue;
+			CCK(cudaMemcpyAsync(h->d_tail, buf + 4 + n_in * h->S, (size_t)h->H * sizeof(__nv_bfloat162), cudaMemcpyDeviceToDevice, st));
+			CCK(cudaMemcpyAsync(buf + 4, h->d_tail, (size_t)h->H * sizeof(__nv_bfloat162), cudaMemcpyDeviceToDevice, st));
+		}
+	}
 	h->n_consumed += n_in;
 	h->n_calls++;
 	*d_out = gp.out;
@@ -505,14 +666,16 @@ int sonde_chan_process_u8(sonde_chan *h, const uint8_t *wide_iq, size_t n_in, vo
 	return chan_run(h, wide_iq, n_in, 3, 1.0f, stream, d_out, out_stride);
 }
 
-int sonde_chan_num_taps(const sonde_chan *h) { return h ? h->K : SONDE_ERR_ARG; }
-int sonde_chan_taps(const sonde_chan *h, double *taps, int cap)
+int sonde_chan_num_taps(const sonde_chan *h) { return h ? h->K * h->L : SONDE_ERR_ARG; }
+int sonde_chan_taps_of(const sonde_chan *h, int channel, double *taps, int cap)
 {
-	if (!h || !taps) return SONDE_ERR_ARG;
-	const int n = cap < h->K ? cap : h->K;
-	memcpy(taps, h->taps.data(), (size_t)n * sizeof(double));
+	if (!h || !taps || channel < 0 || channel >= h->C) return SONDE_ERR_ARG;
+	const std::vector<double> &g = h->protos[h->proto_of[channel]];
+	const int n = cap < (int)g.size() ? cap : (int)g.size();
+	memcpy(taps, g.data(), (size_t)n * sizeof(double));
 	return n;
 }
+int sonde_chan_taps(const sonde_chan *h, double *taps, int cap) { return sonde_chan_taps_of(h, 0, taps, cap); }
 int sonde_chan_steps(const sonde_chan *h, uint32_t *steps, int cap)
 {
 	if (!h || !steps) return SONDE_ERR_ARG;

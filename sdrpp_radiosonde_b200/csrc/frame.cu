@@ -689,12 +689,34 @@ frame_kernel(const frame_params p)
 		/* stage the buffer: up to 2F bits can be needed (F + sync_offset); bits past `avail` are
 		 * never used */
 		const int nw = (2 * F + 31) / 32 + 3;
+		if (fs.n_carry == 0 && fs.zero_prefix == 0) {
+			/* the common case, straight from the ring: all of a lane's aligned 32-bit loads are issued before the first
+			 * use (one round trip to HBM/L2 per window instead of one per 32 words), then each window word is funnel-
+			 * shifted out of two neighbouring ring words (bytes are stream order, MSB first) */
+			constexpr int NI = (WIN_WORDS + 31) / 32;
+			const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(ring);
+			const uint32_t wmask = (p.ring_bytes >> 2) - 1u;
+			const uint32_t w0 = (uint32_t)(fs.d_pos >> 5) & wmask, sh = (uint32_t)(fs.d_pos & 31);
+			uint32_t a[NI], b[NI];
+#pragma unroll
+			for (int i = 0; i < NI; i++) {
+				const int w = lane + 32 * i;
+				a[i] = b[i] = 0;
+				if (w < nw) {
+					a[i] = ring32[(w0 + w) & wmask];
+					b[i] = ring32[(w0 + w + 1) & wmask];
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < NI; i++) {
+				const int w = lane + 32 * i;
+				if (w < nw) ws.win[w] = __funnelshift_l(__byte_perm(b[i], 0, 0x0123), __byte_perm(a[i], 0, 0x0123), sh);
+			}
+		} else
 		for (int w = lane; w < nw; w += 32) {
 			const int b0 = w * 32;
 			uint32_t v;
-			if (fs.n_carry == 0 && fs.zero_prefix == 0) {
-				v = ring_word(ring, rmask, fs.d_pos + b0);
-			} else {
+			{
 				v = 0;
 				for (int k = 0; k < 32; k++) {
 					const int bi = b0 + k;

@@ -59,6 +59,34 @@ def test_oracle_tone_goes_to_dc_and_bf16_rounding():
     assert orc.to_bf16(a).tolist() == [1.0, 1.0, 1.0078125, -3.140625]
 
 
+def test_oracle_rational_resampling_is_upsample_filter_decimate():
+    """interp = L: the polyphase form of the oracle equals the textbook chain (mix to DC, zero-stuff by L, FIR with the
+    L*K-tap prototype, keep every M-th sample) and a tone at the channel centre lands on DC with unit gain."""
+    L, M_, K = 3, 8, 24
+    Kg = L * K
+    t = np.arange(Kg, dtype=np.float64) - 0.5 * (Kg - 1)
+    g = np.sinc(2 * 0.4 / M_ * t) * np.hamming(Kg)            # cut-off 0.4 fs_out at the rate L fs_in
+    g *= L / g.sum()
+    rng = np.random.default_rng(1)
+    step = np.uint32(round(0.1234 * 2 ** 32))
+    n = M_ * 200
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    x = x.astype(np.complex64)
+    y = orc.channelize(x, g, [step], M_, interp=L)[0]
+    mixed = x.astype(np.complex128) * np.exp(-2j * np.pi * (int(step) / 2 ** 32) * np.arange(n))
+    up = np.zeros(n * L, dtype=np.complex128)
+    up[::L] = mixed
+    full = np.convolve(up, g)                                     # full[j] = sum_i g[j - i] up[i]
+    want = full[np.arange(len(y)) * M_ + M_ - 1]
+    assert len(y) == n // M_ * L and np.allclose(y, want, atol=1e-9)
+    tone = np.exp(2j * np.pi * (int(step) / 2 ** 32) * np.arange(n))
+    yt = orc.channelize(tone, g, [step], M_, interp=L)[0]
+    assert np.allclose(yt[K * L // M_ + L:], 1.0, atol=2e-3)
+    y2 = np.concatenate([orc.channelize(x[:M_ * 50], g, [step], M_, interp=L)[0],
+                         orc.channelize(x[M_ * 50:], g, [step], M_, n_start=M_ * 50, history=x[:M_ * 50], interp=L)[0]])
+    assert np.allclose(y, y2, atol=1e-12)
+
+
 def _wideband(rng, n, freqs, fs_in):
     x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.05
     t = np.arange(n)
@@ -202,3 +230,99 @@ def test_channelizer_entry_points_agree_and_reject_bad_arguments():
     with pytest.raises(capi.SondeError):
         ch.process_c64(np.concatenate([xf, xf]))               # longer than max_in_len
     ch.close()
+
+
+def _run_chunks(ch, x, chunks, C):
+    import torch
+    got, pos = [], 0
+    for cl in chunks:
+        ptr, stride, m = ch.process_c64(x[pos:pos + cl])
+        torch.cuda.synchronize()
+        out = capi.device_view(ptr, (C, stride, 2))[:, :m, :].cpu().numpy()
+        got.append(out[..., 0] + 1j * out[..., 1])
+        pos += cl
+    return np.concatenate(got, axis=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,C", [(48, 20), (50, 7), (128, 130)])
+def test_split_precision_reaches_fp32_grade(D, C):
+    """sonde_chan_options.precision = SONDE_CHAN_SPLIT_BF16: hi + lo bf16 operands, three tensor passes.  Tolerance: rms
+    error <= 1e-5 of the output rms against the exact formula in double precision for windows of up to 512 taps (the bench
+    shape, D = 48, measures 4.6e-6; the plain bf16 mode sits at ~1.5e-3), <= 1.5e-5 for the 1024-tap window of D = 128,
+    where the fp32 accumulation over 2048 products inside the tensor core adds its share (measured 1.04e-5)."""
+    rng = np.random.default_rng(50 + D)
+    fs_in = 48000.0 * D
+    freqs = rng.uniform(-0.45, 0.45, C) * fs_in
+    chunks = [D * 300, D * 128, D * 7, D * 600]
+    x = _wideband(rng, sum(chunks), freqs[:4], fs_in)
+    ch = capi.Channelizer(freqs, D, max(chunks), precision=1)
+    try:
+        got = _run_chunks(ch, x, chunks, C)
+        want = orc.channelize(x, ch.taps, ch.steps, D)
+        rms = np.sqrt(np.mean(np.abs(want) ** 2))
+        err = np.sqrt(np.mean(np.abs(got - want) ** 2)) / rms
+        worst = np.abs(got - want).max() / np.abs(want).max()
+        print(f"split bf16 D={D} C={C}: rms err {err:.2e} of rms, max err {worst:.2e} of max |y|")
+        assert err < (1e-5 if ch.K <= 512 else 1.5e-5)
+        assert worst < 3e-5
+    finally:
+        ch.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,M_,C,prec", [(3, 128, 9, 0), (3, 128, 9, 1), (12, 625, 5, 1), (5, 52, 6, 0)])
+def test_rational_resampling_matches_oracle(L, M_, C, prec):
+    """sonde_chan_options.interp: fs_out = fs_in L / M (2.048 MS/s -> 3/128, 2.5 MS/s -> 12/625, and an even, non-multiple-
+    of-4 decimation that uses the zero-slot layout).  Outputs are interleaved branch by branch; chunk boundaries
+    continue the stream."""
+    rng = np.random.default_rng(7 * L + M_)
+    fs_in = 48000.0 * M_ / L
+    freqs = rng.uniform(-0.45, 0.45, C) * fs_in
+    chunks = [M_ * 140, M_ * 3, M_ * 257]
+    x = _wideband(rng, sum(chunks), freqs[:3], fs_in)
+    ch = capi.Channelizer(freqs, M_, max(chunks), precision=prec, interp=L)
+    try:
+        got = _run_chunks(ch, x, chunks, C)
+        assert got.shape[1] == sum(chunks) // M_ * L
+        want = orc.channelize(x, ch.taps, ch.steps, M_, interp=L)
+        rms = np.sqrt(np.mean(np.abs(want) ** 2))
+        err = np.sqrt(np.mean(np.abs(got - want) ** 2)) / rms
+        print(f"L/M = {L}/{M_} precision {prec}: rms err {err:.2e} of rms")
+        # split precision: 1e-5 while the window (taps per branch x slot stride of the zero-slot layout) stays within 512
+        # slots, 2e-5 beyond (fp32 accumulation inside the tensor core over thousands of products; measured 1.6e-5 at
+        # 12/625, whose window is 1696 slots)
+        slots = ch.K // L * (1 if M_ % 4 == 0 else 2 if M_ % 2 == 0 else 4)
+        assert err < ((1e-5 if slots <= 512 else 2e-5) if prec else 1.5e-2)
+        if not prec:
+            want_f = orc.channelize(x, ch.taps, ch.steps, M_, interp=L, bf16=True)
+            assert np.abs(got - want_f).max() / np.abs(want_f).max() < 2e-4
+    finally:
+        ch.close()
+
+
+@pytest.mark.gpu
+def test_per_channel_cutoffs():
+    """sonde_chan_options.cutoff_hz: every channel gets the prototype of its own bandwidth (half the per-type VFO
+    bandwidths of src/main.hpp:45-51); the result equals the oracle run with each channel's own taps, and a narrow
+    channel rejects a tone 8 kHz off its centre that a wide one passes."""
+    D = 48
+    fs_in = 48000.0 * D
+    freqs = np.array([-300e3, -300e3, 150e3, 410e3])
+    cut = np.array([5e3, 21.6e3, 7.5e3, 10e3], dtype=np.float32)
+    n = D * 2000
+    t = np.arange(n)
+    x = (0.5 * np.exp(2j * np.pi * (-300e3 + 8e3) / fs_in * t)).astype(np.complex64)
+    ch = capi.Channelizer(freqs, D, n, taps_per_phase=32, precision=1, cutoffs=cut)
+    try:
+        got = _run_chunks(ch, x, [n], 4)
+        tp = [ch.taps_of(c) for c in range(4)]
+        assert not np.allclose(tp[0], tp[1]) and np.allclose(tp[0], ch.taps)
+        want = orc.channelize(x, ch.taps, ch.steps, D, taps_per_channel=tp)
+        assert np.sqrt(np.mean(np.abs(got - want) ** 2)) < 1e-5 * 0.5
+        p_narrow = np.mean(np.abs(got[0, 100:]) ** 2)
+        p_wide = np.mean(np.abs(got[1, 100:]) ** 2)
+        print(f"tone 8 kHz off centre: 5 kHz channel {10 * np.log10(p_narrow / 0.25):.1f} dB, 21.6 kHz channel {10 * np.log10(p_wide / 0.25):.1f} dB")
+        assert p_wide > 0.9 * 0.25 and p_narrow < 1e-3 * 0.25
+    finally:
+        ch.close()
