@@ -500,8 +500,9 @@ __device__ __forceinline__ void agc_tile(const float *__restrict__ x, float *__r
 
 template <int P, int KM0, int NM, int KS0, int NS, bool IQ, bool SOFT, bool TMA>
 __global__ void __maxnreg__(64)
-demod_pipe_kernel(const demod_params p, const int group_base)
+demod_pipe_kernel(const demod_params p, const int group_base, const int n_here)
 {
+	if ((int)blockIdx.x >= n_here) return;            /* the padding CTA of an odd group count (launch_tpc_pairs) */
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	smem_t<P> &sm = *reinterpret_cast<smem_t<P> *>(smem_raw);
 
@@ -690,8 +691,7 @@ cudaError_t launch3(const demod_params *p, int group_base, int n_groups, cudaStr
 	const cudaError_t ea = sonde_ensure_dynamic_smem(kern, (int)sizeof(smem_t<P>), attr_done);
 	if (ea != cudaSuccess) return ea;
 	const int nwarps = 32 - __builtin_clz(p->pw_mask | ROLE_MASK);
-	kern<<<n_groups, nwarps * 32, sizeof(smem_t<P>), stream>>>(*p, group_base);
-	return cudaGetLastError();
+	return launch_tpc_pairs(kern, n_groups, nwarps * 32, sizeof(smem_t<P>), stream, p->tpc_pairs != 0, *p, group_base, n_groups);
 }
 
 template <int P, int KM0, int NM, int KS0, int NS, bool IQ>

@@ -89,6 +89,10 @@ struct asmem_t {
 	unsigned long long pnfull[2], pnfree[2], dfull, bfull;
 };
 
+/* cabsf as glibc computes it.  Tried and measured slower (tools/stalls.py 5: PW 45.8 -> 51.3 busy cycles/sample): doing the
+ * float <-> double conversions with integer operations (re-biased exponent, shifted mantissa, round-to-nearest-even on the
+ * dropped bits) to take the three F2F per magnitude off the special-function pipe — the parallel warps of this kernel are
+ * bound by issue slots, not by that pipe, and the ~16 extra integer instructions cost more than the conversions. */
 __device__ __forceinline__ float cabs_exact(float re, float im)
 {
 	return (float)sqrt(__dadd_rn(__dmul_rn((double)re, (double)re), __dmul_rn((double)im, (double)im)));
@@ -109,8 +113,9 @@ __device__ __forceinline__ float nco_step(float p, float f)
 
 template <bool IQ, bool SOFT, int LAYOUT>
 __global__ void __launch_bounds__(aroles<LAYOUT>::NWARPS * 32, 1)
-demod_pipe_afsk_kernel(const demod_params p, const int group_base)
+demod_pipe_afsk_kernel(const demod_params p, const int group_base, const int n_here)
 {
+	if ((int)blockIdx.x >= n_here) return;            /* the padding CTA of an odd group count (launch_tpc_pairs) */
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	asmem_t &sm = *reinterpret_cast<asmem_t *>(smem_raw);
 
@@ -523,8 +528,8 @@ cudaError_t launch2(const demod_params *p, int group_base, int n_groups, cudaStr
 	static std::atomic<unsigned long long> attr_done{0};
 	const cudaError_t ea = sonde_ensure_dynamic_smem(demod_pipe_afsk_kernel<IQ, SOFT, LAYOUT>, (int)sizeof(asmem_t), attr_done);
 	if (ea != cudaSuccess) return ea;
-	demod_pipe_afsk_kernel<IQ, SOFT, LAYOUT><<<n_groups, aroles<LAYOUT>::NWARPS * 32, sizeof(asmem_t), stream>>>(*p, group_base);
-	return cudaGetLastError();
+	return launch_tpc_pairs(demod_pipe_afsk_kernel<IQ, SOFT, LAYOUT>, n_groups, aroles<LAYOUT>::NWARPS * 32, sizeof(asmem_t), stream,
+	                              p->tpc_pairs != 0, *p, group_base, n_groups);
 }
 
 template <int LAYOUT>

@@ -84,6 +84,7 @@ struct demod_params {
 	long long    *prof;           /* optional [n_groups][16] cycle counters (diagnostics) */
 	const int32_t *in_row;        /* [C] input row of each (virtual) channel          */
 	uint32_t      pw_mask;        /* K1: bit w set = warp w of the CTA is a parallel-work warp (SMSP = w % 4)  */
+	int32_t       tpc_pairs;      /* launch as clusters of two CTAs: TPC siblings run the same kernel variant  */
 	uint64_t     *nbits_out;      /* [C] stream length after this call (snapshot for the framer, which
 	                                 may run concurrently with the next call's demodulator)             */
 };

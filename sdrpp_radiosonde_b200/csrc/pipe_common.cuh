@@ -12,6 +12,30 @@
 #include "device_state.h"
 #include "strict_math.cuh"
 
+/* Launch a pipeline kernel as thread-block clusters of two, so that both SMs of a TPC run the SAME kernel variant.
+ * Measured (tools/mixprobe.py): when a batch mixes kernel variants, CTAs whose TPC sibling runs a different variant are
+ * 30-50 % slower than beside a sibling of their own kind (the two SMs of a TPC share instruction-fetch resources and the
+ * parallel-work warps stream through a long unrolled body).  An odd group count is padded with one CTA that exits at once
+ * (`n_here` = real groups). */
+template <class Kernel, class... Args>
+static inline cudaError_t launch_tpc_pairs(Kernel kern, int n_groups, int threads, size_t smem, cudaStream_t stream, bool pairs,
+                                           Args... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(pairs ? (unsigned)((n_groups + 1) & ~1) : (unsigned)n_groups, 1, 1);
+	cfg.blockDim = dim3((unsigned)threads, 1, 1);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = 2;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = pairs ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 namespace pipe {
 
 constexpr int G = 8;                     /* channels per CTA                       */

@@ -155,18 +155,50 @@ void build_groups(sonde_b200 *h, const std::vector<int32_t> *active, std::vector
 	 * scales with the channel count, so the batch is spread over all SMs: the fewest waves of one CTA per SM that
 	 * hold it at <= DEMOD_G channels each, then the smallest group size that still fits in those waves
 	 * (1024 channels on 148 SMs: 147 CTAs of 7 instead of 128 of 8). */
-	int gsz = DEMOD_G;
+	/* A batch that mixes kernel variants launches each variant as clusters of two CTAs (launch_tpc_pairs: TPC siblings
+	 * then run the same code), so every variant occupies an even number of SMs; the group size is the smallest one whose
+	 * padded CTA counts still fit the waves. */
+	auto variant_of = [](const sonde_modem &m) { return !m.baud ? -1 : m.afsk ? 3 : m.num_phases == 2 ? 2 : m.freq0 >= 0.19f ? 0 : 1; };
+	int gsz_v[4] = {DEMOD_G, DEMOD_G, DEMOD_G, DEMOD_G};
 	{
-		int n_act = 0;
-		for (int c = 0; c < C; c++) n_act += (!active || (*active)[c]) ? 1 : 0;
+		int per_type[SONDE_NTYPES] = {0};
+		for (int c = 0; c < C; c++)
+			if (!active || (*active)[c]) per_type[h->types[c]]++;
+		int n_var = 0, seen[4] = {0, 0, 0, 0};
+		for (int t = 0; t < SONDE_NTYPES; t++)
+			if (per_type[t] && variant_of(h->modems[t]) >= 0 && !seen[variant_of(h->modems[t])]++) n_var++;
 		const int sms = h->n_sms > 0 ? h->n_sms : 148;
-		const int waves = std::max(1, (n_act + sms * DEMOD_G - 1) / (sms * DEMOD_G));
-		gsz = std::min(DEMOD_G, std::max(1, (n_act + sms * waves - 1) / (sms * waves)));
+		auto ctas_needed = [&](const int (&g)[4]) {
+			int per_var[4] = {0, 0, 0, 0}, total = 0;
+			for (int t = 0; t < SONDE_NTYPES; t++) {
+				const int v = variant_of(h->modems[t]);
+				if (per_type[t] && v >= 0) per_var[v] += (per_type[t] + g[v] - 1) / g[v];
+			}
+			for (int v = 0; v < 4; v++) total += n_var > 1 ? (per_var[v] + 1) & ~1 : per_var[v];
+			return total;
+		};
+		const int budget = sms * std::max(1, (ctas_needed(gsz_v) + sms - 1) / sms);
+		for (int g = 1; g < DEMOD_G; g++) {
+			const int u[4] = {g, g, g, g};
+			if (ctas_needed(u) <= budget) { for (int v = 0; v < 4; v++) gsz_v[v] = g; break; }
+		}
+		/* SMs the uniform size leaves over go to the variants whose CTA time grows fastest with its channel count: the
+		 * AFSK kernel (its parallel warps are bound by the special-function pipe), then the two-branch M10/M20 one */
+		for (bool changed = true; changed;) {
+			changed = false;
+			for (int v : {3, 2}) {
+				if (!seen[v] || gsz_v[v] <= 1) continue;
+				int u[4] = {gsz_v[0], gsz_v[1], gsz_v[2], gsz_v[3]};
+				u[v]--;
+				if (ctas_needed(u) <= budget) { gsz_v[v]--; changed = true; break; }
+			}
+		}
 	}
 	auto add_groups = [&](auto pred) {
 		int added = 0;
 		for (int t = 0; t < SONDE_NTYPES; t++) {
 			if (!pred(h->modems[t])) continue;
+			const int gsz = gsz_v[variant_of(h->modems[t])];
 			std::vector<int32_t> ch;
 			for (int c = 0; c < C; c++)
 				if (h->types[c] == t && (!active || (*active)[c])) ch.push_back(c);
@@ -557,6 +589,7 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	static const uint32_t kPwMask[3] = {0xCCCFCCu /* RS41 */, 0xCCDDCCu /* DFM, iMS-100, MRZ-N1 */, 0xCCCCCCu /* M10/M20 */};
 	const int par = (int)(h->n_issued & 1);
 	dp.nbits_out = h->d_nbits[par];
+	static const int tpc_env = getenv("SONDE_TPC_PAIRS") ? atoi(getenv("SONDE_TPC_PAIRS")) : -1;     /* experiment switch */
 	/* the demodulator of call i+2 appends to ring positions the framer of call i may still be reading */
 	if (h->n_issued >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_done[par], 0));
 	CK(cudaEventRecord(h->ev[0], h->stream));
@@ -567,6 +600,8 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	for (int v = 0; v < 4; v++) n_variants += h->groups_v[v] > 0;
 	static const bool no_fork = getenv("SONDE_NO_FORK") != nullptr;                /* experiment switch */
 	const bool fork = n_variants > 1 && !no_fork;
+	/* variants sharing the GPU: clusters of two, so that TPC siblings run the same code (pipe_common.cuh) */
+	dp.tpc_pairs = tpc_env >= 0 ? tpc_env : (fork ? 1 : 0);
 	if (fork) CK(cudaEventRecord(h->ev_fork, h->stream));
 	int base = 0;
 	for (int v = 0; v < 4; v++) {
