@@ -493,18 +493,18 @@ def main():
     scatter = None
     wide_src = None
     if world > 1 and not args.no_scatter:
+        from cuda.bindings import runtime as cudart
+
+        def ck(r):
+            if isinstance(r, tuple):
+                err, rest = r[0], r[1:]
+            else:
+                err, rest = r, ()
+            if int(err) != 0:
+                raise RuntimeError(f"cudart error {err}")
+            return rest[0] if len(rest) == 1 else rest
+
         try:
-            from cuda.bindings import runtime as cudart
-
-            def ck(r):
-                if isinstance(r, tuple):
-                    err, rest = r[0], r[1:]
-                else:
-                    err, rest = r, ()
-                if int(err) != 0:
-                    raise RuntimeError(f"cudart error {err}")
-                return rest[0] if len(rest) == 1 else rest
-
             n_sc = 8
             blk = C * L * 8
             handles = [None, None]
@@ -560,21 +560,33 @@ def main():
             n_in = L * Dw
             rngw = np.random.default_rng(7)
             freqs = np.random.default_rng(11 + rank).uniform(-0.45, 0.45, C) * FS * Dw
-            wbuf = [torch.empty((n_in,), dtype=torch.complex64, device="cuda") for _ in range(2)]
+            wsrc, whandles = [0, 0], [None, None]
             if rank == 0:
-                for wb in wbuf:
-                    wb.copy_(torch.from_numpy((0.05 * (rngw.standard_normal(n_in) + 1j * rngw.standard_normal(n_in))).astype(np.complex64)))
+                for j in range(2):
+                    wsrc[j] = int(ck(cudart.cudaMalloc(n_in * 8)))
+                    hostw = (0.05 * (rngw.standard_normal(n_in) + 1j * rngw.standard_normal(n_in))).astype(np.complex64)
+                    ck(cudart.cudaMemcpy(wsrc[j], hostw.ctypes.data, n_in * 8, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice))
+                    whandles[j] = bytes(ck(cudart.cudaIpcGetMemHandle(wsrc[j])).reserved)
+            dist.broadcast_object_list(whandles, src=0)
+            if rank != 0:
+                for j in range(2):
+                    hnd = cudart.cudaIpcMemHandle_t()
+                    hnd.reserved = whandles[j]
+                    wsrc[j] = int(ck(cudart.cudaIpcOpenMemHandle(hnd, cudart.cudaIpcMemLazyEnablePeerAccess)))
             chz = capi.Channelizer(freqs, Dw, n_in, device=local_rank)
             dec6 = capi.BatchDecoder(sig_types, L, device=local_rank)
             ext6 = torch.cuda.ExternalStream(dec6.stream)
-            cur = torch.cuda.current_stream()
+            cur = torch.cuda.Stream()
             done6 = [None, None]
 
             def wstep6(i):
+                # pull (copy engine) + channelizer of step i+1 on a side stream beside the decode of step i
                 if done6[i & 1] is not None:
                     cur.wait_event(done6[i & 1])
-                dist.broadcast(torch.view_as_real(wbuf[i & 1]), src=0)          # 18 MB over NVLink (NCCL)
-                ptr, stride, m = chz.process_c64_device(wbuf[i & 1].data_ptr(), n_in, stream=cur.cuda_stream)
+                if rank == 0:
+                    ptr, stride, m = chz.process_c64_device(wsrc[i & 1], n_in, stream=cur.cuda_stream)
+                else:
+                    ptr, stride, m = chz.process_c64_peer(0, wsrc[i & 1], n_in, stream=cur.cuda_stream)
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 ext6.wait_event(ev)
@@ -596,6 +608,13 @@ def main():
             wide_src = {"t": time.perf_counter() - t0, "bytes": n_in * 8, "D": Dw}
             chz.close()
             dec6.close()
+            if rank != 0:
+                for j in range(2):
+                    cudart.cudaIpcCloseMemHandle(wsrc[j])
+            barrier()
+            if rank == 0:
+                for j in range(2):
+                    cudart.cudaFree(wsrc[j])
         except Exception as ex:                      # informational extra
             wide_src = None
             print(f"wideband single-source measurement failed: {type(ex).__name__}: {ex}", file=sys.stderr)
@@ -686,10 +705,14 @@ def main():
         if wide_src:
             tw6 = float(t_all[3])
             line["single_source_wideband"] = {
-                "what": f"rank 0 holds the wideband complex64 IQ ({wide_src['D']} x 48 kS/s, {wide_src['bytes'] / 1e6:.1f} MB per step); NCCL "
-                        "broadcast, then every rank channelises (tcgen05 GEMM) and decodes its own channel block",
+                "what": f"rank 0 holds the wideband complex64 IQ ({wide_src['D']} x 48 kS/s, {wide_src['bytes'] / 1e6:.1f} MB per step); every "
+                        "rank pulls it over NVLink with the copy engine (CUDA IPC + sonde_chan_process_c64_peer), channelises "
+                        "its own channel block (tcgen05 GEMM) and decodes it; pull + GEMM of step i+1 are enqueued beside the "
+                        "decode of step i",
                 "value": world * args.steps * C * L / (tw6 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": tw6 / args.steps,
-                "broadcast_bytes_per_step": wide_src["bytes"]}
+                "efficiency_vs_resident_shards": (ms_max / args.steps) / (tw6 / args.steps),
+                "rank0_egress_bytes_per_step": (world - 1) * wide_src["bytes"],
+                "rank0_egress_gbs": (world - 1) * wide_src["bytes"] / (tw6 / args.steps * 1e-3) / 1e9}
         if not args.no_cpu_baseline and world == 1:
             cpu = CpuPath()
             n_ch = min(C, 2 * ncores)

@@ -93,6 +93,11 @@ SONDE_API int  sonde_chan_process_c64(sonde_chan *h, const float *wide_iq /* hos
                                       void *stream, void **d_out, size_t *out_stride);
 SONDE_API int  sonde_chan_process_c64_device(sonde_chan *h, const void *d_wide_iq /* device [n_in][2] float */,
                                              size_t n_in, void *stream, void **d_out, size_t *out_stride);
+/* The wideband chunk lives on ANOTHER GPU of the box (one front end feeding all GPUs): it is pulled over
+ * NVLink by the copy engine (cudaMemcpyPeerAsync on `stream`: no SMs), then channelised here.  The source buffer must
+ * stay untouched until the stream has passed the call; across processes it is mapped with CUDA IPC. */
+SONDE_API int  sonde_chan_process_c64_peer(sonde_chan *h, int src_device, const void *d_wide_iq /* on src_device */,
+                                           size_t n_in, void *stream, void **d_out, size_t *out_stride);
 /* int16 interleaved I,Q as SDR hardware delivers it; sample = i16 * scale */
 SONDE_API int  sonde_chan_process_s16(sonde_chan *h, const int16_t *wide_iq /* host [n_in][2] */, size_t n_in,
                                       float scale, void *stream, void **d_out, size_t *out_stride);

@@ -334,7 +334,7 @@ class BatchDecoder:
 # ------------------------------------------------------------------------------------------------
 # wideband channelizer (include/sonde_b200_channelizer.h)
 CHAN_EXPORTS = [
-    "sonde_chan_create", "sonde_chan_create_ex", "sonde_chan_taps_of", "sonde_chan_destroy", "sonde_chan_process_c64", "sonde_chan_process_c64_device",
+    "sonde_chan_create", "sonde_chan_create_ex", "sonde_chan_taps_of", "sonde_chan_destroy", "sonde_chan_process_c64", "sonde_chan_process_c64_device", "sonde_chan_process_c64_peer",
     "sonde_chan_process_s16", "sonde_chan_process_u8", "sonde_chan_num_taps", "sonde_chan_taps", "sonde_chan_steps",
     "sonde_chan_last_kernel_ms", "sonde_chan_last_error",
 ]
@@ -366,6 +366,7 @@ def _chan_lib():
         "sonde_chan_destroy": (None, [vp]),
         "sonde_chan_process_c64": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
         "sonde_chan_process_c64_device": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
+        "sonde_chan_process_c64_peer": (ctypes.c_int, [vp, ctypes.c_int, vp, sz, vp, pvp, psz]),
         "sonde_chan_process_s16": (ctypes.c_int, [vp, vp, sz, ctypes.c_float, vp, pvp, psz]),
         "sonde_chan_process_u8": (ctypes.c_int, [vp, vp, sz, vp, pvp, psz]),
         "sonde_chan_num_taps": (ctypes.c_int, [vp]),
@@ -443,6 +444,13 @@ class Channelizer:
 
     def process_c64_device(self, ptr: int, n_in: int, stream=0):
         return self._run(self.lib.sonde_chan_process_c64_device, ptr, n_in, stream)
+
+    def process_c64_peer(self, src_device: int, ptr: int, n_in: int, stream=0):
+        """the chunk is on another GPU (mapped with CUDA IPC across processes): copy-engine pull, then channelise"""
+        out, stride = ctypes.c_void_p(), ctypes.c_size_t()
+        self._ck(self.lib.sonde_chan_process_c64_peer(self.h, int(src_device), ptr, n_in, ctypes.c_void_p(stream or 0),
+                                                      ctypes.byref(out), ctypes.byref(stride)), "sonde_chan_process_c64_peer")
+        return out.value, int(stride.value), n_in // self.D * self.L
 
     def process_c64_host_ptr(self, ptr: int, n_in: int, stream=0):
         """raw host pointer (pinned memory for an asynchronous copy)"""

@@ -578,8 +578,10 @@ void sonde_chan_destroy(sonde_chan *h)
 	delete h;
 }
 
-/* kind: 0 = float2 on the device, 1 = float2 on the host, 2 = short2 on the host, 3 = uchar2 on the host */
-static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float scale, void *stream_, void **d_out, size_t *out_stride)
+/* kind: 0 = float2 on the device, 1 = float2 on the host, 2 = short2 on the host, 3 = uchar2 on the host,
+ * 4 = float2 on another device (`src_device`), pulled with the copy engine */
+static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float scale, void *stream_, void **d_out, size_t *out_stride,
+                    int src_device = -1)
 {
 	if (!h) return SONDE_ERR_ARG;
 	if (!src || !d_out || !out_stride || n_in == 0) return cfail(h, SONDE_ERR_ARG, "null argument or zero length");
@@ -599,10 +601,23 @@ static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float
 	if (kind == 0) {
 		to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(src), cp, n_in, h->S);
 	} else {
-		const size_t esz = kind == 1 ? sizeof(float2) : kind == 2 ? sizeof(short2) : sizeof(uchar2);
+		const size_t esz = (kind == 1 || kind == 4) ? sizeof(float2) : kind == 2 ? sizeof(short2) : sizeof(uchar2);
 		if (!h->d_in) CCK(cudaMalloc(&h->d_in, (size_t)h->cfg.max_in_len * sizeof(float2)));
-		CCK(cudaMemcpyAsync(h->d_in, src, n_in * esz, cudaMemcpyHostToDevice, st));
-		if (kind == 1)      to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(h->d_in), cp, n_in, h->S);
+		if (kind == 4) {
+			if (src_device != h->cfg.device) {
+				int can = 0;
+				CCK(cudaDeviceCanAccessPeer(&can, h->cfg.device, src_device));
+				if (can) {
+					const cudaError_t e = cudaDeviceEnablePeerAccess(src_device, 0);
+					if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cfail(h, SONDE_ERR_CUDA, "cudaDeviceEnablePeerAccess");
+					(void)cudaGetLastError();
+				}
+			}
+			CCK(cudaMemcpyPeerAsync(h->d_in, h->cfg.device, src, src_device, n_in * esz, st));
+		} else {
+			CCK(cudaMemcpyAsync(h->d_in, src, n_in * esz, cudaMemcpyHostToDevice, st));
+		}
+		if (kind == 1 || kind == 4) to_bf16_c64_kernel<<<blocks, 256, 0, st>>>(static_cast<const float2 *>(h->d_in), cp, n_in, h->S);
 		else if (kind == 2) to_bf16_s16_kernel<<<blocks, 256, 0, st>>>(static_cast<const short2 *>(h->d_in), cp, n_in, h->S, scale);
 		else                to_bf16_u8_kernel<<<blocks, 256, 0, st>>>(static_cast<const uchar2 *>(h->d_in), cp, n_in, h->S);
 	}
@@ -655,6 +670,10 @@ int sonde_chan_process_c64(sonde_chan *h, const float *wide_iq, size_t n_in, voi
 int sonde_chan_process_c64_device(sonde_chan *h, const void *d_wide_iq, size_t n_in, void *stream, void **d_out, size_t *out_stride)
 {
 	return chan_run(h, d_wide_iq, n_in, 0, 1.0f, stream, d_out, out_stride);
+}
+int sonde_chan_process_c64_peer(sonde_chan *h, int src_device, const void *d_wide_iq, size_t n_in, void *stream, void **d_out, size_t *out_stride)
+{
+	return chan_run(h, d_wide_iq, n_in, 4, 1.0f, stream, d_out, out_stride, src_device);
 }
 int sonde_chan_process_s16(sonde_chan *h, const int16_t *wide_iq, size_t n_in, float scale, void *stream, void **d_out, size_t *out_stride)
 {

@@ -474,7 +474,8 @@ def test_full_size_configs_replica_consistency_and_oracle(name):
     """The BASELINE configs at full per-GPU size (1024-2048 channels x 10 s = 480000 samples in 1 s buffers).
     Size-independent properties: the batch is NB distinct signals per type tiled over all channels, so
     (1) every replica must produce records bit-identical to its base channel — whatever CTA group, SM or lane of
-    the serial warps it landed on — and (2) each base channel's records equal the oracle's on the same signal."""
+    the serial warps it landed on — and (2) each base channel's records equal the oracle's on the same signal and those of
+    the compiled reference's decoder loop fed by the restated discriminator."""
     import torch
     C, type_of = FULL_CONFIGS[name]
     NB, L, nsec = 4, 48000, 10
@@ -518,11 +519,16 @@ def test_full_size_configs_replica_consistency_and_oracle(name):
             assert keys == first[src[c]][1], (name, c, "differs from its base channel", first[src[c]][0])
         n_ok += sum(int(r["ok"]) for r in frames[c])
     orc = reflib.OracleLib() if reflib.have_oracle() else None
+    ref = reflib.RefLib() if reflib.have_ref() else None
     if orc is not None:
         for (t, b), (c, keys) in first.items():
             rb = (synth.MODEMS[t].frame_bits + 7) // 8
             want = orc.frames_run_iq(t, base[t][b], L)
             assert keys == [rec_key(w, rb) for w in want], (name, t, b)
+            if ref is not None:
+                # and the UNMODIFIED reference's own decoder loop behind the restated discriminator (all types, AFSK included)
+                want_ref = ref.frames_run(t, orc.discriminate(base[t][b]), L)
+                assert keys == [rec_key(w, rb) for w in want_ref], (name, t, b, "compiled reference")
     print(f"{name}: {C} channels x {n} samples, {sum(len(f) for f in frames)} frame windows, {n_ok} pass their gate")
     assert n_ok > C
 
