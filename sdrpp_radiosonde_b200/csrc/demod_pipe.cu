@@ -60,6 +60,9 @@ constexpr int XS = T + 12;                           /* x row: 8 floats of slack
                                                         8 channel lanes' LDS.128 on distinct banks                 */
 constexpr int YM = 32;                               /* slots mirrored after the end of the y ring                */
 constexpr int QN = 244;                              /* paired FIR input, see q_phys(): 242 pairs, rows 16 B aligned */
+#ifndef DISC_ROLLED
+#define DISC_ROLLED 1
+#endif
 constexpr uint32_t ZSENT = 0x7fc5a5a5u;              /* s value of a sample that bypassed the AGC (agc.c:23)      */
 
 template <int P>
@@ -129,15 +132,31 @@ __device__ __forceinline__ void item_disc(smem_t<P> &sm, const demod_params &p, 
 	const int xs = k % NX, rs = k % NRAW;
 	const int ch = sm.chan[g];
 	const size_t rowoff = (size_t)sm.row[g] * p.row_stride + (size_t)k * T;
-	float xv[4][2];
+	bool zero = false;
 	/* x slot free = the AGC warp has consumed tile k-3.  This also guards the parity wait below: tile k-3 then has
 	 * landed, so rawfull[rs] is in tile k's phase or past it. */
 	if (k >= NX) flag_wait(&sm.ag_done, k - NX + 1, wacc, prof_on);
 	if (TMA) mbar_wait_t(&sm.rawfull[rs], (k / NRAW) & 1, wacc, prof_on);
 	if (IQ) {
-		float re[8], im[8], phs[8];
+		/* DISC_ROLLED: the four 64-sample pieces one after the other in a rolled loop (a quarter of the code: the parallel
+		 * warps stream through their straight-line bodies once per item and the two SMs of a TPC share instruction fetch)
+		 * instead of eight samples as one straight-line block */
 		float carry = 0.0f;
+		if (lane == 0) {
+			/* phase of the sample before the tile: the previous call's last sample, or the look-back sample */
+			if (k == 0) {
+				carry = p.st[ch].disc_prev;
+			} else {
+				const float2 pr = TMA ? sm.raw[rs][g][1] : __ldg(static_cast<const float2 *>(p.in) + rowoff - 1);
+				carry = det_phase(pr.x, pr.y);
+			}
+		}
+		float last = 0.0f;
+#if DISC_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
 		for (int i = 0; i < 4; i++) {
 			const int t = 2 * lane + 64 * i;
 			float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -150,59 +169,37 @@ __device__ __forceinline__ void item_disc(smem_t<P> &sm, const demod_params &p, 
 				if (t + 1 < n) { const float2 a = __ldg(src + 1); f.z = a.x; f.w = a.y; }
 			}
 			/* samples past the end of the buffer: (0, 0), phase 0 */
-			re[2 * i] = (t < n) ? f.x : 0.0f;         im[2 * i] = (t < n) ? f.y : 0.0f;
-			re[2 * i + 1] = (t + 1 < n) ? f.z : 0.0f; im[2 * i + 1] = (t + 1 < n) ? f.w : 0.0f;
-		}
-		det_phase_n<8>(re, im, phs);
-		float ph[4][2];
-#pragma unroll
-		for (int i = 0; i < 4; i++) { ph[i][0] = phs[2 * i]; ph[i][1] = phs[2 * i + 1]; }
-		if (lane == 0) {
-			/* phase of the sample before the tile: the previous call's last sample, or the look-back sample */
-			if (k == 0) {
-				carry = p.st[ch].disc_prev;
-			} else {
-				const float2 pr = TMA ? sm.raw[rs][g][1] : __ldg(static_cast<const float2 *>(p.in) + rowoff - 1);
-				carry = det_phase(pr.x, pr.y);
-			}
-		}
-#pragma unroll
-		for (int i = 0; i < 4; i++) {
+			const float re[2] = {(t < n) ? f.x : 0.0f, (t + 1 < n) ? f.z : 0.0f};
+			const float im[2] = {(t < n) ? f.y : 0.0f, (t + 1 < n) ? f.w : 0.0f};
+			float ph[2];
+			det_phase_n<2>(re, im, ph);
 			/* previous sample's phase: the neighbouring lane's second sample; lane 0 takes lane 31's of the piece before */
-			float up = __shfl_up_sync(FULL, ph[i][1], 1);
-			const float edge = (i == 0) ? carry : __shfl_sync(FULL, ph[i > 0 ? i - 1 : 0][1], 31);
-			if (lane == 0) up = edge;
-			xv[i][0] = disc_step(ph[i][0], up, p.fm_gain);
-			xv[i][1] = disc_step(ph[i][1], ph[i][0], p.fm_gain);
+			float up = __shfl_up_sync(FULL, ph[1], 1);
+			if (lane == 0) up = carry;
+			carry = __shfl_sync(FULL, ph[1], 31);
+			const float x0 = disc_step(ph[0], up, p.fm_gain), x1 = disc_step(ph[1], ph[0], p.fm_gain);
+			zero |= (t < n && x0 == 0.0f) || (t + 1 < n && x1 == 0.0f);
+			*reinterpret_cast<float2 *>(&sm.x[xs][g][t]) = make_float2(x0, x1);
+			/* the phase of the buffer's last sample is the next call's `previous phase` */
+			if (((n - 1) >> 6) == i) last = ((n - 1) & 1) ? ph[1] : ph[0];
 		}
-		/* the phase of the buffer's last sample is the next call's `previous phase` */
-		if (k == ntiles - 1 && (((n - 1) & 63) >> 1) == lane) {
-			float last = 0.0f;
-#pragma unroll
-			for (int i = 0; i < 4; i++)
-				if (((n - 1) >> 6) == i) last = ((n - 1) & 1) ? ph[i][1] : ph[i][0];
-			p.st[ch].disc_prev = last;
-		}
+		if (k == ntiles - 1 && (((n - 1) & 63) >> 1) == lane) p.st[ch].disc_prev = last;
 	} else {
 #pragma unroll
 		for (int i = 0; i < 4; i++) {
 			const int t = 2 * lane + 64 * i;
+			float x0, x1;
 			if (TMA) {
 				const float2 f = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(&sm.raw[rs][g][0]) + t);
-				xv[i][0] = f.x; xv[i][1] = f.y;
+				x0 = f.x; x1 = f.y;
 			} else {
 				const float *src = static_cast<const float *>(p.in) + rowoff + t;
-				xv[i][0] = (t < n) ? __ldg(src) : 0.0f;
-				xv[i][1] = (t + 1 < n) ? __ldg(src + 1) : 0.0f;
+				x0 = (t < n) ? __ldg(src) : 0.0f;
+				x1 = (t + 1 < n) ? __ldg(src + 1) : 0.0f;
 			}
+			zero |= (t < n && x0 == 0.0f) || (t + 1 < n && x1 == 0.0f);
+			*reinterpret_cast<float2 *>(&sm.x[xs][g][t]) = make_float2(x0, x1);
 		}
-	}
-	bool zero = false;
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		const int t = 2 * lane + 64 * i;
-		zero |= (t < n && xv[i][0] == 0.0f) || (t + 1 < n && xv[i][1] == 0.0f);
-		*reinterpret_cast<float2 *>(&sm.x[xs][g][t]) = make_float2(xv[i][0], xv[i][1]);
 	}
 	if (__any_sync(FULL, zero) && lane == 0) atomicOr(&sm.zflag[xs], 1);
 	warp_sync_hard();
