@@ -402,6 +402,29 @@ def main():
         c1.record()
         torch.cuda.synchronize()
         e2e["link_gbs"] = 5 * C * L * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        if world > 1:
+            # what the HOST can deliver when every rank copies at once: all ranks start the same bare copy together, from
+            # ordinary pinned memory and from write-combined pinned memory (no snoop traffic); gathered per rank below
+            from cuda.bindings import runtime as cudart_
+            cur_stream = torch.cuda.current_stream().cuda_stream
+
+            def all_at_once(host_ptr):
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(5):
+                    cudart_.cudaMemcpyAsync(dst.data_ptr(), host_ptr, C * L * 8, cudart_.cudaMemcpyKind.cudaMemcpyHostToDevice, cur_stream)
+                a1.record()
+                torch.cuda.synchronize()
+                return 5 * C * L * 8 / (a0.elapsed_time(a1) * 1e-3) / 1e9
+            e2e["link_all"] = all_at_once(pins[0].ptr)
+            e2e["link_all_wc"] = 0.0
+            err, wc_ptr = cudart_.cudaHostAlloc(C * L * 8, cudart_.cudaHostAllocWriteCombined)
+            if int(err) == 0:
+                e2e["link_all_wc"] = all_at_once(int(wc_ptr))
+                cudart_.cudaFreeHost(wc_ptr)
+            else:
+                barrier()
         del dst
         dec2.close()
         for pb in pins:
@@ -627,9 +650,15 @@ def main():
                           (wide["t"] * 1e3) if wide and "t" in wide else 0.0],
                          dtype=torch.float64, device="cuda")
     tot = torch.tensor([frames, ok], dtype=torch.float64, device="cuda")
+    link_all = None
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        if e2e and "link_all" in e2e:
+            mine = torch.tensor([e2e["link_all"], e2e["link_all_wc"]], dtype=torch.float64, device="cuda")
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            link_all = [[round(float(v[0]), 1) for v in every], [round(float(v[1]), 1) for v in every]]
     ms_max, e2e_ms_max = float(t_all[0]), float(t_all[1])
     frames, ok = int(tot[0]), int(tot[1])
 
@@ -677,6 +706,10 @@ def main():
                            "h2d_link_gbs_measured": e2e["link_gbs"],
                            "note": "bounded by the host link: every step moves C*L*8 bytes of complex64 IQ over PCIe; "
                                    "h2d_link_gbs_measured is a bare pinned-memory copy of the same buffer on rank 0"}
+            if link_all:
+                line["e2e"]["h2d_link_gbs_all_ranks_at_once"] = {"pinned": link_all[0], "write_combined": link_all[1],
+                    "note": "every rank runs the same bare H2D copy at the same time: what the host side of this box delivers "
+                            "per GPU when all GPUs are fed at once (the e2e figure cannot exceed it)"}
             t16 = float(t_all[4])
             line["e2e_s16"] = {"error": e2e["err16"]} if e2e.get("err16") or t16 <= 0 else {"value": world * args.steps * C * L / (t16 * 1e-3) / 1e6, "unit": UNIT,
                                "h2d_bytes_per_step": C * L * 4, "ms_per_step": t16 / args.steps,

@@ -637,6 +637,8 @@ demod_pipe_kernel(const demod_params p, const int group_base, const int n_here)
 			warp_sync_hard();
 			if (k >= 1 && lane == 0) flag_publish(&sm.tm_rel, k);      /* tiles 0 .. k-1 are consumed */
 		}
+		/* without the soft-symbol tap the fast rounds do not count symbols: one per bit of this call */
+		if (!SOFT) tr.nsoft = (int)(tr.nb - (uint32_t)nbits0);
 		n_rounds = tr.nsoft;
 		if (own) {
 			demod_state &st = p.st[ch];

@@ -479,6 +479,7 @@ static int apply_active(sonde_b200 *h)
 	std::vector<int32_t> active, gchan, gtype;
 	compute_active(h, active);
 	CK(cudaStreamSynchronize(h->stream));        /* launches in flight still read the old tables and group counts */
+	CK(cudaStreamSynchronize(h->fstream));       /* ... and a framer kernel on its own stream reads d_active */
 	build_groups(h, &active, gchan, gtype);
 	h->gchan_host = gchan;
 	if (!gchan.empty()) {
@@ -586,7 +587,7 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 		const char *e = getenv("SONDE_PW_MASK");
 		return e ? (uint32_t)strtoul(e, nullptr, 16) : 0u;
 	}();
-	static const uint32_t kPwMask[3] = {0xCCCFCCu /* RS41 */, 0xCCDDCCu /* DFM, iMS-100, MRZ-N1 */, 0xCCCCCCu /* M10/M20 */};
+	static const uint32_t kPwMask[3] = {0xCCCFCCu /* RS41 */, 0xCCCFCCu /* DFM, iMS-100, MRZ-N1 */, 0xCCEECCu /* M10/M20: two PW warps beside the AGC warp */};
 	const int par = (int)(h->n_issued & 1);
 	dp.nbits_out = h->d_nbits[par];
 	static const int tpc_env = getenv("SONDE_TPC_PAIRS") ? atoi(getenv("SONDE_TPC_PAIRS")) : -1;     /* experiment switch */
@@ -857,7 +858,16 @@ static int pull_counts(sonde_b200 *h, int par)
 }
 
 /* AUTO policy (SD/decode.c:174-224): an undetermined channel locks to the first decoder, in the reference's
- * order, that produced a frame passing its gate in this call; the losers are switched off for later calls. */
+ * order, that produced a frame passing its gate in this call; the losers are switched off for later calls.
+ *
+ * Deliberate differences from the reference's loop, which decides inside a buffer, per decode() call:
+ *   - granularity: the decision is taken per process call (buffer), at fetch time;
+ *   - criterion: the reference locks when SondeData.fields != 0 — for RS41 any CRC-valid subframe, even when the
+ *     Reed-Solomon decode of the frame failed — and, if several decoders report data in one iteration, the LAST
+ *     set_active_decoder() call wins (decode.c:242-251).  Here the lock needs a frame that passes the decoder's FEC /
+ *     checksum gate (rec.ok > 0: at least as strict) and the FIRST decoder in the reference's order wins.  On a signal
+ *     that only one decoder can parse — every real transmission — both rules lock to the same decoder; the stricter gate
+ *     can delay the lock of a heavily corrupted RS41 stream by the frames whose RS decode fails. */
 static int auto_update(sonde_b200 *h)
 {
 	bool changed = false;

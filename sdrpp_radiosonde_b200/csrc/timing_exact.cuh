@@ -110,6 +110,19 @@ __device__ __forceinline__ int tmx_literal_round(tmx_regs &t, const float *y, co
 	return maxslots;
 }
 
+/* retime() + update_estimate() of a fast round: as tmx_retime(), with the mid-symbol value passed in and without the
+ * state writes a completed fast round makes redundant (target stays 1; interm is dead after a symbol, gfsk.c:73,93,99) */
+__device__ __forceinline__ void tmx_retime_fast(tmx_regs &t, const float ph, const float yv, const float interm, const tmx_consts &c)
+{
+	const float err = (fmul(yv, t.prev) < 0.0f) ? fmul(fsub(yv, t.prev), interm) : 0.0f;
+	t.prev = yv;
+	float fd = fsub(t.freq, c.center);
+	t.phase = fsub(ph, fsub(2.0f, max_nan(-2.0f, min_nan(2.0f, fmul(err, c.alpha)))));
+	fd = fadd(fd, fmul(err, c.beta));
+	fd = max_nan(-c.max_fdev, min_nan(c.max_fdev, fd));
+	t.freq = fadd(c.center, fd);
+}
+
 /* All rounds of one lane that start at slot `sabs` (ring position `sring`) and whose candidate slots end before slot
  * `end`: W = KS0 + NS - 1 slots must be readable from the start of each round (the ring has a mirror of its first
  * slots behind its last one).
@@ -117,7 +130,15 @@ __device__ __forceinline__ int tmx_literal_round(tmx_regs &t, const float *y, co
  * Shape of the loop (ncu on a first version that handled the two rare events inside the round showed a quarter of
  * every round in BSSY/BSYNC reconvergence, branch resolution and predicate latency): the inner loop is straight-line
  * code with one backward branch; a lane that meets a rare event (the round does not fit the windows -> literal round;
- * a 32-bit word of bits is complete -> store it) leaves the inner loop, handles it and re-enters. */
+ * a 32-bit word of bits is complete -> store it) leaves the inner loop, handles it and re-enters.
+ *
+ * Round 2, second pass (ncu: 71 SASS instructions per round, the half after the add chain issue-bound; and lanes =
+ * channels whose 32-bit words of bits complete at different rounds left the loop one by one, after which the warp ran
+ * the loop body once per straggler).  Now: the inner loop holds TWO rounds with the candidate registers alternating
+ * between two sets (the six loop-carried MOVs of the one-round form disappear); the bookkeeping a completed fast round
+ * implies is left out of it (target is 1 on entry and stays 1, the bit and soft-symbol counts advance by the number of
+ * rounds); new bits are funnel-shifted into a 64-bit accumulator and a stretch ends after at most 32 rounds — a count
+ * that is the same in every lane — so that the completed word is stored AFTER the loop by all lanes together. */
 template <int KM0, int NM, int KS0, int NS, int RING, bool SOFT>
 __device__ __forceinline__ void tmx_run(tmx_regs &t, const float *yrow, int &sabs, int &sring, const int end,
                                         const tmx_consts &c, uint8_t *ring, const uint32_t ring_mask, float *soft,
@@ -132,70 +153,80 @@ __device__ __forceinline__ void tmx_run(tmx_regs &t, const float *yrow, int &sab
 	/* The candidate FIR outputs of a round are fetched at the END of the round before it (as soon as its first slot is
 	 * known) and carried in registers: the loads are in flight during the loop branch, and ptxas cannot turn them into
 	 * loads predicated on this round's comparisons, which would put the shared-memory latency behind the add chain. */
-	float ymc[NM], ysc[NS];
-	auto fetch = [&](const int at) {
+	float ymA[NM], ysA[NS], ymB[NM], ysB[NS];
+	auto fetch = [&](float (&ym)[NM], float (&ys)[NS], const int at) {
 		const uint32_t ya = ybase + 4u * (uint32_t)at;
 #pragma unroll
-		for (int j = 0; j < NM; j++) ymc[j] = lds_f32(ya + 4u * (KM0 - 1 + j));   /* slot k (1-based) reads y[k - 1] */
+		for (int j = 0; j < NM; j++) ym[j] = lds_f32(ya + 4u * (KM0 - 1 + j));   /* slot k (1-based) reads y[k - 1] */
 #pragma unroll
-		for (int j = 0; j < NS; j++) ysc[j] = lds_f32(ya + 4u * (KS0 - 1 + j));
+		for (int j = 0; j < NS; j++) ys[j] = lds_f32(ya + 4u * (KS0 - 1 + j));
 	};
-	/* The inner loop is a do-while with ONE conditional backward branch whose predicate (this round fits, another
-	 * round may start, no word of bits completes) is known long before the branch: a branch that has to wait for a
-	 * predicate computed just before it costs the lane ~12 cycles. */
+	int room = 0;                                    /* fast rounds this stretch may still run (32 at its start) */
+	uint32_t acc_hi = 0;                             /* bits shifted out of t.acc during the stretch */
+	/* one fast round on the candidates (ymc, ysc); prefetches the next round's into (ymn, ysn).
+	 * 1: the round does not fit the windows, nothing consumed; 2: consumed, but no further round may start here; 0: go on */
+	auto round = [&](const float (&ymc)[NM], const float (&ysc)[NS], float (&ymn)[NM], float (&ysn)[NS]) -> int {
+		/* the reference's chain of adds */
+		float p[W + 1];
+		p[0] = t.phase;
+#pragma unroll
+		for (int i = 1; i <= W; i++) p[i] = fadd(p[i - 1], t.freq);
+		const bool ok = p[KM0 - 1] < 1.0f && p[KM0 + NM - 1] >= 1.0f && p[KS0 - 1] < 2.0f && p[W] >= 2.0f;
+		/* earliest slot at or above the threshold wins (timing.c:35) */
+		float ym = ymc[NM - 1];
+#pragma unroll
+		for (int j = NM - 2; j >= 0; j--) ym = (p[KM0 + j] >= 1.0f) ? ymc[j] : ym;
+		float ys = ysc[NS - 1], pl = p[W];
+		int ks = W;
+#pragma unroll
+		for (int j = NS - 2; j >= 0; j--) {
+			const bool hit = p[KS0 + j] >= 2.0f;
+			ys = hit ? ysc[j] : ys;
+			pl = hit ? p[KS0 + j] : pl;
+			ks = hit ? KS0 + j : ks;
+		}
+		if (__builtin_expect(!ok, 0)) return 1;
+		left -= ks;
+		sring += ks;
+		sring = (int)min((unsigned)sring, (unsigned)(sring - RING));      /* wrap without a predicate */
+		room--;
+		const bool again = (left | (room - 1)) >= 0;                      /* left >= 0 and room >= 1 */
+		fetch(ymn, ysn, sring);                          /* next round's candidates (harmless if there is no next round) */
+		tmx_retime_fast(t, pl, ys, ym, c);
+		acc_hi = __funnelshift_l(t.acc, acc_hi, 1);                       /* (hi:lo) = (hi:lo) << 1 | bit */
+		t.acc = __funnelshift_l(ys > 0.0f ? 0x80000000u : 0u, t.acc, 1);
+		if (SOFT) {
+			if (soft && t.nsoft < soft_cap) soft[t.nsoft] = ys;
+			t.nsoft++;
+		}
+		return again ? 0 : 2;
+	};
 	if (left >= 0) {
-		fetch(sring);
 		for (;;) {
-			int ev;                                  /* 0: out of slots, 1: literal round needed, 2: word of bits complete */
-			for (;;) {
-				const bool word = ((t.nb + 1u) & 31u) == 0u;
-				/* the reference's chain of adds */
-				float p[W + 1];
-				p[0] = t.phase;
-#pragma unroll
-				for (int i = 1; i <= W; i++) p[i] = fadd(p[i - 1], t.freq);
-				const bool ok = t.target == 1.0f && p[KM0 - 1] < 1.0f && p[KM0 + NM - 1] >= 1.0f && p[KS0 - 1] < 2.0f &&
-				                p[W] >= 2.0f;
-				/* earliest slot at or above the threshold wins (timing.c:35) */
-				float ym = ymc[NM - 1];
-#pragma unroll
-				for (int j = NM - 2; j >= 0; j--) ym = (p[KM0 + j] >= 1.0f) ? ymc[j] : ym;
-				float ys = ysc[NS - 1], pl = p[W];
-				int ks = W;
-#pragma unroll
-				for (int j = NS - 2; j >= 0; j--) {
-					const bool hit = p[KS0 + j] >= 2.0f;
-					ys = hit ? ysc[j] : ys;
-					pl = hit ? p[KS0 + j] : pl;
-					ks = hit ? KS0 + j : ks;
+			int ev = 1;                              /* 1: literal round needed; else: stretch over */
+			if (t.target == 1.0f) {                  /* a fast round starts at a symbol boundary */
+				room = 32;
+				fetch(ymA, ysA, sring);
+				for (;;) {
+					int r = round(ymA, ysA, ymB, ysB);
+					if (__builtin_expect(r != 0, 0)) { ev = r; break; }
+					r = round(ymB, ysB, ymA, ysA);
+					if (__builtin_expect(r != 0, 0)) { ev = r; break; }
 				}
-				if (__builtin_expect(!ok, 0)) { ev = 1; break; }
-				left -= ks;
-				sring += ks;
-				sring = (int)min((unsigned)sring, (unsigned)(sring - RING));      /* wrap without a predicate */
-				const bool again = left >= 0 && !word;
-				fetch(sring);                            /* next round's candidates (harmless if there is no next round) */
-				t.interm = ym;
-				tmx_retime(t, pl, ys, c);
-				t.acc = (t.acc << 1) | (ys > 0.0f ? 1u : 0u);
-				if (SOFT) {
-					if (soft && t.nsoft < soft_cap) soft[t.nsoft] = ys;
+				/* one bit per completed round; with at most 31 bits pending and 32 new ones exactly one word can be complete */
+				const uint32_t pend = (t.nb & 31u) + (uint32_t)(32 - room);
+				t.nb += (uint32_t)(32 - room);
+				if (pend >= 32u) {
+					const uint32_t word = __funnelshift_r(t.acc, acc_hi, pend - 32u);
+					*reinterpret_cast<uint32_t *>(ring + ((((t.nb - pend) >> 3)) & ring_mask)) = __byte_perm(word, 0, 0x0123);
 				}
-				t.nsoft++;
-				t.nb++;
-				if (__builtin_expect(again, 1)) continue;
-				ev = word ? 2 : 0;
-				break;
 			}
-			if (ev == 2) {
-				*reinterpret_cast<uint32_t *>(ring + (((t.nb - 32u) >> 3) & ring_mask)) = __byte_perm(t.acc, 0, 0x0123);
-			} else if (ev == 1) {
+			if (ev == 1) {
 				n_slow++;
 				const int used = tmx_literal_round<SOFT>(t, yrow + sring, W, c, ring, ring_mask, soft, soft_cap);
 				left -= used;
 				sring += used;
 				sring = (sring >= RING) ? sring - RING : sring;
-				fetch(sring);
 			}
 			if (left < 0) break;
 		}

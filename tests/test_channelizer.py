@@ -199,6 +199,14 @@ def test_channelizer_entry_points_agree_and_reject_bad_arguments():
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
     assert np.array_equal(outs[1].view(np.uint32), outs[2].view(np.uint32))
     assert np.abs(outs[0]).max() > 0
+    # the peer entry point (source buffer on "another" GPU, here device 0 itself: same copy-engine path)
+    ch = capi.Channelizer(freqs, D, n_in)
+    xd = torch.view_as_real(torch.from_numpy(xf)).cuda()
+    ptr, stride, m = ch.process_c64_peer(0, xd.data_ptr(), n_in)
+    torch.cuda.synchronize()
+    peer = capi.device_view(ptr, (C, stride, 2))[:, :m].cpu().numpy().copy()
+    ch.close()
+    assert np.array_equal(peer.view(np.uint32), outs[2].view(np.uint32))
 
     # 8-bit offset-binary IQ == the float entry point on (u8 - 127.5) / 128
     u8 = rng.integers(0, 256, size=(n_in, 2)).astype(np.uint8)

@@ -1,0 +1,7 @@
+cd $GRAFT_REPO_ROOT
+run() { for m in $2; do echo "=== type $1 mask $m"; SONDE_PW_MASK=$m timeout 60 python tools/stalls.py $1 2>&1 | tail -6 | grep -v "PW last\|rounds"; done; }
+run 2 "CCECCC CEECCC CCEEEC CCEEEE"
+echo "=== full gpu tests"
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+P='import sys,json; d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frame_kernel_ms"], d["value"])'
+for c in 2 3 4 5; do echo "=== cfg $c"; timeout 300 python bench.py --config $c --seconds 2 --steps 20 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "$P"; done
