@@ -52,8 +52,16 @@ namespace {
 
 using namespace pipe;
 
-constexpr int W_TM = 0, W_AG = 1, W_LD = 4;          /* warp ids of the single-warp roles (SMSP = id % 4)        */
-constexpr uint32_t ROLE_MASK = (1u << W_TM) | (1u << W_AG) | (1u << W_LD);
+/* AGC_SPLIT 1 puts the bias and the level recurrence on two warps (A1, A2).  Measured and NOT adopted (exp47, tools/ubench/
+ * ubench4/5): alone on an SM the bias loop runs at 13.5 cycles/sample (its dependent chain is 3 x 4.04 = 12.1), inside the
+ * kernel at 19 whether fused with the level recurrence or not, because any second warp on its SMSP — the level warp as
+ * much as a parallel-work warp — costs every dependent operation about 1.5 cycles; giving A1 an SMSP of its own would
+ * take issue capacity from the parallel warps, which are the bound.  RS41 0.644 ms split vs 0.631 fused, M10 0.98 vs 0.85. */
+#ifndef AGC_SPLIT
+#define AGC_SPLIT 0
+#endif
+constexpr int W_TM = 0, W_AG = 1, W_LD = 4, W_A2 = 5; /* warp ids of the single-warp roles (SMSP = id % 4)       */
+constexpr uint32_t ROLE_MASK = (1u << W_TM) | (1u << W_AG) | (1u << W_LD) | (AGC_SPLIT ? (1u << W_A2) : 0u);
 constexpr int NRAW = 3, NSV = 2, NY = 3;             /* ring depths in tiles (NX = 3 from pipe_common)            */
 constexpr int RAWS = T + 2;                          /* raw row: 2 samples of look-back + the tile                */
 constexpr int XS = T + 12;                           /* x row: 8 floats of slack for the AGC prefetch; 268 % 32 = 12 keeps the
@@ -81,8 +89,9 @@ struct smem_t {
 	/* mbarriers: only where the waiter is one sequential warp (LD: rawfree, AG: xfull / svfree, TM: yfull) or the
 	 * wait is guarded (rawfull).  A parity wait passes falsely when the barrier is a whole phase behind, and the PW
 	 * items are not sequential waiters, so what they wait for is published as monotonic counters instead. */
-	unsigned long long rawfull[NRAW], rawfree[NRAW], xfull[NX], svfree[NSV], yfull[NY];
-	int ag_done;                         /* tiles the AGC warp has finished (x slot consumed, s / v written)          */
+	unsigned long long rawfull[NRAW], rawfree[NRAW], xfull[NX], svfree[NSV], vfree[NSV], yfull[NY];
+	int ag_done;                         /* tiles whose s AND v are written (the fused warp, or A2 when the AGC is split) */
+	int a1_done;                         /* tiles the bias warp has finished (x slot consumed, s written)              */
 	int tm_rel;                          /* y tiles the timing warp has released                                     */
 	int a_done[G];                       /* per channel: tiles whose gain stage + head copy are done                  */
 	int s4_done[G][2];                   /* per channel and tile parity: tiles whose FIR is done                     */
@@ -135,7 +144,7 @@ __device__ __forceinline__ void item_disc(smem_t<P> &sm, const demod_params &p, 
 	bool zero = false;
 	/* x slot free = the AGC warp has consumed tile k-3.  This also guards the parity wait below: tile k-3 then has
 	 * landed, so rawfull[rs] is in tile k's phase or past it. */
-	if (k >= NX) flag_wait(&sm.ag_done, k - NX + 1, wacc, prof_on);
+	if (k >= NX) flag_wait(AGC_SPLIT ? &sm.a1_done : &sm.ag_done, k - NX + 1, wacc, prof_on);
 	if (TMA) mbar_wait_t(&sm.rawfull[rs], (k / NRAW) & 1, wacc, prof_on);
 	if (IQ) {
 		/* DISC_ROLLED: the four 64-sample pieces one after the other in a rolled loop (a quarter of the code: the parallel
@@ -296,7 +305,10 @@ __device__ __forceinline__ void item_fir(smem_t<P> &sm, const demod_params &p, c
 		}
 	}
 	warp_sync_hard();
-	if (lane == 0) mbar_arrive(&sm.svfree[ss]);
+	if (lane == 0) {
+		mbar_arrive(&sm.svfree[ss]);
+		if (AGC_SPLIT) mbar_arrive(&sm.vfree[ss]);
+	}
 	/* head = the last 48 inputs before this tile: a_h_prev[256 + m], kept as the .y of pair 192 + m (straight-line on
 	 * purpose, see warp_sync_hard) */
 	static_assert(SONDE_FIR_HIST == 48, "two entries for the first 16 lanes, one for the others");
@@ -495,6 +507,87 @@ __device__ __forceinline__ void agc_tile(const float *__restrict__ x, float *__r
 	}
 }
 
+/* ---- split AGC (AGC_SPLIT): one recurrence per warp ------------------------------------------------------------------
+ * A1  s = x - bias ; bias = bias * 0.99 + s * 0.01        (3 dependent operations per sample)
+ * A2  v = avg      ; avg  = avg * 0.999 + |s| * 0.001     (2), one tile behind A1, reading s from shared memory
+ * In one warp the two chains share an in-order instruction stream and neither runs at its own latency (18.6 busy
+ * cycles/sample with nothing else on the SM); on two warps each does.  Same register rotation as agc_tile: a block of 8 is
+ * stored only after the next one has been computed. */
+struct rec_block {
+	float4 o0, o1;
+};
+template <class F>
+__device__ __forceinline__ void rec_tile(const float *__restrict__ in, float *__restrict__ out, const int n, float &st, F f)
+{
+	const int nb = n >> 3;                       /* whole blocks of 8 */
+	int i = 0;
+	if (nb > 0) {
+		const float4 *ip = reinterpret_cast<const float4 *>(in);
+		float4 xa = ip[0], xb = ip[1];
+		rec_block A, B, C;
+		auto blk = [&](rec_block &o) {
+			o.o0.x = f(xa.x, st); o.o0.y = f(xa.y, st); o.o0.z = f(xa.z, st); o.o0.w = f(xa.w, st);
+			o.o1.x = f(xb.x, st); o.o1.y = f(xb.y, st); o.o1.z = f(xb.z, st); o.o1.w = f(xb.w, st);
+		};
+		auto put = [&](const int at, const rec_block &o) {
+			*reinterpret_cast<float4 *>(out + at) = o.o0;
+			*reinterpret_cast<float4 *>(out + at + 4) = o.o1;
+		};
+		int b = 0;
+		{
+			const float4 na = ip[2], nbv = ip[3];      /* rows have slack behind them: the prefetch may run past n */
+			blk(A);
+			xa = na; xb = nbv;
+		}
+		for (b = 1; b + 2 < nb; b += 3) {
+			{ const float4 na = ip[2 * b + 2], nbv = ip[2 * b + 3]; blk(B); put(8 * (b - 1), A); xa = na; xb = nbv; }
+			{ const float4 na = ip[2 * b + 4], nbv = ip[2 * b + 5]; blk(C); put(8 * b, B); xa = na; xb = nbv; }
+			{ const float4 na = ip[2 * b + 6], nbv = ip[2 * b + 7]; blk(A); put(8 * (b + 1), C); xa = na; xb = nbv; }
+		}
+		if (b < nb) {
+			const float4 na = ip[2 * b + 2], nbv = ip[2 * b + 3];
+			blk(B); put(8 * (b - 1), A);
+			xa = na; xb = nbv;
+			if (b + 1 < nb) { blk(C); put(8 * b, B); put(8 * (b + 1), C); }
+			else put(8 * b, B);
+		} else {
+			put(8 * (b - 1), A);
+		}
+		i = nb << 3;
+	}
+	for (; i < n; i++) out[i] = f(in[i], st);
+}
+
+__device__ __forceinline__ void bias_tile(const float *__restrict__ x, float *__restrict__ s, const int n, float &bias, const bool check_zero)
+{
+	const float b1 = fsub(1.0f, 0.01f), b0 = 0.01f;
+	if (!check_zero) {
+		rec_tile(x, s, n, bias, [=](const float xi, float &b) { const float o = fsub(xi, b); b = fadd(fmul(b, b1), fmul(o, b0)); return o; });
+	} else {
+		for (int i = 0; i < n; i++) {                 /* exact zeros bypass the AGC (agc.c:23) */
+			const float xi = x[i];
+			if (xi == 0.0f) { s[i] = __uint_as_float(ZSENT); continue; }
+			const float o = fsub(xi, bias);
+			bias = fadd(fmul(bias, b1), fmul(o, b0));
+			s[i] = o;
+		}
+	}
+}
+__device__ __forceinline__ void level_tile(const float *__restrict__ s, float *__restrict__ v, const int n, float &avg, const bool check_zero)
+{
+	const float g1 = fsub(1.0f, 0.001f), g0 = 0.001f;
+	if (!check_zero) {
+		rec_tile(s, v, n, avg, [=](const float si, float &a) { const float o = a; a = fadd(fmul(a, g1), fmul(fabsf(si), g0)); return o; });
+	} else {
+		for (int i = 0; i < n; i++) {
+			const float si = s[i];
+			v[i] = avg;
+			if (__float_as_uint(si) == ZSENT) continue;
+			avg = fadd(fmul(avg, g1), fmul(fabsf(si), g0));
+		}
+	}
+}
+
 template <int P, int KM0, int NM, int KS0, int NS, bool IQ, bool SOFT, bool TMA>
 __global__ void __maxnreg__(64)
 demod_pipe_kernel(const demod_params p, const int group_base, const int n_here)
@@ -526,9 +619,11 @@ demod_pipe_kernel(const demod_params p, const int group_base, const int n_here)
 		sm.qnext = 0;
 		for (int i = 0; i < NRAW; i++) { mbar_init(&sm.rawfull[i], 1); mbar_init(&sm.rawfree[i], gact); }
 		for (int i = 0; i < NX; i++) { mbar_init(&sm.xfull[i], gact); sm.zflag[i] = 0; }
-		for (int i = 0; i < NSV; i++) { mbar_init(&sm.svfree[i], gact); sm.svz[i] = 0; }
+		/* split AGC: s is read by the gain stage of every channel AND by the level warp, v by the gain stage only */
+		for (int i = 0; i < NSV; i++) { mbar_init(&sm.svfree[i], gact + (AGC_SPLIT ? 1 : 0)); mbar_init(&sm.vfree[i], gact); sm.svz[i] = 0; }
 		for (int i = 0; i < NY; i++) mbar_init(&sm.yfull[i], gact);
 		sm.ag_done = 0;
+		sm.a1_done = 0;
 		sm.tm_rel = 0;
 		for (int g = 0; g < G; g++) { sm.a_done[g] = 0; sm.s4_done[g][0] = 0; sm.s4_done[g][1] = 0; }
 	}
@@ -564,7 +659,46 @@ demod_pipe_kernel(const demod_params p, const int group_base, const int n_here)
 			}
 		}
 		return;
-	} else if (warp == W_AG) {
+	} else if (AGC_SPLIT && warp == W_AG) {
+		/* =============================== A1: the bias recurrence ============================ */
+		const int g = lane & (G - 1);
+		const bool own = lane < gact;
+		float bias = own ? p.st[chans[g]].agc_bias : 0.0f;
+		for (int k = 0; k < ntiles; k++) {
+			const int n = min(T, L - k * T);
+			const int xs = k % NX, ss = k % NSV;
+			mbar_wait_t(&sm.xfull[xs], (k / NX) & 1, wacc[0], prof_on);
+			if (k >= NSV) mbar_wait_t(&sm.svfree[ss], ((k / NSV) - 1) & 1, wacc[1], prof_on);
+			const int z = sm.zflag[xs];
+			if (own) bias_tile(sm.x[xs][g], sm.s[ss][g], n, bias, z != 0);
+			warp_sync_hard();
+			if (lane == 0) {
+				sm.svz[ss] = z;
+				sm.zflag[xs] = 0;
+				flag_publish(&sm.a1_done, k + 1);
+			}
+		}
+		if (own) p.st[chans[g]].agc_bias = bias;
+	} else if (AGC_SPLIT && warp == W_A2) {
+		/* =============================== A2: the level recurrence, one tile behind A1 ====== */
+		const int g = lane & (G - 1);
+		const bool own = lane < gact;
+		float avg = own ? p.st[chans[g]].agc_avg : 5.0f;
+		for (int k = 0; k < ntiles; k++) {
+			const int n = min(T, L - k * T);
+			const int ss = k % NSV;
+			flag_wait(&sm.a1_done, k + 1, wacc[0], prof_on);
+			if (k >= NSV) mbar_wait_t(&sm.vfree[ss], ((k / NSV) - 1) & 1, wacc[1], prof_on);
+			const int z = sm.svz[ss];
+			if (own) level_tile(sm.s[ss][g], sm.v[ss][g], n, avg, z != 0);
+			warp_sync_hard();
+			if (lane == 0) {
+				mbar_arrive(&sm.svfree[ss]);                 /* this warp is done reading s */
+				flag_publish(&sm.ag_done, k + 1);
+			}
+		}
+		if (own) p.st[chans[g]].agc_avg = avg;
+	} else if (!AGC_SPLIT && warp == W_AG) {
 		/* =============================== AG: the two AGC recurrences ======================== */
 		const int g = lane & (G - 1);
 		const bool own = lane < gact;
