@@ -366,7 +366,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         nbuf = min(n_chunks, 3)
-        pins = [capi.PinnedBuffer((C, L), np.complex64) for _ in range(nbuf)]
+        # write-combined staging: the host only writes it, and with several GPUs fed at once it is what the host side delivers best
+        pins = [capi.PinnedBuffer((C, L), np.complex64, write_combined=True) for _ in range(nbuf)]
         for k, pb in enumerate(pins):
             pb.array[...] = host_iq[:, k * L:(k + 1) * L]
         dec2 = capi.BatchDecoder(sig_types, L, device=local_rank)
@@ -417,21 +418,28 @@ def main():
                 a1.record()
                 torch.cuda.synchronize()
                 return 5 * C * L * 8 / (a0.elapsed_time(a1) * 1e-3) / 1e9
-            e2e["link_all"] = all_at_once(pins[0].ptr)
+            try:
+                e2e["link_all"] = all_at_once(pins[0].ptr)
+            except Exception as ex:                      # informational probe: never lose the main line over it
+                print(f"all-ranks link probe failed: {type(ex).__name__}: {ex}", file=sys.stderr)
+                e2e["link_all"] = 0.0
             e2e["link_all_wc"] = 0.0
-            err, wc_ptr = cudart_.cudaHostAlloc(C * L * 8, cudart_.cudaHostAllocWriteCombined)
-            if int(err) == 0:
-                e2e["link_all_wc"] = all_at_once(int(wc_ptr))
-                cudart_.cudaFreeHost(wc_ptr)
-            else:
-                barrier()
+            try:
+                err, wc_ptr = cudart_.cudaHostAlloc(C * L * 8, cudart_.cudaHostAllocDefault)
+                if int(err) == 0:
+                    e2e["link_all_wc"] = all_at_once(int(wc_ptr))
+                    cudart_.cudaFreeHost(wc_ptr)
+                else:
+                    barrier()
+            except Exception as ex:
+                print(f"write-combined link probe failed: {type(ex).__name__}: {ex}", file=sys.stderr)
         del dst
         dec2.close()
         for pb in pins:
             pb.free()
         try:
             # the same loop through the int16 entry point (half the PCIe bytes; informational, `e2e` stays complex64)
-            pins16 = [capi.PinnedBuffer((C, L, 2), np.int16) for _ in range(nbuf)]
+            pins16 = [capi.PinnedBuffer((C, L, 2), np.int16, write_combined=True) for _ in range(nbuf)]
             for k, pb in enumerate(pins16):
                 blk = host_iq[:, k * L:(k + 1) * L]
                 pb.array[..., 0] = np.clip(np.round(blk.real * 16384.0), -32768, 32767)
@@ -705,9 +713,9 @@ def main():
                            "h2d_gbs_achieved": e2e["h2d"] / (e2e_ms_max / args.steps * 1e-3) / 1e9,
                            "h2d_link_gbs_measured": e2e["link_gbs"],
                            "note": "bounded by the host link: every step moves C*L*8 bytes of complex64 IQ over PCIe; "
-                                   "h2d_link_gbs_measured is a bare pinned-memory copy of the same buffer on rank 0"}
+                                   "h2d_link_gbs_measured is a bare copy of the same (write-combined pinned) buffer on rank 0"}
             if link_all:
-                line["e2e"]["h2d_link_gbs_all_ranks_at_once"] = {"pinned": link_all[0], "write_combined": link_all[1],
+                line["e2e"]["h2d_link_gbs_all_ranks_at_once"] = {"write_combined": link_all[0], "pinned": link_all[1],
                     "note": "every rank runs the same bare H2D copy at the same time: what the host side of this box delivers "
                             "per GPU when all GPUs are fed at once (the e2e figure cannot exceed it)"}
             t16 = float(t_all[4])

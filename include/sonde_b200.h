@@ -195,6 +195,11 @@ SONDE_API int  sonde_b200_modem_info(int type, int samplerate, float *taps, int 
 
 /* Pinned host memory for the host-buffer entry points (plain malloc'd memory also works, slower). */
 SONDE_API void *sonde_b200_host_alloc(size_t bytes);
+/* The same as write-combined memory: for staging buffers the host only WRITES (sequentially: reading them back on the
+ * CPU is very slow).  The GPU's reads then cause no cache snooping on the host, which matters when several GPUs of a box
+ * are fed at once (two B200s copying together: 55.5 GB/s each from write-combined, 48 GB/s each from ordinary pinned
+ * memory; bench.py e2e.h2d_link_gbs_all_ranks_at_once). */
+SONDE_API void *sonde_b200_host_alloc_wc(size_t bytes);
 SONDE_API void  sonde_b200_host_free(void *p);
 
 /* Diagnostics: the first call switches on the pipeline kernel's per-CTA stall counters; later calls copy them

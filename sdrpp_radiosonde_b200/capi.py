@@ -25,7 +25,7 @@ EXPORTS = [
     "sonde_b200_process_iq_s16", "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
     "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_detected_types", "sonde_b200_auto_plausible", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
     "sonde_b200_soft_stride", "sonde_b200_fetch_soft", "sonde_b200_fetch_state", "sonde_b200_modem_info",
-    "sonde_b200_host_alloc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_debug_demod_state", "sonde_b200_process_iq_peer", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
+    "sonde_b200_host_alloc", "sonde_b200_host_alloc_wc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_debug_demod_state", "sonde_b200_process_iq_peer", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
     "sonde_b200_last_kernel_ms", "sonde_b200_launch_count", "sonde_b200_last_error", "sonde_b200_version",
 ]
 
@@ -102,6 +102,7 @@ def load():
         "sonde_b200_fetch_state": (ctypes.c_int, [vp, f32p]),
         "sonde_b200_modem_info": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, f32p, ctypes.c_int, f32p]),
         "sonde_b200_host_alloc": (vp, [sz]),
+        "sonde_b200_host_alloc_wc": (vp, [sz]),
         "sonde_b200_host_free": (None, [vp]),
         "sonde_b200_stream": (vp, [vp]),
         "sonde_b200_debug_stalls": (ctypes.c_int, [vp, vp, ctypes.c_int]),
@@ -143,12 +144,13 @@ def _i32p(a):
 
 
 class PinnedBuffer:
-    """Page-locked host memory from sonde_b200_host_alloc(), viewed as a numpy array."""
+    """Page-locked host memory from sonde_b200_host_alloc() (or, write_combined=True, sonde_b200_host_alloc_wc():
+    write-only staging — never read it back on the CPU), viewed as a numpy array."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, write_combined=False):
         self.lib = load()
         self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        self.ptr = self.lib.sonde_b200_host_alloc(self.nbytes)
+        self.ptr = (self.lib.sonde_b200_host_alloc_wc if write_combined else self.lib.sonde_b200_host_alloc)(self.nbytes)
         if not self.ptr:
             raise MemoryError("sonde_b200_host_alloc failed")
         buf = (ctypes.c_uint8 * self.nbytes).from_address(self.ptr)

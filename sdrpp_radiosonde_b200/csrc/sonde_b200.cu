@@ -1093,6 +1093,12 @@ void *sonde_b200_host_alloc(size_t bytes)
 	return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
 }
 
+void *sonde_b200_host_alloc_wc(size_t bytes)
+{
+	void *p = nullptr;
+	return cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) == cudaSuccess ? p : nullptr;
+}
+
 void sonde_b200_host_free(void *p)
 {
 	if (p) cudaFreeHost(p);
