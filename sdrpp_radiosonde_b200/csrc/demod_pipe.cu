@@ -30,6 +30,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <cuda.h>
 
 #include "pipe_common.cuh"
 #include "timing_exact.cuh"
@@ -52,6 +55,12 @@ namespace {
 
 using namespace pipe;
 
+/* tensor maps of the input [rows][len] for the 2-D staging of a tile (encoded per call on the host, sonde_launch_demod_pipe):
+ * `tile` has a box of T columns x tma_box_rows rows, `lookback` one of 2 columns x the same rows */
+struct k1_maps {
+	CUtensorMap tile, lookback;
+};
+
 /* AGC_SPLIT 1 puts the bias and the level recurrence on two warps (A1, A2).  Measured and NOT adopted (exp47, tools/ubench/
  * ubench4/5): alone on an SM the bias loop runs at 13.5 cycles/sample (its dependent chain is 3 x 4.04 = 12.1), inside the
  * kernel at 19 whether fused with the level recurrence or not, because any second warp on its SMSP — the level warp as
@@ -63,7 +72,6 @@ using namespace pipe;
 constexpr int W_TM = 0, W_AG = 1, W_LD = 4, W_A2 = 5; /* warp ids of the single-warp roles (SMSP = id % 4)       */
 constexpr uint32_t ROLE_MASK = (1u << W_TM) | (1u << W_AG) | (1u << W_LD) | (AGC_SPLIT ? (1u << W_A2) : 0u);
 constexpr int NRAW = 3, NSV = 2, NY = 3;             /* ring depths in tiles (NX = 3 from pipe_common)            */
-constexpr int RAWS = T + 2;                          /* raw row: 2 samples of look-back + the tile                */
 constexpr int XS = T + 12;                           /* x row: 8 floats of slack for the AGC prefetch; 268 % 32 = 12 keeps the
                                                         8 channel lanes' LDS.128 on distinct banks                 */
 constexpr int YM = 32;                               /* slots mirrored after the end of the y ring                */
@@ -75,7 +83,9 @@ constexpr uint32_t ZSENT = 0x7fc5a5a5u;              /* s value of a sample that
 
 template <int P>
 struct smem_t {
-	float2 raw[NRAW][G][RAWS];           /* TMA landing zone: IQ (or FM floats packed at the row start)              */
+	float2 rawt[NRAW][G][T];             /* TMA landing zone, one tile: IQ rows of T float2 (FM: dense rows of T floats
+	                                        from the start of the slot) — the shape a 2-D box of G rows lands in            */
+	float2 rawlb[NRAW][G][2];            /* IQ: the two samples before the tile (the discriminator's look-back)         */
 	float x[NX][G][XS];                  /* discriminator output / FM input                                          */
 	float s[NSV][G][RS];                 /* bias-removed samples                                                     */
 	float v[NSV][G][RS];                 /* moving_avg before each sample's update                                   */
@@ -156,7 +166,7 @@ __device__ __forceinline__ void item_disc(smem_t<P> &sm, const demod_params &p, 
 			if (k == 0) {
 				carry = p.st[ch].disc_prev;
 			} else {
-				const float2 pr = TMA ? sm.raw[rs][g][1] : __ldg(static_cast<const float2 *>(p.in) + rowoff - 1);
+				const float2 pr = TMA ? sm.rawlb[rs][g][1] : __ldg(static_cast<const float2 *>(p.in) + rowoff - 1);
 				carry = det_phase(pr.x, pr.y);
 			}
 		}
@@ -170,7 +180,7 @@ __device__ __forceinline__ void item_disc(smem_t<P> &sm, const demod_params &p, 
 			const int t = 2 * lane + 64 * i;
 			float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 			if (TMA) {
-				f = *reinterpret_cast<const float4 *>(&sm.raw[rs][g][2 + t]);
+				f = *reinterpret_cast<const float4 *>(&sm.rawt[rs][g][t]);
 			} else {
 				const float2 *src = static_cast<const float2 *>(p.in) + rowoff + t;
 				/* rows need not be 16-byte aligned on this path */
@@ -199,7 +209,7 @@ __device__ __forceinline__ void item_disc(smem_t<P> &sm, const demod_params &p, 
 			const int t = 2 * lane + 64 * i;
 			float x0, x1;
 			if (TMA) {
-				const float2 f = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(&sm.raw[rs][g][0]) + t);
+				const float2 f = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(&sm.rawt[rs][0][0]) + g * T + t);
 				x0 = f.x; x1 = f.y;
 			} else {
 				const float *src = static_cast<const float *>(p.in) + rowoff + t;
@@ -590,10 +600,10 @@ __device__ __forceinline__ void level_tile(const float *__restrict__ s, float *_
 
 template <int P, int KM0, int NM, int KS0, int NS, bool IQ, bool SOFT, bool TMA>
 __global__ void __maxnreg__(64)
-demod_pipe_kernel(const demod_params p, const int group_base, const int n_here)
+demod_pipe_kernel(const demod_params p, const int group_base, const int n_here, const __grid_constant__ k1_maps maps)
 {
 	if ((int)blockIdx.x >= n_here) return;            /* the padding CTA of an odd group count (launch_tpc_pairs) */
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	extern __shared__ __align__(128) unsigned char smem_raw[];        /* 2-D TMA destinations want 128 bytes */
 	smem_t<P> &sm = *reinterpret_cast<smem_t<P> *>(smem_raw);
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -643,18 +653,28 @@ demod_pipe_kernel(const demod_params p, const int group_base, const int n_here)
 		 * discriminator of a tile does not depend on the previous tile's item) into sm.raw, up to NRAW tiles ahead. */
 		if (TMA && lane == 0) {
 			constexpr uint32_t ESZ = IQ ? 8u : 4u;
+			const int box = p.tma_box_rows;
 			for (int tile = 0; tile < ntiles; tile++) {
 				const int slot = tile % NRAW;
 				if (tile >= NRAW) mbar_wait(&sm.rawfree[slot], ((tile / NRAW) - 1) & 1);
-				const int n = min(T, L - tile * T);
-				const int lb = (IQ && tile > 0) ? 2 : 0;
-				const uint32_t bytes = (uint32_t)(n + lb) * ESZ;
-				mbar_expect_tx(&sm.rawfull[slot], bytes * (uint32_t)gact);
-				for (int g = 0; g < gact; g++) {
-					void *dst = IQ ? static_cast<void *>(&sm.raw[slot][g][2 - lb]) : static_cast<void *>(&sm.raw[slot][g][0]);
-					tma_load_1d(dst,
-					            static_cast<const char *>(p.in) + ((size_t)sm.row[g] * p.row_stride + (size_t)tile * T - lb) * ESZ,
-					            bytes, &sm.rawfull[slot]);
+				const bool lb = IQ && tile > 0;
+				if (box > 0) {
+					/* ONE tensor copy per tile: T columns x `box` consecutive rows (columns past the buffer are zero-filled
+					 * and count towards the transaction), plus the 2-column look-back box */
+					mbar_expect_tx(&sm.rawfull[slot], (uint32_t)box * (T * ESZ + (lb ? 16u : 0u)));
+					tma_load_2d(&sm.rawt[slot][0][0], &maps.tile, tile * T, sm.row[0], &sm.rawfull[slot]);
+					if (lb) tma_load_2d(&sm.rawlb[slot][0][0], &maps.lookback, tile * T - 2, sm.row[0], &sm.rawfull[slot]);
+				} else {
+					const int n = min(T, L - tile * T);
+					const uint32_t bytes = (uint32_t)n * ESZ;
+					mbar_expect_tx(&sm.rawfull[slot], (bytes + (lb ? 16u : 0u)) * (uint32_t)gact);
+					for (int g = 0; g < gact; g++) {
+						const char *src = static_cast<const char *>(p.in) + ((size_t)sm.row[g] * p.row_stride + (size_t)tile * T) * ESZ;
+						void *dst = IQ ? static_cast<void *>(&sm.rawt[slot][g][0])
+						               : static_cast<void *>(reinterpret_cast<float *>(&sm.rawt[slot][0][0]) + g * T);
+						tma_load_1d(dst, src, bytes, &sm.rawfull[slot]);
+						if (lb) tma_load_1d(&sm.rawlb[slot][g][0], src - 16, 16u, &sm.rawfull[slot]);
+					}
 				}
 			}
 		}
@@ -816,6 +836,41 @@ demod_pipe_kernel(const demod_params p, const int group_base, const int n_here)
 	}
 }
 
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+/* The input of this call as a 2-D tensor [n_rows][len] (row pitch row_stride): columns past `len` and before 0 read as
+ * zero, which is what the tile tail and the look-back of tile 0 want.  Driver entry point through the runtime (libcuda is
+ * not linked); encoding is host arithmetic only. */
+cudaError_t encode_k1_maps(k1_maps *m, const demod_params *p, bool iq)
+{
+	static encode_tiled_fn encode = [] {
+		encode_tiled_fn f = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+		return f;
+	}();
+	if (!encode) return cudaErrorNotSupported;
+	const size_t esz = iq ? 8 : 4;
+	const cuuint64_t gdim[2] = {(cuuint64_t)p->len, (cuuint64_t)p->n_rows};
+	const cuuint64_t gstr[1] = {(cuuint64_t)p->row_stride * esz};
+	const cuuint32_t estr[2] = {1, 1};
+	const CUtensorMapDataType dt = iq ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+	const cuuint32_t box[2] = {(cuuint32_t)T, (cuuint32_t)p->tma_box_rows};
+	if (encode(&m->tile, dt, 2, const_cast<void *>(p->in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+		return cudaErrorInvalidValue;
+	m->lookback = m->tile;
+	if (iq) {
+		const cuuint32_t boxl[2] = {2, (cuuint32_t)p->tma_box_rows};
+		if (encode(&m->lookback, dt, 2, const_cast<void *>(p->in), gdim, gstr, boxl, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+			return cudaErrorInvalidValue;
+	}
+	return cudaSuccess;
+}
+
 template <int P, int KM0, int NM, int KS0, int NS, bool IQ, bool SOFT, bool TMA>
 cudaError_t launch3(const demod_params *p, int group_base, int n_groups, cudaStream_t stream)
 {
@@ -824,7 +879,13 @@ cudaError_t launch3(const demod_params *p, int group_base, int n_groups, cudaStr
 	const cudaError_t ea = sonde_ensure_dynamic_smem(kern, (int)sizeof(smem_t<P>), attr_done);
 	if (ea != cudaSuccess) return ea;
 	const int nwarps = 32 - __builtin_clz(p->pw_mask | ROLE_MASK);
-	return launch_tpc_pairs(kern, n_groups, nwarps * 32, sizeof(smem_t<P>), stream, p->tpc_pairs != 0, *p, group_base, n_groups);
+	k1_maps maps;
+	memset(&maps, 0, sizeof(maps));
+	if (TMA && p->tma_box_rows > 0) {
+		const cudaError_t em = encode_k1_maps(&maps, p, IQ);
+		if (em != cudaSuccess) return em;
+	}
+	return launch_tpc_pairs(kern, n_groups, nwarps * 32, sizeof(smem_t<P>), stream, p->tpc_pairs != 0, *p, group_base, n_groups, maps);
 }
 
 template <int P, int KM0, int NM, int KS0, int NS, bool IQ>

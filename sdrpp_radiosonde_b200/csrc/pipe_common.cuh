@@ -95,6 +95,13 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(s32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(s32(b)) : "memory");
 }
+/* TMA, tensor form: one elected thread copies a 2-D box (columns x rows of a row-major array described by a CUtensorMap,
+ * out-of-bounds elements zero-filled) into shared memory (cp.async.bulk.tensor.2d, SASS UTMALDG) */
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, int col, int row, unsigned long long *b)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+	             ::"r"(s32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(s32(b)), "r"(col), "r"(row) : "memory");
+}
 /* all lanes of a warp finished their writes -> one arrival */
 __device__ __forceinline__ void warp_arrive(unsigned long long *b, int lane)
 {

@@ -46,6 +46,9 @@ struct sonde_b200 {
 	std::vector<int32_t> locked;         /* decoder type a user channel reports (SONDE_AUTO = undetermined)*/
 	std::vector<int32_t> gchan_host;     /* host copy of d_group_chan                                      */
 	int32_t *d_in_row = nullptr, *d_active = nullptr;
+	std::vector<int32_t> in_row_host;    /* input row of every (virtual) channel */
+	int box_rows_v[4] = {0, 0, 0, 0};    /* per kernel variant: rows of the 2-D TMA box (= its group size) when the channels of
+	                                        every group sit in consecutive input rows, else 0 (one bulk copy per row) */
 	std::vector<sonde_frame_rec> h_recs; /* staging for fetch() when virtual != user channels              */
 	std::vector<int32_t> h_vcounts;
 	bool has_auto = false;
@@ -216,6 +219,17 @@ void build_groups(sonde_b200 *h, const std::vector<int32_t> *active, std::vector
 	h->groups_v[2] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 2; });
 	h->groups_v[3] = add_groups([](const sonde_modem &m) { return m.baud && m.afsk; });
 	h->n_groups = (int)gtype.size();
+	/* 2-D staging: a group can be fetched with one tensor copy when its channels are consecutive input rows */
+	int gi = 0;
+	for (int v = 0; v < 4; v++) {
+		bool consec = h->groups_v[v] > 0 && !h->in_row_host.empty();
+		for (int k = 0; k < h->groups_v[v]; k++, gi++) {
+			const int32_t *ch = &gchan[(size_t)gi * DEMOD_G];
+			for (int j = 1; j < DEMOD_G && ch[j] >= 0; j++)
+				consec = consec && h->in_row_host[ch[j]] == h->in_row_host[ch[0]] + j;
+		}
+		h->box_rows_v[v] = consec ? gsz_v[v] : 0;
+	}
 }
 
 uint32_t next_pow2(uint32_t v)
@@ -276,6 +290,7 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 			in_row.push_back(c);
 		}
 	}
+	h->in_row_host = in_row;
 	h->locked = h->user_types;
 	h->plausible.assign(cfg->n_channels, (1u << SONDE_NTYPES) - 1u);
 	h->narrowed_at.assign(cfg->n_channels, -1);
@@ -614,6 +629,9 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 			else if (h->cfg.reserved & 1)  CK(sonde_launch_demod_gfsk(&dp, base, h->groups_v[v], v == 2 ? 2 : 1, st));
 			else {
 				dp.pw_mask = mask_env ? mask_env : kPwMask[v];
+				static const bool no_2d = getenv("SONDE_NO_TMA2D") != nullptr;              /* experiment switch */
+				dp.tma_box_rows = (dp.use_tma && !no_2d) ? h->box_rows_v[v] : 0;
+				dp.n_rows = h->n_user;
 				CK(sonde_launch_demod_pipe(&dp, base, h->groups_v[v], v, st));
 			}
 			h->launches++;
