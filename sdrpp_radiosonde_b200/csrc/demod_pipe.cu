@@ -55,8 +55,9 @@ namespace {
 
 using namespace pipe;
 
-/* tensor maps of the input [rows][len] for the 2-D staging of a tile (encoded per call on the host, sonde_launch_demod_pipe):
- * `tile` has a box of T columns x tma_box_rows rows, `lookback` one of 2 columns x the same rows */
+/* tensor maps of the input [rows][len] for the tensor staging of a tile (encoded per call on the host, encode_k1_maps): the
+ * rows are split as row = quotient * step + residue, so that channels `step` rows apart are consecutive in the third
+ * dimension; `tile` has a box of T columns x 1 x tma_box_rows, `lookback` one of 2 columns x 1 x the same rows */
 struct k1_maps {
 	CUtensorMap tile, lookback;
 };
@@ -653,7 +654,11 @@ demod_pipe_kernel(const demod_params p, const int group_base, const int n_here, 
 		 * discriminator of a tile does not depend on the previous tile's item) into sm.raw, up to NRAW tiles ahead. */
 		if (TMA && lane == 0) {
 			constexpr uint32_t ESZ = IQ ? 8u : 4u;
-			const int box = p.tma_box_rows;
+			/* the tensor copy fetches tma_box_rows rows: a group that would reach past the input (the last, partial one of an
+			 * interleaved batch) takes the row copies instead */
+			const int step = p.tma_row_step;
+			const int box = (p.tma_box_rows > 0 && sm.row[0] + (p.tma_box_rows - 1) * step < p.n_rows) ? p.tma_box_rows : 0;
+			const int rres = box > 0 ? sm.row[0] % step : 0, rquo = box > 0 ? sm.row[0] / step : 0;
 			for (int tile = 0; tile < ntiles; tile++) {
 				const int slot = tile % NRAW;
 				if (tile >= NRAW) mbar_wait(&sm.rawfree[slot], ((tile / NRAW) - 1) & 1);
@@ -662,8 +667,8 @@ demod_pipe_kernel(const demod_params p, const int group_base, const int n_here, 
 					/* ONE tensor copy per tile: T columns x `box` consecutive rows (columns past the buffer are zero-filled
 					 * and count towards the transaction), plus the 2-column look-back box */
 					mbar_expect_tx(&sm.rawfull[slot], (uint32_t)box * (T * ESZ + (lb ? 16u : 0u)));
-					tma_load_2d(&sm.rawt[slot][0][0], &maps.tile, tile * T, sm.row[0], &sm.rawfull[slot]);
-					if (lb) tma_load_2d(&sm.rawlb[slot][0][0], &maps.lookback, tile * T - 2, sm.row[0], &sm.rawfull[slot]);
+					tma_load_3d(&sm.rawt[slot][0][0], &maps.tile, tile * T, rres, rquo, &sm.rawfull[slot]);
+					if (lb) tma_load_3d(&sm.rawlb[slot][0][0], &maps.lookback, tile * T - 2, rres, rquo, &sm.rawfull[slot]);
 				} else {
 					const int n = min(T, L - tile * T);
 					const uint32_t bytes = (uint32_t)n * ESZ;
@@ -853,18 +858,19 @@ cudaError_t encode_k1_maps(k1_maps *m, const demod_params *p, bool iq)
 	}();
 	if (!encode) return cudaErrorNotSupported;
 	const size_t esz = iq ? 8 : 4;
-	const cuuint64_t gdim[2] = {(cuuint64_t)p->len, (cuuint64_t)p->n_rows};
-	const cuuint64_t gstr[1] = {(cuuint64_t)p->row_stride * esz};
-	const cuuint32_t estr[2] = {1, 1};
+	const int step = p->tma_row_step > 0 ? p->tma_row_step : 1;
+	const cuuint64_t gdim[3] = {(cuuint64_t)p->len, (cuuint64_t)step, (cuuint64_t)((p->n_rows + step - 1) / step)};
+	const cuuint64_t gstr[2] = {(cuuint64_t)p->row_stride * esz, (cuuint64_t)p->row_stride * esz * step};
+	const cuuint32_t estr[3] = {1, 1, 1};
 	const CUtensorMapDataType dt = iq ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-	const cuuint32_t box[2] = {(cuuint32_t)T, (cuuint32_t)p->tma_box_rows};
-	if (encode(&m->tile, dt, 2, const_cast<void *>(p->in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	const cuuint32_t box[3] = {(cuuint32_t)T, 1, (cuuint32_t)p->tma_box_rows};
+	if (encode(&m->tile, dt, 3, const_cast<void *>(p->in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 	           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
 		return cudaErrorInvalidValue;
 	m->lookback = m->tile;
 	if (iq) {
-		const cuuint32_t boxl[2] = {2, (cuuint32_t)p->tma_box_rows};
-		if (encode(&m->lookback, dt, 2, const_cast<void *>(p->in), gdim, gstr, boxl, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		const cuuint32_t boxl[3] = {2, 1, (cuuint32_t)p->tma_box_rows};
+		if (encode(&m->lookback, dt, 3, const_cast<void *>(p->in), gdim, gstr, boxl, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 		           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
 			return cudaErrorInvalidValue;
 	}

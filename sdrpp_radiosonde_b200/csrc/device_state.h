@@ -73,7 +73,9 @@ struct demod_params {
 	int32_t       use_tma;        /* rows 16-byte aligned: stage tiles with cp.async.bulk */
 	int32_t       tma_box_rows;   /* > 0: the rows of every group are consecutive input rows and a tile is staged with ONE 2-D
 	                                 tensor-map copy of this many rows (K1: k1_maps kernel argument); 0: one 1-D bulk copy per row */
-	int32_t       n_rows;         /* rows of the input array (the tensor map's outer dimension)                 */
+	int32_t       tma_row_step;   /* the channels of a group are this many input rows apart (1 = consecutive; 2 = two sonde types
+	                                 on alternating channels, ...)                                              */
+	int32_t       n_rows;         /* rows of the input array                                                   */
 	float         fm_gain;
 	int32_t       n_groups;
 	const int32_t *group_chan;    /* [n_groups][DEMOD_G] channel ids, -1 = empty      */

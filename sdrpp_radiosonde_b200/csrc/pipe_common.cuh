@@ -102,6 +102,12 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, in
 	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
 	             ::"r"(s32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(s32(b)), "r"(col), "r"(row) : "memory");
 }
+/* the same for a 3-D tensor (column, row residue, row quotient): rows a fixed step apart are consecutive in the third dimension */
+__device__ __forceinline__ void tma_load_3d(void *dst_smem, const void *tmap, int c0, int c1, int c2, unsigned long long *b)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+	             ::"r"(s32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(s32(b)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 /* all lanes of a warp finished their writes -> one arrival */
 __device__ __forceinline__ void warp_arrive(unsigned long long *b, int lane)
 {

@@ -47,8 +47,9 @@ struct sonde_b200 {
 	std::vector<int32_t> gchan_host;     /* host copy of d_group_chan                                      */
 	int32_t *d_in_row = nullptr, *d_active = nullptr;
 	std::vector<int32_t> in_row_host;    /* input row of every (virtual) channel */
-	int box_rows_v[4] = {0, 0, 0, 0};    /* per kernel variant: rows of the 2-D TMA box (= its group size) when the channels of
-	                                        every group sit in consecutive input rows, else 0 (one bulk copy per row) */
+	int box_rows_v[4] = {0, 0, 0, 0};    /* per kernel variant: rows of the TMA box (= its group size) when the channels of every
+	                                        group sit a fixed number of input rows apart (row_step_v), else 0: one bulk copy per row */
+	int row_step_v[4] = {1, 1, 1, 1};
 	std::vector<sonde_frame_rec> h_recs; /* staging for fetch() when virtual != user channels              */
 	std::vector<int32_t> h_vcounts;
 	bool has_auto = false;
@@ -219,16 +220,23 @@ void build_groups(sonde_b200 *h, const std::vector<int32_t> *active, std::vector
 	h->groups_v[2] = add_groups([](const sonde_modem &m) { return m.baud && !m.afsk && m.num_phases == 2; });
 	h->groups_v[3] = add_groups([](const sonde_modem &m) { return m.baud && m.afsk; });
 	h->n_groups = (int)gtype.size();
-	/* 2-D staging: a group can be fetched with one tensor copy when its channels are consecutive input rows */
+	/* tensor staging: a group can be fetched with one tensor copy when its channels are a fixed number of input rows apart —
+	 * 1 for a typed batch or AUTO channels, k when k sonde types alternate from channel to channel — and that step is the
+	 * same for all groups of the kernel variant */
 	int gi = 0;
 	for (int v = 0; v < 4; v++) {
-		bool consec = h->groups_v[v] > 0 && !h->in_row_host.empty();
+		int step = 0;                                        /* 0: not seen yet, -1: no common step */
 		for (int k = 0; k < h->groups_v[v]; k++, gi++) {
 			const int32_t *ch = &gchan[(size_t)gi * DEMOD_G];
-			for (int j = 1; j < DEMOD_G && ch[j] >= 0; j++)
-				consec = consec && h->in_row_host[ch[j]] == h->in_row_host[ch[0]] + j;
+			for (int j = 1; j < DEMOD_G && ch[j] >= 0 && step >= 0 && !h->in_row_host.empty(); j++) {
+				const int d = h->in_row_host[ch[j]] - h->in_row_host[ch[j - 1]];
+				if (d <= 0 || (step > 0 && d != step)) step = -1;
+				else step = d;
+			}
 		}
-		h->box_rows_v[v] = consec ? gsz_v[v] : 0;
+		if (step == 0) step = 1;                             /* single-channel groups */
+		h->box_rows_v[v] = (h->groups_v[v] > 0 && step > 0 && !h->in_row_host.empty()) ? gsz_v[v] : 0;
+		h->row_step_v[v] = step > 0 ? step : 1;
 	}
 }
 
@@ -631,6 +639,7 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 				dp.pw_mask = mask_env ? mask_env : kPwMask[v];
 				static const bool no_2d = getenv("SONDE_NO_TMA2D") != nullptr;              /* experiment switch */
 				dp.tma_box_rows = (dp.use_tma && !no_2d) ? h->box_rows_v[v] : 0;
+				dp.tma_row_step = h->row_step_v[v];
 				dp.n_rows = h->n_user;
 				CK(sonde_launch_demod_pipe(&dp, base, h->groups_v[v], v, st));
 			}
