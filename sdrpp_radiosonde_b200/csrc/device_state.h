@@ -107,6 +107,8 @@ struct frame_params {
 	int32_t       *counts;        /* [C][2] frames / ok of this call                 */
 	const int32_t *active;        /* [C] 0 = channel switched off (AUTO loser)        */
 	int32_t        skip_warps;    /* idle warps in front of the working ones of each CTA (SMSP placement, frame.cu) */
+	int32_t        work_warps;    /* working warps per CTA (0 = default)                                              */
+	int32_t        persist;       /* > 0: at most this many CTAs, every working warp loops over its channels          */
 };
 
 

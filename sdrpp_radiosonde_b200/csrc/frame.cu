@@ -38,7 +38,7 @@ extern "C" cudaError_t sonde_upload_modems_frame(const sonde_modem *m)
 namespace {
 
 constexpr int WARPS_PER_CTA = 2;    /* 64 threads x 128 registers: small enough to sit beside a K1 CTA (768 x 72) on the same SM */
-constexpr int MAX_SKIP_WARPS = 2;   /* optional idle warps 0..1: the working warps then sit on SMSP 2 and 3 (warp id % 4) */
+constexpr int MAX_SKIP_WARPS = 0;   /* idle warps in front of the working ones (SMSP placement experiments: compile with 3) */
 constexpr int WIN_WORDS = 264;            /* >= 2 * 4144 / 32 + 4 : the framer buffer holds up to 2F bits */
 constexpr int WORK_BYTES = 1024;
 constexpr unsigned FULL = 0xffffffffu;
@@ -641,22 +641,13 @@ __device__ void deframe_c50(warp_smem &ws, int lane, int &status)
 
 /* ---- the framer walk ------------------------------------------------------------------------ */
 
-__global__ void __launch_bounds__((WARPS_PER_CTA + MAX_SKIP_WARPS) * 32)
-frame_kernel(const frame_params p)
+/* the framer walk of one channel by one warp */
+__device__ __forceinline__ void frame_channel(const frame_params &p, const int ch, warp_smem &ws, cta_smem &sm, const int lane)
 {
-	__shared__ cta_smem sm;
-	const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5) - p.skip_warps;
-	load_gf_tables(sm.gf, threadIdx.x, blockDim.x);
-	__syncthreads();
-	if (wid < 0) return;
-
-	const int ch = blockIdx.x * WARPS_PER_CTA + wid;
-	if (ch >= p.n_channels) return;
 	if (p.active && !p.active[ch]) {
 		if (lane == 0 && p.counts) { p.counts[2 * ch] = 0; p.counts[2 * ch + 1] = 0; }
 		return;
 	}
-	warp_smem &ws = sm.w[wid];
 
 	const int type = p.types[ch];
 	const sonde_modem &md = c_modem[type];
@@ -859,6 +850,27 @@ frame_kernel(const frame_params p)
 	}
 }
 
+/* One warp per channel.  Experiment hooks (profiles/r2_step_experiments.md, exp52): `skip_warps` idle warps in front of the
+ * `work_warps` working ones choose the SMSPs the working warps sit on (warp id % 4); with `persist` the grid is smaller than
+ * the batch and every working warp walks over its channels one after the other — a framer that runs beside the next call's
+ * demodulator as one quiet warp per SM.  Every such placement made the step slower than the framer simply running in
+ * order behind the demodulator (0.70-0.87 ms against 0.654), so that is what the library does. */
+__global__ void __launch_bounds__((WARPS_PER_CTA + MAX_SKIP_WARPS) * 32)
+frame_kernel(const frame_params p)
+{
+	__shared__ cta_smem sm;
+	const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5) - p.skip_warps;
+	load_gf_tables(sm.gf, threadIdx.x, blockDim.x);
+	__syncthreads();
+	if (wid < 0) return;
+	const int work = p.work_warps > 0 ? p.work_warps : WARPS_PER_CTA;
+	const int stride = p.persist ? (int)gridDim.x * work : p.n_channels;
+	for (int ch = blockIdx.x * work + wid; ch < p.n_channels; ch += stride) {
+		frame_channel(p, ch, sm.w[wid], sm, lane);
+		__syncwarp();
+	}
+}
+
 }  // namespace
 
 extern "C" cudaError_t sonde_upload_gf_tables(void)
@@ -886,8 +898,10 @@ extern "C" cudaError_t sonde_upload_gf_tables(void)
 
 extern "C" cudaError_t sonde_launch_frames(const frame_params *p, cudaStream_t stream)
 {
-	const int ctas = (p->n_channels + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-	if (p->skip_warps < 0 || p->skip_warps > MAX_SKIP_WARPS) return cudaErrorInvalidValue;
-	frame_kernel<<<ctas, (WARPS_PER_CTA + p->skip_warps) * 32, 0, stream>>>(*p);
+	if (p->skip_warps < 0 || p->skip_warps > MAX_SKIP_WARPS || p->work_warps < 0 || p->work_warps > WARPS_PER_CTA) return cudaErrorInvalidValue;
+	const int work = p->work_warps > 0 ? p->work_warps : WARPS_PER_CTA;
+	int ctas = (p->n_channels + work - 1) / work;
+	if (p->persist > 0 && ctas > p->persist) ctas = p->persist;
+	frame_kernel<<<ctas, (work + p->skip_warps) * 32, 0, stream>>>(*p);
 	return cudaGetLastError();
 }

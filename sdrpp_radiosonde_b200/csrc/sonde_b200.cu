@@ -671,11 +671,17 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	static const bool frame_serial = getenv("SONDE_FRAME_SERIAL") != nullptr;      /* experiment switch */
 	static const int frame_skip = getenv("SONDE_FRAME_SKIP") ? atoi(getenv("SONDE_FRAME_SKIP")) : 0;
 	fp.skip_warps = frame_skip;
-	/* Several kernel variants forked over the SMs: the framer then runs in order behind them.  Measured (tools/timeline.py,
-	 * BASELINE config 5): beside the forked demodulators of the next call its CTAs are placed first and hold back theirs,
-	 * 2.16 ms per step against 1.74 ms in order; with one variant the two orders cost the same (K1 is latency-bound and
-	 * loses to the framer's warps what the overlap gains). */
-	cudaStream_t fs_ = (frame_serial || fork) ? h->stream : h->fstream;
+	static const int frame_work = getenv("SONDE_FRAME_WORK") ? atoi(getenv("SONDE_FRAME_WORK")) : 0;
+	static const int frame_persist = getenv("SONDE_FRAME_PERSIST") ? atoi(getenv("SONDE_FRAME_PERSIST")) : 0;
+	fp.work_warps = frame_work;
+	fp.persist = frame_persist;
+	/* The framer runs in order behind the demodulator(s) of its call.  Measured with CUPTI timelines (tools/timeline.py,
+	 * profiles/r2_step_experiments.md): on its own stream beside the next call's demodulator it costs that kernel — latency-
+	 * bound serial warps, one CTA per SM — as much as it saves or more (config 2: 0.668 ms per step beside, 0.654 in order;
+	 * config 5, forked variants: 2.16 against 1.74), however its warps are placed or throttled.  SONDE_FRAME_OVERLAP=1 restores
+	 * the separate stream for experiments. */
+	static const bool frame_overlap = getenv("SONDE_FRAME_OVERLAP") != nullptr;
+	cudaStream_t fs_ = (frame_overlap && !frame_serial && !fork) ? h->fstream : h->stream;
 	CK(cudaStreamWaitEvent(fs_, h->ev_demod[par], 0));
 	CK(cudaEventRecord(h->evf[0], fs_));
 	CK(sonde_launch_frames(&fp, fs_));
