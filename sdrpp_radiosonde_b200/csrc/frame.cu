@@ -276,17 +276,21 @@ __device__ int bch63_fix_lane(uint64_t &msg, const gf_tables &gt)
 {
 	constexpr int N = 63, TT = 4, T2 = 2;
 	const gf<N> f = {gt.exp64, gt.log64};
-	uint32_t syn[TT];
-	uint32_t any = 0;
+	/* syndromes at the roots {2,4,8,16} = alpha^1..alpha^4 (ims100/protocol.h:62).  The reference evaluates the message
+	 * polynomial by Horner's rule (rs.c:215-224: 63 dependent table multiplications per root); over GF(2) coefficients that
+	 * is the XOR of alpha^((j+1) k) over the set bits k — the same field element, from independent table reads. */
+	uint32_t syn[TT] = {0, 0, 0, 0};
+	for (uint64_t m = msg & ~(1ull << 63); m; m &= m - 1) {
+		const uint32_t k = (uint32_t)__ffsll((long long)m) - 1u;
 #pragma unroll
-	for (int j = 0; j < TT; j++) {
-		const uint32_t z = 2u << j;                         /* ims100/protocol.h:62 roots {2,4,8,16} */
-		uint32_t r = 0;
-		for (int k = N - 1; k >= 0; k--) r = f.mul(r, z) ^ (uint32_t)((msg >> k) & 1);
-		syn[j] = r;
-		any |= r;
+		for (int j = 0; j < TT; j++) {
+			uint32_t e = (uint32_t)(j + 1) * k;              /* < 252; 64 == 1 (mod 63) */
+			e = (e & 63u) + (e >> 6);
+			e = (e >= (uint32_t)N) ? e - N : e;
+			syn[j] ^= gt.exp64[e];
+		}
 	}
-	if (!any) return 0;
+	if (!(syn[0] | syn[1] | syn[2] | syn[3])) return 0;
 
 	uint32_t lam[T2 + 1] = {1, 0, 0}, plam[T2 + 1] = {1, 0, 0}, tmp[T2 + 1];
 	int deg = 0, m = 1;
@@ -309,15 +313,28 @@ __device__ int bch63_fix_lane(uint64_t &msg, const gf_tables &gt)
 			m++;
 		}
 	}
-	int count = 0;
-	uint32_t pos[T2];
-	for (int x = 1; x <= N && count < deg; x++) {
-		uint32_t r = 0;
-		for (int k = T2; k >= 0; k--) r = f.mul(r, x) ^ lam[k];
-		if (r == 0) pos[count++] = gt.log64[f.div(1, x)];
+	/* roots of lambda among x = 1..63 (rs.c:175-183 walks them in this order and stops once it has `deg` of them; a
+	 * polynomial of degree <= 2 has no more, so scanning all of them finds the same set).  lambda(x) = lam2 x^2 + lam1 x +
+	 * lam0 from independent table reads instead of 63 dependent Horner evaluations. */
+	const uint32_t l1 = gt.log64[lam[1]], l2 = gt.log64[lam[2]];
+	uint64_t roots = 0;
+#pragma unroll 7
+	for (int x = 1; x <= N; x++) {
+		const uint32_t lx = gt.log64[x];                        /* log 1 == 63 (the table quirk): harmless modulo 63 */
+		uint32_t e1 = l1 + lx, e2 = l2 + 2u * lx;               /* <= 126, <= 189 */
+		e1 = (e1 >= (uint32_t)N) ? e1 - N : e1;
+		e1 = (e1 >= (uint32_t)N) ? e1 - N : e1;
+		e2 = (e2 & 63u) + (e2 >> 6);
+		e2 = (e2 >= (uint32_t)N) ? e2 - N : e2;
+		const uint32_t r = (lam[2] ? gt.exp64[e2] : 0u) ^ (lam[1] ? gt.exp64[e1] : 0u) ^ lam[0];
+		roots |= (uint64_t)(r == 0u) << x;
 	}
+	const int count = __popcll(roots);
 	if (count != deg) return -1;
-	for (int i = 0; i < count; i++) msg ^= 1ull << pos[i];      /* pos may be 63: message[64] in ims100/frame.c:28-31 */
+	for (uint64_t m = roots; m; m &= m - 1) {
+		const uint32_t x = (uint32_t)__ffsll((long long)m) - 1u;
+		msg ^= 1ull << gt.log64[f.div(1, x)];                   /* position may be 63: message[64] in ims100/frame.c:28-31 */
+	}
 	return count;
 }
 

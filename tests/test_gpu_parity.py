@@ -52,6 +52,31 @@ def test_frames_match_reference_fm(stype, chunk):
             assert sum(int(w.ok) for w in want) > 0, "signal did not decode at all"
 
 
+@pytest.mark.parametrize("nerr", [4, 14, 40])
+def test_ims100_bch_error_paths_match_reference(nerr):
+    """iMS-100 frames with 4 / 14 / 40 raw bit flips each (before the Manchester and differential stages spread them): the
+    12 BCH(63,51) messages of a frame then see none, one, two (corrected) or more errors (decoder failure, or a
+    mis-correction that may touch the padding symbols the reference shares between the messages of a frame,
+    ims100/frame.c:33).  The kernel's syndromes and root search read the GF tables in parallel instead of Horner's rule;
+    records, status (number of corrected bits or -1) and bytes must equal the compiled reference's."""
+    if not reflib.have_ref():
+        pytest.skip("compiled reference not built")
+    ref = reflib.RefLib()
+    n_ch, n, chunk = 4, 48000 * 4, 48000
+    batch = make_fm_batch(synth.IMS100, n_ch, n, bit_errors=nerr)
+    got = run_gpu([synth.IMS100] * n_ch, batch, chunk, kind="fm")
+    rb = (synth.MODEMS[synth.IMS100].frame_bits + 7) // 8
+    statuses = []
+    for c in range(n_ch):
+        want = ref.frames_run(synth.IMS100, batch[c], chunk)
+        assert [rec_key(g, rb) for g in got["frames"][c]] == [rec_key(w, rb) for w in want], (nerr, c)
+        statuses += [int(w.status) for w in want]
+    print(f"{nerr} flips per frame: {len(statuses)} frames, status histogram {sorted(set(statuses))[:12]}")
+    assert len(statuses) >= 8
+    if nerr >= 14:
+        assert any(st > 0 for st in statuses) or any(st < 0 for st in statuses)
+
+
 @pytest.mark.parametrize("stype", GFSK_TYPES)
 @pytest.mark.parametrize("chunk", [1024, 48000])
 def test_bits_soft_and_state_bit_exact(stype, chunk):
