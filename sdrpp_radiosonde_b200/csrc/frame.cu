@@ -223,14 +223,26 @@ __device__ int rs255_fix_warp(warp_smem &ws, const gf_tables &gt, int lane)
 	__syncwarp();
 
 	/* roots: x = 1..255 in increasing order (rs.c:175-183) */
+	/* lambda(x) = sum_k lam[k] x^k as thirteen INDEPENDENT table reads per point (exp[(log lam_k + k log x) mod 255]) — the
+	 * same field element as the reference's Horner evaluation (rs.c:177-181), without its chain of 12 dependent
+	 * multiplications (24 dependent shared-memory reads) per point */
+	uint32_t llam[T2 + 1];
+#pragma unroll
+	for (int k = 0; k <= T2; k++) llam[k] = ws.lam[k] ? gt.log256[ws.lam[k]] : 0xffffu;
 	int count = 0;
 	for (int base = 1; base <= N; base += 32) {
 		const int x = base + lane;
 		bool is_root = false;
 		if (x <= N) {
+			const uint32_t lx = gt.log256[x];                 /* log 1 == 255 (the table quirk): harmless modulo 255 */
 			uint32_t r = 0;
 #pragma unroll
-			for (int k = T2; k >= 0; k--) r = f.mul(r, x) ^ ws.lam[k];
+			for (int k = 0; k <= T2; k++) {
+				uint32_t e = llam[k] + (uint32_t)k * lx;      /* <= 255 + 12 * 255; 256 == 1 (mod 255) */
+				e = (e & 255u) + (e >> 8);
+				e = (e >= (uint32_t)N) ? e - N : e;
+				r ^= (llam[k] != 0xffffu) ? gt.exp256[e & 255u] : 0u;
+			}
 			is_root = (r == 0);
 		}
 		const unsigned bal = __ballot_sync(FULL, is_root);
@@ -258,9 +270,25 @@ __device__ int rs255_fix_warp(warp_smem &ws, const gf_tables &gt, int lane)
 	if (lane < count) {
 		const uint32_t x = ws.root[lane];
 		const uint32_t fcr = f.pw(x, (0 - 1 + N) % N);
+		/* omega(x) and lambda'(x) the same way: independent terms instead of Horner chains (rs.c:226-256) */
+		const uint32_t lx = gt.log256[x];
 		uint32_t num = 0, den = 0;
-		for (int k = TT - 1; k >= 0; k--) num = f.mul(num, x) ^ ws.omg[k];
-		for (int k = T2 - 1; k >= 0; k--) den = f.mul(den, x) ^ ws.lpr[k];
+#pragma unroll 8
+		for (int k = 0; k < TT; k++) {
+			const uint32_t c = ws.omg[k];
+			uint32_t e = gt.log256[c] + (uint32_t)k * lx;         /* <= 255 + 23 * 255 */
+			e = (e & 255u) + (e >> 8);
+			e = (e >= (uint32_t)N) ? e - N : e;
+			num ^= c ? gt.exp256[e] : 0u;
+		}
+#pragma unroll
+		for (int k = 0; k < T2; k++) {
+			const uint32_t c = ws.lpr[k];
+			uint32_t e = gt.log256[c] + (uint32_t)k * lx;
+			e = (e & 255u) + (e >> 8);
+			e = (e >= (uint32_t)N) ? e - N : e;
+			den ^= c ? gt.exp256[e] : 0u;
+		}
 		const int p = ws.pos[lane];
 		/* p == 255 (locator of symbol 0, because logtable[1] == n) is one past the block in the
 		 * reference (rs41/frame.c:43): that write never reaches the frame. */
@@ -740,14 +768,33 @@ __device__ __forceinline__ void frame_channel(const frame_params &p, const int c
 		__syncwarp();
 
 		/* sync search */
+		/* a lane takes 32 consecutive offsets at a time: three window words in registers, every offset a funnel shift away
+		 * (the first version read three shared-memory words per offset: 38 % of the kernel's stall samples) */
 		uint32_t best = 0xffffffffu;
-		for (int q = lane; q < nq; q += 32) {
-			const uint64_t wbits = win_bits64(ws.win, q) >> (64 - S);
-			const int d = __popcll((wbits ^ syncword) & syncmask);
-			const int di = S - d;
-			const uint32_t key = (di < d) ? (((uint32_t)di << 18) | ((uint32_t)q << 1) | 1u)
-			                              : (((uint32_t)d << 18) | ((uint32_t)q << 1));
-			best = min(best, key);
+		if (nq < 512) {
+			/* short frames (SRS-C50, iMet-4: many per call, few offsets each): one offset per lane and step */
+			for (int q = lane; q < nq; q += 32) {
+				const uint64_t wbits = win_bits64(ws.win, q) >> (64 - S);
+				const int d = __popcll((wbits ^ syncword) & syncmask);
+				const int di = S - d;
+				const uint32_t key = (di < d) ? (((uint32_t)di << 18) | ((uint32_t)q << 1) | 1u)
+				                              : (((uint32_t)d << 18) | ((uint32_t)q << 1));
+				best = min(best, key);
+			}
+		} else
+		for (int w = lane; 32 * w < nq; w += 32) {
+			const uint32_t w0 = ws.win[w], w1 = ws.win[w + 1], w2 = ws.win[w + 2];
+#pragma unroll 8
+			for (int b = 0; b < 32; b++) {
+				const int q = 32 * w + b;
+				const uint64_t win64 = ((uint64_t)__funnelshift_l(w1, w0, b) << 32) | __funnelshift_l(w2, w1, b);
+				const uint64_t wbits = win64 >> (64 - S);
+				const int d = __popcll((wbits ^ syncword) & syncmask);
+				const int di = S - d;
+				const uint32_t key = (di < d) ? (((uint32_t)di << 18) | ((uint32_t)q << 1) | 1u)
+				                              : (((uint32_t)d << 18) | ((uint32_t)q << 1));
+				best = (q < nq) ? min(best, key) : best;
+			}
 		}
 #pragma unroll
 		for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(FULL, best, o));
