@@ -195,10 +195,11 @@ SONDE_API int  sonde_b200_modem_info(int type, int samplerate, float *taps, int 
 
 /* Pinned host memory for the host-buffer entry points (plain malloc'd memory also works, slower). */
 SONDE_API void *sonde_b200_host_alloc(size_t bytes);
-/* The same as write-combined memory: for staging buffers the host only WRITES (sequentially: reading them back on the
- * CPU is very slow).  The GPU's reads then cause no cache snooping on the host, which matters when several GPUs of a box
- * are fed at once (two B200s copying together: 55.5 GB/s each from write-combined, 48 GB/s each from ordinary pinned
- * memory; bench.py e2e.h2d_link_gbs_all_ranks_at_once). */
+/* The same as write-combined memory, for staging buffers the host only WRITES (reading them back on the CPU is very slow):
+ * the GPU's reads then cause no cache snooping on the host.  Whether that helps depends on the host: with two B200s of
+ * one box copying at once a bare copy ran at 55.5 GB/s per GPU from write-combined and 48 GB/s from ordinary pinned
+ * memory, with all eight at once at 13-16 GB/s against 23-35 GB/s (bench.py e2e.h2d_link_gbs_all_ranks_at_once reports
+ * both for the box it runs on).  The library itself stages through ordinary pinned memory. */
 SONDE_API void *sonde_b200_host_alloc_wc(size_t bytes);
 SONDE_API void  sonde_b200_host_free(void *p);
 

@@ -114,7 +114,7 @@ public:
 		for (size_t c = 0; c < in.size(); c++) m_tele.emplace_back(types[c]);
 		m_backlog.assign(in.size(), {});
 		for (auto &st : m_stage) {
-			st = (float *)sonde_b200_host_alloc_wc((size_t)in.size() * max_chunk * 2 * sizeof(float));
+			st = (float *)sonde_b200_host_alloc((size_t)in.size() * max_chunk * 2 * sizeof(float));
 			if (!st) throw std::runtime_error("pinned staging allocation failed");
 		}
 		for (auto *s : m_in) dsp::block::registerInput(s);
