@@ -524,56 +524,11 @@ __device__ __forceinline__ void agc_tile(const float *__restrict__ x, float *__r
  * In one warp the two chains share an in-order instruction stream and neither runs at its own latency (18.6 busy
  * cycles/sample with nothing else on the SM); on two warps each does.  Same register rotation as agc_tile: a block of 8 is
  * stored only after the next one has been computed. */
-struct rec_block {
-	float4 o0, o1;
-};
-template <class F>
-__device__ __forceinline__ void rec_tile(const float *__restrict__ in, float *__restrict__ out, const int n, float &st, F f)
-{
-	const int nb = n >> 3;                       /* whole blocks of 8 */
-	int i = 0;
-	if (nb > 0) {
-		const float4 *ip = reinterpret_cast<const float4 *>(in);
-		float4 xa = ip[0], xb = ip[1];
-		rec_block A, B, C;
-		auto blk = [&](rec_block &o) {
-			o.o0.x = f(xa.x, st); o.o0.y = f(xa.y, st); o.o0.z = f(xa.z, st); o.o0.w = f(xa.w, st);
-			o.o1.x = f(xb.x, st); o.o1.y = f(xb.y, st); o.o1.z = f(xb.z, st); o.o1.w = f(xb.w, st);
-		};
-		auto put = [&](const int at, const rec_block &o) {
-			*reinterpret_cast<float4 *>(out + at) = o.o0;
-			*reinterpret_cast<float4 *>(out + at + 4) = o.o1;
-		};
-		int b = 0;
-		{
-			const float4 na = ip[2], nbv = ip[3];      /* rows have slack behind them: the prefetch may run past n */
-			blk(A);
-			xa = na; xb = nbv;
-		}
-		for (b = 1; b + 2 < nb; b += 3) {
-			{ const float4 na = ip[2 * b + 2], nbv = ip[2 * b + 3]; blk(B); put(8 * (b - 1), A); xa = na; xb = nbv; }
-			{ const float4 na = ip[2 * b + 4], nbv = ip[2 * b + 5]; blk(C); put(8 * b, B); xa = na; xb = nbv; }
-			{ const float4 na = ip[2 * b + 6], nbv = ip[2 * b + 7]; blk(A); put(8 * (b + 1), C); xa = na; xb = nbv; }
-		}
-		if (b < nb) {
-			const float4 na = ip[2 * b + 2], nbv = ip[2 * b + 3];
-			blk(B); put(8 * (b - 1), A);
-			xa = na; xb = nbv;
-			if (b + 1 < nb) { blk(C); put(8 * b, B); put(8 * (b + 1), C); }
-			else put(8 * b, B);
-		} else {
-			put(8 * (b - 1), A);
-		}
-		i = nb << 3;
-	}
-	for (; i < n; i++) out[i] = f(in[i], st);
-}
-
 __device__ __forceinline__ void bias_tile(const float *__restrict__ x, float *__restrict__ s, const int n, float &bias, const bool check_zero)
 {
 	const float b1 = fsub(1.0f, 0.01f), b0 = 0.01f;
 	if (!check_zero) {
-		rec_tile(x, s, n, bias, [=](const float xi, float &b) { const float o = fsub(xi, b); b = fadd(fmul(b, b1), fmul(o, b0)); return o; });
+		agc_bias_tile_fast(x, s, n, bias);
 	} else {
 		for (int i = 0; i < n; i++) {                 /* exact zeros bypass the AGC (agc.c:23) */
 			const float xi = x[i];
@@ -588,7 +543,7 @@ __device__ __forceinline__ void level_tile(const float *__restrict__ s, float *_
 {
 	const float g1 = fsub(1.0f, 0.001f), g0 = 0.001f;
 	if (!check_zero) {
-		rec_tile(s, v, n, avg, [=](const float si, float &a) { const float o = a; a = fadd(fmul(a, g1), fmul(fabsf(si), g0)); return o; });
+		agc_level_tile_fast(s, v, n, avg);
 	} else {
 		for (int i = 0; i < n; i++) {
 			const float si = s[i];

@@ -33,6 +33,7 @@
 
 #include "pipe_common.cuh"
 #include "timing_round.cuh"
+#include "timing_exact.cuh"
 
 static __constant__ sonde_modem c_modem[SONDE_NTYPES_];
 
@@ -369,7 +370,10 @@ demod_pipe_afsk_kernel(const demod_params p, const int group_base, const int n_h
 			mbar_wait_t(&sm.sfree[ss], par ^ 1, wacc[1], prof_on);
 			const float *__restrict__ x = sm.x[xs][g];
 			float *__restrict__ s = sm.s[ss][g];
-			if (lane < G) agc_bias_tile(x, s, n, bias, sm.zflag[xs] != 0);
+			if (lane < G) {
+				if (sm.zflag[xs] != 0) agc_bias_tile(x, s, n, bias, true);
+				else agc_bias_tile_fast(x, s, n, bias);              /* register-rotated blocks of 8 (pipe_common.cuh) */
+			}
 			warp_arrive(&sm.sfull[ss], lane);
 		}
 		if (own) p.st[chans[g]].agc_bias = bias;
@@ -387,7 +391,10 @@ demod_pipe_afsk_kernel(const demod_params p, const int group_base, const int n_h
 			const float *__restrict__ s = sm.s[ss][g];
 			const float *__restrict__ x = sm.x[xs][g];
 			float *__restrict__ v = sm.v[ss][g];
-			if (lane < G) agc_level_tile(s, x, v, n, avg, sm.zflag[xs] != 0);
+			if (lane < G) {
+				if (sm.zflag[xs] != 0) agc_level_tile(s, x, v, n, avg, true);
+				else agc_level_tile_fast(s, v, n, avg);
+			}
 			warp_arrive(&sm.vfull[ss], lane);
 			if (lane == 0) mbar_arrive(&sm.sfree[ss]);
 		}
@@ -468,12 +475,17 @@ demod_pipe_afsk_kernel(const demod_params p, const int group_base, const int n_h
 			(comp == 0 ? as.mark_re : comp == 1 ? as.mark_im : comp == 2 ? as.space_re : as.space_im) = sum;
 		}
 	} else {
-		/* =============================== TM: timing + slicer (see demod_pipe.cu) ============= */
+		/* =============================== TM: timing + slicer ==================================
+		 * The chain-compare rounds of demod_pipe.cu (timing_exact.cuh) on a tile at a time: rounds whose candidate slots lie
+		 * inside the tile take the fast path, the one or two that straddle its end the literal slot loop (which carries
+		 * phase / state / interm across the boundary exactly as the reference's per-sample loop does).  Windows: iMet-1/4
+		 * (1200 baud, 40 NCO slots per symbol) mid-symbol hit on slot 18..21, symbol on 38..41; SRS-C50 (2380 baud, 20.2
+		 * slots) 8..11 and 18..21.  A round outside its window is replayed literally, so the choice only affects speed. */
 		const int g = lane & (G - 1);
 		const bool own = lane < G && chans[g] >= 0;
 		const int ch = own ? chans[g] : 0;
-		tm_regs tr = {};
-		const float center = md.freq0, alpha = md.alpha, beta = md.beta, max_fdev = md.max_fdev;
+		tmx_regs tr = {};
+		const tmx_consts tc = {md.freq0, md.alpha, md.beta, md.max_fdev};
 		uint8_t *ring = p.ring + (size_t)ch * p.ring_bytes;
 		float *soft = (own && p.soft) ? p.soft + (size_t)ch * p.soft_stride : nullptr;
 		const uint32_t ring_mask = p.ring_bytes - 1;
@@ -483,31 +495,43 @@ demod_pipe_afsk_kernel(const demod_params p, const int group_base, const int n_h
 			tr.prev = st.t_prev; tr.phase = st.t_phase; tr.freq = st.t_freq;
 			tr.target = (float)st.t_state;
 			tr.interm = 0.0f;                               /* afsk.c:95 */
-			tr.acc = st.bit_acc; nbits0 = st.nbits; tr.nb = (uint32_t)nbits0; tr.nsoft = 0;
+			nbits0 = st.nbits; tr.nb = (uint32_t)nbits0; tr.nsoft = 0;
+			/* rebuild the 32-bit word in progress: its complete bytes are in the ring, the last < 8 bits in the state */
+			const uint32_t cnt = tr.nb & 31u, wordoff = ((tr.nb >> 5) << 2) & ring_mask;
+			uint32_t acc = 0;
+			for (uint32_t bb = 0; bb < (cnt >> 3); bb++) acc = (acc << 8) | ring[wordoff + bb];
+			tr.acc = (acc << (cnt & 7u)) | (st.bit_acc & ((1u << (cnt & 7u)) - 1u));
 		} else {
-			tr.freq = center; tr.target = 1.0f;
+			tr.freq = tc.center; tr.target = 1.0f;
 		}
-		float rf = rcp_approx(tr.freq);
-		const float DELTA = 8.0f * ((float)(N + 16) * 1.2e-7f) / center;       /* see demod_pipe.cu */
+		const bool wide = md.freq0 < 0.075f;               /* 40 slots per symbol */
+		constexpr int NOWRAP = 1 << 30;                      /* tiles are not a ring: the wrap of tmx_run never triggers */
 		for (int k = 0; k < ntiles; k++) {
 			const int n = min(T, L - k * T);
 			const int ss = k % NS2;
 			mbar_wait_t(&sm.yfull[ss], (k / NS2) & 1, wacc[0], prof_on);
-			const float (*y)[G][RS] = sm.y[ss];
-			const int ns = own ? n : 0;
-			tm_tile<1, N, SOFT, G, RS>(tr, rf, y, g, ns, center, alpha, beta, max_fdev, DELTA, ring, ring_mask, soft,
-			                           p.soft_stride, n_rounds, n_slow, prof_on);
+			if (own) {
+				const float *yrow = &sm.y[ss][0][g][0];
+				int sabs = 0, sring = 0;
+				if (wide) tmx_run<18, 4, 38, 4, NOWRAP, SOFT>(tr, yrow, sabs, sring, n, tc, ring, ring_mask, soft, p.soft_stride, n_slow);
+				else      tmx_run<8, 4, 18, 4, NOWRAP, SOFT>(tr, yrow, sabs, sring, n, tc, ring, ring_mask, soft, p.soft_stride, n_slow);
+				while (sabs < n)
+					sabs += tmx_literal_round<SOFT>(tr, yrow + sabs, min(41, n - sabs), tc, ring, ring_mask, soft, p.soft_stride);
+			}
 			__syncwarp();
 			warp_arrive(&sm.yfree[ss], lane);
 		}
+		if (!SOFT) tr.nsoft = (int)(tr.nb - (uint32_t)nbits0);
+		n_rounds = tr.nsoft;
 		if (own) {
 			demod_state &st = p.st[ch];
 			const uint64_t nbits = nbits0 + (uint64_t)(tr.nb - (uint32_t)nbits0);
-			const int cnt = (int)(tr.nb & 7u);
+			const uint32_t cnt = tr.nb & 31u, wordoff = ((tr.nb >> 5) << 2) & ring_mask, rem = cnt & 7u;
+			for (uint32_t bb = 0; bb < (cnt >> 3); bb++) ring[wordoff + bb] = (uint8_t)(tr.acc >> (cnt - 8u * (bb + 1u)));
+			if (rem) ring[wordoff + (cnt >> 3)] = (uint8_t)(tr.acc << (8u - rem));
 			st.t_prev = tr.prev; st.t_phase = tr.phase; st.t_freq = tr.freq; st.t_state = (int)tr.target;
-			st.bit_acc = tr.acc & ((1u << cnt) - 1u); st.bit_cnt = cnt; st.nbits = nbits; st.nsoft = tr.nsoft;
+			st.bit_acc = tr.acc & ((1u << rem) - 1u); st.bit_cnt = (int)rem; st.nbits = nbits; st.nsoft = tr.nsoft;
 			p.nbits_out[ch] = nbits;
-			if (cnt) ring[(uint32_t)(nbits >> 3) & ring_mask] = (uint8_t)(tr.acc << (8 - cnt));
 		}
 	}
 	if (prof_on && lane == 0) {
