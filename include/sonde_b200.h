@@ -216,7 +216,8 @@ SONDE_API int  sonde_b200_debug_demod_state(sonde_b200 *h, void *out, size_t cap
 SONDE_API void *sonde_b200_stream(sonde_b200 *h);
 
 /* Device-side join: the stream returned by sonde_b200_stream() waits for the framer kernels of every call made
- * so far (they run on an internal stream so that frame(i) overlaps demod(i+1)).  Does not block the host. */
+ * so far.  The framer runs in order on that stream by default, so this is a no-op then; with the experiment switch
+ * SONDE_FRAME_OVERLAP=1 it runs on an internal stream beside the next call's demodulator.  Does not block the host. */
 SONDE_API int  sonde_b200_join(sonde_b200 *h);
 
 /* Block until everything enqueued so far has finished. */

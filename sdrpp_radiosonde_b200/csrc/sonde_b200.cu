@@ -76,7 +76,7 @@ struct sonde_b200 {
 	sonde_frame_rec *d_recs[2] = {nullptr, nullptr};
 	int32_t *d_counts[2] = {nullptr, nullptr};
 	cudaStream_t cstream = nullptr, dstream = nullptr;        /* H2D copies, D2H fetches */
-	cudaStream_t fstream = nullptr;                          /* framer kernels: frame(i) overlaps demod(i+1) */
+	cudaStream_t fstream = nullptr;                          /* framer kernels when SONDE_FRAME_OVERLAP=1: frame(i) beside demod(i+1) */
 	cudaStream_t vstream[4] = {nullptr, nullptr, nullptr, nullptr};   /* one per demod kernel variant: they run concurrently */
 	cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev_demod[2] = {nullptr, nullptr}, evf[2] = {nullptr, nullptr};
@@ -329,8 +329,8 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 	if (sonde_upload_modems_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_modems_afsk_pipe(h->modems) != cudaSuccess) return bail(SONDE_ERR_CUDA);
 	if (sonde_upload_gf_tables() != cudaSuccess) return bail(SONDE_ERR_CUDA);
-	/* Stream priorities: frame(i) (fstream) and demod(i+1) (stream) become runnable at the same moment, when demod(i)
-	 * retires.  The demodulator is the critical path and needs one large CTA on every SM; if the framer's small CTAs are
+	/* Stream priorities (matter only with SONDE_FRAME_OVERLAP=1, see run_chunk): frame(i) (fstream) and demod(i+1) (stream)
+	 * become runnable at the same moment, when demod(i) retires.  The demodulator is the critical path and needs one large CTA on every SM; if the framer's small CTAs are
 	 * placed first, several of them land on each SM and the demodulator's CTA has to wait until they have finished
 	 * (measured: the step cost demod + frame although the two overlap).  With the demodulator streams at the highest
 	 * priority its CTAs are placed first and the framer fills what is left beside them. */
@@ -654,7 +654,6 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 	CK(cudaEventRecord(h->ev[1], h->stream));
 	CK(cudaEventRecord(h->ev_demod[par], h->stream));
 
-	/* the framer runs on its own stream: frame(i) overlaps demod(i+1); framer kernels stay in order */
 	frame_params fp;
 	memset(&fp, 0, sizeof(fp));
 	fp.n_channels = h->cfg.n_channels;
