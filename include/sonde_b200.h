@@ -203,6 +203,11 @@ SONDE_API void *sonde_b200_host_alloc(size_t bytes);
 SONDE_API void *sonde_b200_host_alloc_wc(size_t bytes);
 SONDE_API void  sonde_b200_host_free(void *p);
 
+/* Diagnostics, host only (no GPU needed): how a batch of `types` would be grouped into CTAs — per kernel variant v = 0..3
+ * out17[4 v + {0,1,2,3}] = groups, channels per group, rows of the TMA box (0: one bulk copy per row), input-row step of a
+ * group's channels; out17[16] = CTAs of one call including cluster padding. */
+SONDE_API int  sonde_b200_debug_plan(const int32_t *types, int n_channels, int samplerate, int n_sms, int32_t *out17);
+
 /* Diagnostics: the first call switches on the pipeline kernel's per-CTA stall counters; later calls copy them
  * out: out[groups][16] cycles = [role*4 + {wait for input, wait for output slot, total}], roles 0..3 = parallel
  * warps, AGC bias lane, AGC level lane, timing lane.  Returns the number of CTA groups. */

@@ -25,7 +25,7 @@ EXPORTS = [
     "sonde_b200_process_iq_s16", "sonde_b200_process_iq_device", "sonde_b200_process_fm_device", "sonde_b200_max_frames",
     "sonde_b200_fetch", "sonde_b200_fetch_counts", "sonde_b200_fetch_totals", "sonde_b200_detected_types", "sonde_b200_auto_plausible", "sonde_b200_bits_stride", "sonde_b200_fetch_bits",
     "sonde_b200_soft_stride", "sonde_b200_fetch_soft", "sonde_b200_fetch_state", "sonde_b200_modem_info",
-    "sonde_b200_host_alloc", "sonde_b200_host_alloc_wc", "sonde_b200_host_free", "sonde_b200_debug_stalls", "sonde_b200_debug_demod_state", "sonde_b200_process_iq_peer", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
+    "sonde_b200_host_alloc", "sonde_b200_host_alloc_wc", "sonde_b200_host_free", "sonde_b200_debug_plan", "sonde_b200_debug_stalls", "sonde_b200_debug_demod_state", "sonde_b200_process_iq_peer", "sonde_b200_stream", "sonde_b200_sync", "sonde_b200_join",
     "sonde_b200_last_kernel_ms", "sonde_b200_launch_count", "sonde_b200_last_error", "sonde_b200_version",
 ]
 

@@ -259,6 +259,52 @@ int max_new_bits(const sonde_modem &m, int len)
 
 extern "C" {
 
+/* Host-only view of how a batch would be laid out on the GPU (no device needed; what build_groups decides): per kernel
+ * variant v = 0..3 (RS41-like, 2400-baud GFSK, two-branch M10/M20, AFSK) out[4 v + {0,1,2,3}] = CTA groups, channels per
+ * group, rows of the TMA box (0 = one bulk copy per row), input-row step between the channels of a group; out[16] = CTAs
+ * including the padding of the cluster-of-two launches of a mixed batch.  types[c] may be SONDE_AUTO. */
+int sonde_b200_debug_plan(const int32_t *types, int n_channels, int samplerate, int n_sms, int32_t *out17)
+{
+	if (!types || n_channels <= 0 || !out17) return SONDE_ERR_ARG;
+	static const int32_t kAutoOrder[SONDE_NTYPES] = {SONDE_RS41, SONDE_M10, SONDE_IMS100, SONDE_DFM09, SONDE_IMET4,
+	                                                SONDE_C50, SONDE_MRZN1};
+	sonde_b200 tmp;
+	sonde_b200 *h = &tmp;
+	for (int c = 0; c < n_channels; c++) {
+		if (types[c] == SONDE_AUTO) {
+			for (int k = 0; k < SONDE_NTYPES; k++) { h->types.push_back(kAutoOrder[k]); h->in_row_host.push_back(c); }
+		} else if (types[c] >= 0 && types[c] < SONDE_NTYPES) {
+			h->types.push_back(types[c]);
+			h->in_row_host.push_back(c);
+		} else {
+			return SONDE_ERR_ARG;
+		}
+	}
+	h->n_user = n_channels;
+	h->cfg.n_channels = (int32_t)h->types.size();
+	h->n_sms = n_sms;
+	for (int t = 0; t < SONDE_NTYPES; t++)
+		if (sonde_modem_init(&h->modems[t], t, samplerate)) memset(&h->modems[t], 0, sizeof(sonde_modem));
+	std::vector<int32_t> gchan, gtype;
+	build_groups(h, nullptr, gchan, gtype);
+	int n_var = 0, total = 0;
+	for (int v = 0; v < 4; v++) n_var += h->groups_v[v] > 0;
+	for (int v = 0; v < 4; v++) {
+		int gsz = 0;
+		int gi = 0;
+		for (int k = 0; k < v; k++) gi += h->groups_v[k];
+		if (h->groups_v[v])
+			for (int j = 0; j < DEMOD_G && gchan[(size_t)gi * DEMOD_G + j] >= 0; j++) gsz++;
+		out17[4 * v + 0] = h->groups_v[v];
+		out17[4 * v + 1] = gsz;
+		out17[4 * v + 2] = h->box_rows_v[v];
+		out17[4 * v + 3] = h->row_step_v[v];
+		total += n_var > 1 ? (h->groups_v[v] + 1) & ~1 : h->groups_v[v];
+	}
+	out17[16] = total;
+	return SONDE_OK;
+}
+
 const char *sonde_b200_version(void) { return "sonde_b200 0.1 (sm_100a)"; }
 
 const char *sonde_b200_last_error(const sonde_b200 *h) { return h ? h->err.c_str() : "null handle"; }

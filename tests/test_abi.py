@@ -60,3 +60,45 @@ def test_no_cpu_fallback():
     with pytest.raises(capi.SondeError) as e:
         capi.BatchDecoder([synth.RS41], 1024)
     assert e.value.code == capi.ERR_NODEVICE
+
+
+def test_batch_layout_plan_host_only():
+    """sonde_b200_debug_plan (no GPU): how build_groups lays a batch out on 148 SMs.  Per kernel variant: groups, channels
+    per group, rows of the TMA box (0 = one bulk copy per row), input-row step of a group's channels; total CTAs."""
+    import ctypes
+    import numpy as np
+    from sdrpp_radiosonde_b200 import capi, synth
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    lib.sonde_b200_debug_plan.restype = ctypes.c_int
+
+    def plan(types, sms=148):
+        t = np.ascontiguousarray(types, dtype=np.int32)
+        out = np.zeros(17, dtype=np.int32)
+        rc = lib.sonde_b200_debug_plan(t.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(t.size), ctypes.c_int(48000),
+                                       ctypes.c_int(sms), out.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        return out[:16].reshape(4, 4), int(out[16])
+
+    # BASELINE config 2: 1024 x RS41 -> 147 CTAs of 7 channels on the 148 SMs, one tensor box of 7 consecutive rows per tile
+    v, total = plan(np.full(1024, synth.RS41))
+    assert v[0].tolist() == [147, 7, 7, 1] and total == 147 and v[1:, 0].sum() == 0
+    # fewer channels than SMs: one channel per CTA
+    v, total = plan(np.full(146, synth.RS41))
+    assert v[0].tolist() == [146, 1, 1, 1]
+    # config 3: DFM and M10 on alternating channels -> two waves, each group's channels two rows apart (3-D tensor map)
+    v, total = plan([synth.DFM09 if c % 2 == 0 else synth.M10 for c in range(2048)])
+    assert v[1].tolist() == [147, 7, 7, 2] and v[2].tolist() == [147, 7, 7, 2] and total == 296
+    # config 5, typed: seven types interleaved -> every variant padded to an even CTA count (clusters of two), all of it
+    # within one wave, the AFSK kernel gets the smaller groups, rows 7 apart
+    v, total = plan([c % 7 for c in range(1024)])
+    assert total <= 148
+    assert v[3][1] < v[0][1] and v[3][1] <= v[2][1]
+    assert all(int(r[3]) == 7 for r in v if r[0] > 0) and all(int(r[2]) == int(r[1]) for r in v if r[0] > 0)
+    padded = sum((int(g) + 1) & ~1 for g in v[:, 0])
+    assert padded == total
+    # AUTO channels: the virtual channels of one decoder are consecutive user channels -> consecutive rows
+    v, total = plan(np.full(64, -1))
+    assert all(int(r[3]) == 1 and int(r[2]) == int(r[1]) for r in v if r[0] > 0)
+    # a batch whose groups are not evenly spaced falls back to row copies for that variant
+    v, total = plan([synth.RS41, synth.M10, synth.RS41, synth.RS41, synth.M10, synth.RS41, synth.RS41] * 64)
+    assert v[0][2] == 0
