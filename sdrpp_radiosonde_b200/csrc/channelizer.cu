@@ -356,6 +356,7 @@ struct sonde_chan {
 	chan_maps maps;
 	CUtensorMap tmB;
 	uint64_t n_consumed = 0;            /* wideband samples consumed so far */
+	unsigned long long peers_enabled = 0;   /* source devices already given peer access (process_c64_peer) */
 	long n_calls = 0;
 	cudaEvent_t ev[2] = {nullptr, nullptr};
 	bool have_timing = false;
@@ -604,7 +605,7 @@ static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float
 		const size_t esz = (kind == 1 || kind == 4) ? sizeof(float2) : kind == 2 ? sizeof(short2) : sizeof(uchar2);
 		if (!h->d_in) CCK(cudaMalloc(&h->d_in, (size_t)h->cfg.max_in_len * sizeof(float2)));
 		if (kind == 4) {
-			if (src_device != h->cfg.device) {
+			if (src_device != h->cfg.device && !(src_device >= 0 && src_device < 64 && ((h->peers_enabled >> src_device) & 1ull))) {
 				int can = 0;
 				CCK(cudaDeviceCanAccessPeer(&can, h->cfg.device, src_device));
 				if (can) {
@@ -612,6 +613,7 @@ static int chan_run(sonde_chan *h, const void *src, size_t n_in, int kind, float
 					if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cfail(h, SONDE_ERR_CUDA, "cudaDeviceEnablePeerAccess");
 					(void)cudaGetLastError();
 				}
+				if (src_device >= 0 && src_device < 64) h->peers_enabled |= 1ull << src_device;   /* without P2P the driver stages the copy */
 			}
 			CCK(cudaMemcpyPeerAsync(h->d_in, h->cfg.device, src, src_device, n_in * esz, st));
 		} else {
