@@ -656,7 +656,7 @@ static int run_chunk(sonde_b200 *h, const void *d_in, size_t len, size_t row_str
 		const char *e = getenv("SONDE_PW_MASK");
 		return e ? (uint32_t)strtoul(e, nullptr, 16) : 0u;
 	}();
-	static const uint32_t kPwMask[3] = {0xCCCFCCu /* RS41 */, 0xCCCFCCu /* DFM, iMS-100, MRZ-N1 */, 0xCCEECCu /* M10/M20: two PW warps beside the AGC warp */};
+	static const uint32_t kPwMask[3] = {0xCCCFCCu /* RS41 */, 0xCCDFCCu /* DFM, iMS-100, MRZ-N1: their timing lane has slack for a second PW warp on its SMSP */, 0xCCEECCu /* M10/M20: two PW warps beside the AGC warp */};
 	const int par = (int)(h->n_issued & 1);
 	dp.nbits_out = h->d_nbits[par];
 	static const int tpc_env = getenv("SONDE_TPC_PAIRS") ? atoi(getenv("SONDE_TPC_PAIRS")) : -1;     /* experiment switch */
