@@ -12,7 +12,11 @@
  *                    or a comma-separated list, one per file
  *     -b, --buflen   samples per channel per GPU call (default 1024 = the reference's BUFLEN, SD/main.c:32)
  *     -c, --csv      write <prefix><channel>.csv per channel
- *     -i, --iq       the files are raw complex64 IQ at 48 kS/s instead of raw float32 FM audio (SD/main.c:257-262)
+ *     -i, --iq       the files are raw complex64 IQ at 48 kS/s instead of FM audio
+ * Input files are read the way the reference reads them (SD/main.c:248-266, SD/io/wavfile.c): a file that starts with a
+ * 44-byte RIFF/WAVE header is a WAV recording (8 / 16 / 32-bit samples, first channel, 32 KiB blocks — a trailing partial
+ * block is ignored, as there), anything else raw mono float32 at 48 kHz read from behind those 44 bytes.  All recordings
+ * of a batch must have the same sample rate.
  *     -q, --quiet    no per-point lines on stdout
  * stdout (unless -q): one line per data point  "<channel> <serial> <seq> <lat> <lon> <alt> <temp>"
  * and always one summary line per channel     "CH <channel> type=<decoder> frames=<n> ok=<n> points=<n>".
@@ -30,6 +34,56 @@
 #include "telemetry.hpp"
 
 namespace {
+
+/* One recording, read like the reference's wav_read_wrapper / raw_read_wrapper (SD/main.c:384-405, SD/io/wavfile.c:33-113) */
+struct Input {
+	FILE *f = nullptr;
+	bool wav = false;
+	int bps = 32, nch = 1, rate = 48000;
+	std::vector<unsigned char> blk;
+	size_t off = 0;                              /* position in the current block, in samples of bps/8 bytes */
+
+	bool open(const char *name, bool iq)
+	{
+		if (!(f = fopen(name, "rb"))) return false;
+		if (iq) return true;
+		unsigned char hdr[44];
+		if (fread(hdr, sizeof(hdr), 1, f) == 1 && !memcmp(hdr, "RIFF", 4) && !memcmp(hdr + 8, "WAVE", 4)) {
+			nch = hdr[22] | (hdr[23] << 8);
+			rate = (int)(hdr[24] | (hdr[25] << 8) | (hdr[26] << 16) | ((unsigned)hdr[27] << 24));
+			bps = hdr[34] | (hdr[35] << 8);
+			if (bps && nch) { wav = true; blk.resize(32768); }
+		}
+		/* not a WAV file: raw float32 — the reference goes on reading behind the 44 bytes its header probe consumed
+		 * (a file shorter than that is read from wherever the short read left it) */
+		return true;
+	}
+	/* raw: the number of samples read (a short last read is decoded with the previous buffer's tail, SD/main.c:328-333);
+	 * WAV: `count` or 0 — a read that cannot be completed ends the recording */
+	size_t read(void *dst_, size_t count, size_t esz)
+	{
+		if (!f) return 0;
+		if (!wav) return fread(dst_, esz, count, f);
+		float *dst = (float *)dst_;
+		const size_t per = blk.size() / (size_t)(bps / 8), want = count;
+		while (count > 0) {
+			if (!off && fread(blk.data(), blk.size(), 1, f) != 1) return 0;
+			size_t n = (per - off) / (size_t)nch;
+			if (n > count) n = count;
+			if (n == 0) return 0;
+			for (size_t i = 0; i < n; i++, off += (size_t)nch) {
+				if (bps == 8)       *dst++ = (float)(blk[off] - 127);
+				else if (bps == 16) { short v; memcpy(&v, &blk[2 * off], 2); *dst++ = (float)v; }
+				else if (bps == 32) { float v; memcpy(&v, &blk[4 * off], 4); *dst++ = v; }
+				else return 0;
+			}
+			count -= n;
+			off %= per;
+		}
+		return want;
+	}
+	void close() { if (f) fclose(f); f = nullptr; }
+};
 
 const char *kNames[] = {"auto", "c50", "dfm", "imet4", "ims100", "m10", "mrzn1", "rs41"};
 const int kTypes[] = {SONDE_AUTO, SONDE_C50, SONDE_DFM09, SONDE_IMET4, SONDE_IMS100, SONDE_M10, SONDE_MRZN1, SONDE_RS41};
@@ -127,13 +181,15 @@ int main(int argc, char **argv)
 	}
 
 	const size_t esz = iq ? 8 : 4;
-	std::vector<FILE *> in(C, nullptr);
-	for (size_t c = 0; c < C; c++)
-		if (!(in[c] = fopen(files[c].c_str(), "rb"))) { fprintf(stderr, "cannot open %s\n", files[c].c_str()); return 2; }
+	std::vector<Input> in(C);
+	for (size_t c = 0; c < C; c++) {
+		if (!in[c].open(files[c].c_str(), iq)) { fprintf(stderr, "cannot open %s\n", files[c].c_str()); return 2; }
+		if (in[c].rate != in[0].rate) { fprintf(stderr, "%s: %d S/s, the batch runs at %d S/s\n", files[c].c_str(), in[c].rate, in[0].rate); return 2; }
+	}
 
 	sonde_b200_config cfg = {};
 	cfg.n_channels = (int32_t)C;
-	cfg.samplerate = 48000;
+	cfg.samplerate = in[0].rate;
 	cfg.max_chunk_len = (int32_t)buflen;
 	cfg.types = types.data();
 	sonde_b200 *h = nullptr;
@@ -174,10 +230,10 @@ int main(int argc, char **argv)
 		bool any = false;
 		for (size_t c = 0; c < C; c++) {
 			char *row = stage[slot] + c * buflen * esz;
-			const size_t got = in[c] ? fread(row, esz, buflen, in[c]) : 0;
+			const size_t got = in[c].read(row, buflen, esz);
 			if (got == 0) {
 				memset(row, 0, buflen * esz);
-				if (in[c]) { fclose(in[c]); in[c] = nullptr; }
+				in[c].close();
 			} else {
 				any = true;
 				last_call[c] = n_submitted;          /* this call still carries samples of recording c */
@@ -233,7 +289,7 @@ int main(int argc, char **argv)
 	for (size_t c = 0; c < C; c++) {
 		printf("CH %zu type=%s frames=%ld ok=%ld points=%ld\n", c, name_of(locked[c]), n_frames[c], n_ok[c], n_points[c]);
 		if (csv[c]) fclose(csv[c]);
-		if (in[c]) fclose(in[c]);
+		in[c].close();
 	}
 	sonde_b200_host_free(stage[0]);
 	sonde_b200_host_free(stage[1]);
