@@ -286,10 +286,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # the decode kernel runs one CTA per SM on 128 of the 148 SMs; keep NCCL's copy kernels inside the 20 free
-        # SMs so that a scatter running beside it does not push decode CTAs into a second wave
-        # (and NCCL's default 4-CTA clusters cannot be placed at all in the scattered free SMs while the decode kernel
-        # is resident: with clusters the scatter simply queues behind the decode — measured, tools/scatter_probe.py)
+        # NCCL only carries barriers, the timing / count reductions and (shard.gather_records) the record all-gather here; the
+        # single-source legs below move their data with the copy engines.  Small CTA budget and no clusters, so that a
+        # collective never has to wait for SMs the decode kernel (one large CTA on 147 of the 148 SMs) holds.
         os.environ.setdefault("NCCL_MAX_CTAS", "16")
         os.environ.setdefault("NCCL_CGA_CLUSTER_SIZE", "1")
         os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
