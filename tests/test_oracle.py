@@ -266,3 +266,71 @@ def test_discriminator_drift_vs_libm_atan2f():
     fl = ref.frames_run(synth.RS41, fm_libm, 48000)
     assert [int(r.ok) for r in fp] == [int(r.ok) for r in fl] and sum(int(r.ok) for r in fp) >= 3
     assert [bytes(r.data[:320]) for r in fp if r.ok] == [bytes(r.data[:320]) for r in fl if r.ok]
+
+
+def _gf_tables(m, poly):
+    """alpha[] / logtable[] exactly as rs_init_internal builds them (SD/decode/ecc/rs.c:66-89): n = 2^m - 1 entries of
+    successive doublings reduced by `poly`; logtable[1] ends up = n, not 0, because alpha[n] = 1 overwrites it."""
+    n = (1 << m) - 1
+    ex, lg = [0] * (n + 1), [0] * (n + 1)
+    a = 1
+    ex[0] = 1
+    for i in range(1, n + 1):
+        a <<= 1
+        if a > n:
+            a ^= poly
+        ex[i] = a
+        lg[a] = i
+    return n, ex, lg
+
+
+def test_gf_polynomial_evaluation_by_independent_terms():
+    """The framer kernel evaluates every polynomial over GF(2^m) as an XOR of independent table reads
+    exp[(log c_k + k log x) mod n] where the reference uses Horner's rule with its log/antilog multiply
+    (rs.c:215-224, 258-270).  Same field element, including through the logtable[1] == n quirk — checked here on
+    random polynomials for both fields (GF(256)/0x11D of RS(255,231), GF(64)/0x61 of BCH(63,51)), for the
+    binary-coefficient case the BCH syndromes use, and at every evaluation point."""
+    rng = np.random.default_rng(11)
+    for m, poly in ((8, 0x11D), (6, 0x61)):
+        n, ex, lg = _gf_tables(m, poly)
+        assert lg[1] == n and ex[0] == 1 and ex[n] == 1
+
+        def mul(x, y):
+            return 0 if (x == 0 or y == 0) else ex[(lg[x] + lg[y]) % n]
+
+        def horner(coef, x):                     # coef[k] multiplies x^k
+            r = 0
+            for c in reversed(coef):
+                r = mul(r, x) ^ c
+            return r
+
+        def terms(coef, x):
+            r = 0
+            for k, c in enumerate(coef):
+                if c:
+                    r ^= ex[(lg[c] + k * lg[x]) % n]
+            return r
+
+        for _ in range(60):
+            deg = int(rng.integers(1, 25))
+            coef = [int(v) for v in rng.integers(0, n + 1, deg + 1)]
+            if rng.random() < 0.3:
+                coef = [c if rng.random() < 0.5 else 0 for c in coef]
+            for x in range(1, n + 1):
+                assert horner(coef, x) == terms(coef, x), (m, coef, x)
+        # binary message polynomials at the BCH roots alpha^1 .. alpha^4: XOR of alpha^(j k) over the set bits
+        if m == 6:
+            for _ in range(200):
+                msg = int(rng.integers(0, 1 << 62)) | (int(rng.integers(0, 2)) << 62)
+                bits = [(msg >> k) & 1 for k in range(63)]
+                for j in range(1, 5):
+                    z = 1 << j                                   # roots {2, 4, 8, 16}
+                    want = horner(bits, z)
+                    got = 0
+                    for k in range(63):
+                        if bits[k]:
+                            e = j * k
+                            e = (e & 63) + (e >> 6)
+                            e = e - 63 if e >= 63 else e
+                            got ^= ex[e]
+                    assert want == got, (msg, j)
