@@ -3,15 +3,20 @@
  *
  * The reference's CLI (SD/main.c:96-366) decodes ONE recording per process: read 1024 samples, decode(), print,
  * append to CSV/GPX/KML.  This runner decodes MANY recordings at once — every input file is one channel of one GPU
- * batch — and writes, per channel, the same CSV the reference's `-c` option writes (SD/io/csv.c:8-60) from the same
- * aggregation of decoder fragments (SD/decode.c:278-376 append_data_point: fields accumulate in one `printable`
- * record per channel, pressure falls back to the barometric formula, one row per fragment that carried data).
+ * batch — and writes, per channel, the same CSV / GPX / KML files the reference's `-c`, `-g`, `-k` and `-l` options write
+ * (SD/io/csv.c, gpx.c, kml.c; the writers are host/track_files.hpp) from the same aggregation of decoder fragments
+ * (SD/decode.c:278-376 append_data_point: fields accumulate in one `printable` record per channel, pressure falls back
+ * to the barometric formula, one row per fragment that carried data).
  *
- *   sonde_b200_batch [-t type] [-b buflen] [-c csv_prefix] [-i] [-q] file0 [file1 ...]
+ *   sonde_b200_batch [-t type] [-b buflen] [-c prefix] [-g prefix] [-k prefix] [-l prefix] [-i] [-q] file0 [file1 ...]
  *     -t, --type     auto|c50|dfm|imet4|ims100|m10|mrzn1|rs41 (the reference's names, SD/main.c:66; default auto),
  *                    or a comma-separated list, one per file
  *     -b, --buflen   samples per channel per GPU call (default 1024 = the reference's BUFLEN, SD/main.c:32)
  *     -c, --csv      write <prefix><channel>.csv per channel
+ *     -g, --gpx      write <prefix><channel>.gpx per channel: one track per serial, points that carry position and speed
+ *     -k, --kml      write <prefix><channel>.kml per channel
+ *     -l, --live-kml write <prefix><channel>.kml (a network link) and <prefix><channel>.kml-live.kml, which is complete
+ *                    after every point
  *     -i, --iq       the files are raw complex64 IQ at 48 kS/s instead of FM audio
  * Input files are read the way the reference reads them (SD/main.c:248-266, SD/io/wavfile.c): a file that starts with a
  * 44-byte RIFF/WAVE header is a WAV recording (8 / 16 / 32-bit samples, first channel, 32 KiB blocks — a trailing partial
@@ -32,6 +37,7 @@
 #include "../../include/sonde_b200.h"
 #include "sonde_data.hpp"
 #include "telemetry.hpp"
+#include "track_files.hpp"
 
 namespace {
 
@@ -129,28 +135,11 @@ bool append_data_point(SondeData &printable, const SondeData &d)
 	return true;
 }
 
-/* SD/io/csv.c:26-60 */
-void csv_add_point(FILE *f, const SondeData &d)
-{
-	char timestr[sizeof("YYYY-MM-DDThh:mm:ssZ") + 1];
-	if (d.fields & DATA_TIME) {
-		strftime(timestr, sizeof(timestr), "%Y-%m-%dT%H:%M:%SZ", gmtime(&d.time));
-		fprintf(f, "%s,", timestr);
-	} else {
-		fprintf(f, ",");
-	}
-	if (d.fields & DATA_PTU) fprintf(f, "%f,%f,%f,", d.temp, d.rh, d.pressure); else fprintf(f, ",,,");
-	if (d.fields & DATA_POS) fprintf(f, "%f,%f,%f,", d.lat, d.lon, d.alt); else fprintf(f, ",,,");
-	if (d.fields & DATA_SPEED) fprintf(f, "%f,%f,%f,", d.speed, d.heading, d.climb); else fprintf(f, ",,,");
-	if (d.fields & DATA_OZONE) fprintf(f, "O3=%fmPa", d.o3_mpa);
-	fprintf(f, "\n");
-}
-
 }  // namespace
 
 int main(int argc, char **argv)
 {
-	std::string type_arg = "auto", csv_prefix;
+	std::string type_arg = "auto", csv_prefix, gpx_prefix, kml_prefix, live_prefix;
 	size_t buflen = 1024;
 	bool iq = false, quiet = false;
 	std::vector<std::string> files;
@@ -160,9 +149,12 @@ int main(int argc, char **argv)
 		if (a == "-t" || a == "--type") type_arg = need("-t");
 		else if (a == "-b" || a == "--buflen") buflen = strtoul(need("-b").c_str(), nullptr, 10);
 		else if (a == "-c" || a == "--csv") csv_prefix = need("-c");
+		else if (a == "-g" || a == "--gpx") gpx_prefix = need("-g");
+		else if (a == "-k" || a == "--kml") kml_prefix = need("-k");
+		else if (a == "-l" || a == "--live-kml") live_prefix = need("-l");
 		else if (a == "-i" || a == "--iq") iq = true;
 		else if (a == "-q" || a == "--quiet") quiet = true;
-		else if (a == "-h" || a == "--help") { printf("usage: %s [-t type[,type...]] [-b buflen] [-c csv_prefix] [-i] [-q] file...\n", argv[0]); return 0; }
+		else if (a == "-h" || a == "--help") { printf("usage: %s [-t type[,type...]] [-b buflen] [-c csv_prefix] [-g gpx_prefix] [-k kml_prefix] [-l live_kml_prefix] [-i] [-q] file...\n", argv[0]); return 0; }
 		else files.push_back(a);
 	}
 	const size_t C = files.size();
@@ -203,16 +195,24 @@ int main(int argc, char **argv)
 	std::vector<int32_t> counts(C), locked(types);
 	std::vector<radiosonde::Telemetry> tele;
 	std::vector<SondeData> printable(C), fragment(C);
-	std::vector<FILE *> csv(C, nullptr);
+	struct Outputs {
+		radiosonde::cli::CsvFile csv;
+		radiosonde::cli::GpxFile gpx;
+		radiosonde::cli::KmlFile kml, live;
+	};
+	std::vector<Outputs> out(C);
 	std::vector<long> n_frames(C, 0), n_ok(C, 0), n_points(C, 0);
 	for (size_t c = 0; c < C; c++) {
 		tele.emplace_back(types[c] == SONDE_AUTO ? SONDE_RS41 : types[c]);
 		memset(&printable[c], 0, sizeof(SondeData));
 		memset(&fragment[c], 0, sizeof(SondeData));
-		if (!csv_prefix.empty()) {
-			const std::string name = csv_prefix + std::to_string(c) + ".csv";
-			if (!(csv[c] = fopen(name.c_str(), "wb"))) { fprintf(stderr, "cannot create %s\n", name.c_str()); return 2; }
-			fprintf(csv[c], "Time,Temperature,RH,Pressure,Latitude,Longitude,Altitude,Speed,Heading,Climb,XDATA\n");
+		const std::string ch = std::to_string(c);
+		if ((!csv_prefix.empty() && !out[c].csv.init((csv_prefix + ch + ".csv").c_str())) ||
+		    (!gpx_prefix.empty() && !out[c].gpx.init((gpx_prefix + ch + ".gpx").c_str())) ||
+		    (!kml_prefix.empty() && out[c].kml.init((kml_prefix + ch + ".kml").c_str(), false)) ||
+		    (!live_prefix.empty() && out[c].live.init((live_prefix + ch + ".kml").c_str(), true))) {
+			fprintf(stderr, "cannot create the output files of channel %zu\n", c);
+			return 2;
 		}
 	}
 	/* two pinned staging buffers: buffer k+1 is read and submitted while buffer k decodes (sonde_b200.h, fetch()) */
@@ -275,7 +275,15 @@ int main(int argc, char **argv)
 				n_points[c]++;
 				const SondeData &d = printable[c];
 				if (!quiet) printf("%zu %s %d %.5f %.5f %.1f %.1f\n", c, d.serial, d.seq, d.lat, d.lon, d.alt, d.temp);
-				if (csv[c]) csv_add_point(csv[c], d);
+				/* SD/main.c:347-365 */
+				Outputs &o = out[c];
+				o.csv.add_point(d);
+				o.kml.start_track(d.serial);
+				o.kml.add_trackpoint(d);
+				o.live.start_track(d.serial);
+				o.live.add_trackpoint(d);
+				if (d.fields & DATA_SERIAL) o.gpx.start_track(d.serial);
+				o.gpx.add_trackpoint(d);
 			}
 		}
 	};
@@ -288,7 +296,10 @@ int main(int argc, char **argv)
 	if (in_flight) deliver();
 	for (size_t c = 0; c < C; c++) {
 		printf("CH %zu type=%s frames=%ld ok=%ld points=%ld\n", c, name_of(locked[c]), n_frames[c], n_ok[c], n_points[c]);
-		if (csv[c]) fclose(csv[c]);
+		out[c].kml.close();
+		out[c].live.close();
+		out[c].gpx.close();
+		out[c].csv.close();
 		in[c].close();
 	}
 	sonde_b200_host_free(stage[0]);

@@ -1,0 +1,69 @@
+"""SURVEY.md §8 f-4, the file writers: sdrpp_radiosonde_b200/host/track_files.hpp (the module's GPXWriter / PTUWriter
+and the command-line tool's CSV / GPX / KML / live-KML files) against the reference's own writers, compiled unmodified
+from the sources where they lie into oracle/_ref/libwriters_ref.so (`make -C oracle writers`).  Host code only — no GPU."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+LIB = os.path.join(ROOT, "oracle", "_ref", "libwriters_ref.so")
+EXE = os.path.join(ROOT, "build", "track_files_test")
+
+
+@pytest.fixture(scope="module")
+def driver():
+    if os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "cli", "writers"], check=True, capture_output=True)
+    if not os.path.exists(LIB):
+        pytest.skip("oracle/_ref/libwriters_ref.so not built (needs /root/reference at build time)")
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", f"-I{ROOT}/include",
+                    os.path.join(ROOT, "tests", "cpp", "track_files_test.cpp"), "-o", EXE, "-ldl"], check=True)
+    return EXE
+
+
+def test_writers_match_reference_byte_for_byte(driver, tmp_path):
+    """120 rounds x (module GPX with re-init, PTU log, tool CSV + GPX + KML + live KML + link file) driven with random
+    call sequences: serial changes, refused names, NaN / zero / repeated / out-of-range fixes, negative coordinates,
+    stop without start; mid-run snapshots of the files that are kept complete while they grow."""
+    r = subprocess.run([driver, LIB, str(tmp_path), "120"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout[-500:] + r.stderr[-2000:]
+    n = int(r.stdout.split()[1])
+    assert n >= 120 * 8
+
+
+def test_module_gpx_is_complete_after_every_call(driver, tmp_path):
+    """The property the module's writer exists for (src/gpx.hpp:6-9): whatever the last call was, the file on disk is
+    a complete GPX document.  Checked with an XML parser on a file written by a small program built on the header."""
+    import xml.etree.ElementTree as ET
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "sdrpp_radiosonde_b200/host/track_files.hpp"
+#include <cstdlib>
+int main(int argc, char **argv) {
+	radiosonde::GPXWriter w;
+	if (!w.init(argv[1])) return 2;
+	const int stop_after = atoi(argv[2]);
+	int n = 0;
+	auto done = [&] { if (++n == stop_after) _Exit(0); };       /* dies without running any destructor */
+	w.startTrack("S1234567"); done();
+	for (int i = 0; i < 5; i++) { w.addTrackPoint(1700000000 + i, 45.0f + i * 0.01f, 9.0f, 1000.0f + i, 5.0f, 270.0f); done(); }
+	w.startTrack("T7654321"); done();
+	w.addTrackPoint(1700000100, -33.5f, 151.0f, 20000.0f, 12.0f, 10.0f); done();
+	w.stopTrack(); done();
+	return 0;
+}
+''')
+    exe = tmp_path / "t"
+    subprocess.run(["g++", "-O1", "-std=c++17", f"-I{ROOT}", f"-I{ROOT}/include", str(src), "-o", str(exe)], check=True)
+    ns = {"g": "http://www.topografix.com/GPX/1/1"}
+    for stop_after in range(1, 10):
+        out = tmp_path / f"o{stop_after}.gpx"
+        subprocess.run([str(exe), str(out), str(stop_after)], check=True)
+        root = ET.parse(out).getroot()                          # raises on a file that is not well-formed
+        trks = root.findall("g:trk", ns)
+        pts = root.findall(".//g:trkpt", ns)
+        assert len(trks) == (1 if stop_after <= 6 else 2)
+        assert len(pts) == min(max(stop_after - 1, 0), 5) + (1 if stop_after >= 8 else 0)
+        assert trks[0].find("g:name", ns).text == "S1234567"
