@@ -6,11 +6,15 @@ same autodetect decision."""
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
 
 from sdrpp_radiosonde_b200 import synth
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import batch_checks  # noqa: E402
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 REF = os.path.join(ROOT, "oracle", "_ref", "sondedump_ref")
@@ -106,94 +110,13 @@ def test_batch_runner_fails_loudly_without_gpu(tmp_path):
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/sondedump_ref not built")
 def test_batch_runner_csv_equals_reference_cli_per_channel(tmp_path):
-    """sonde_b200_batch (the runner of its own on the batch ABI): five recordings of five sonde
-    types — of different lengths, one not a multiple of the 1024-sample buffer — decoded in ONE batch; every channel's
-    CSV must be byte-identical to what the reference's CLI writes for that recording alone (-t <type> -c)."""
-    cases = [("rs41", synth.RS41, 48000 * 6), ("dfm", synth.DFM09, 48000 * 5 + 1024 * 3), ("m10", synth.M10, 48000 * 4 + 517),
-             ("c50", synth.C50, 48000 * 4), ("mrzn1", synth.MRZN1, 48000 * 5)]
-    files = []
-    for i, (flag, stype, n) in enumerate(cases):
-        raw = tmp_path / f"in{i}.raw"
-        synth.make_fm(synth.default_spec(stype, 10 + i), n).astype(np.float32).tofile(raw)
-        files.append(str(raw))
-    r = subprocess.run([BATCH, "-q", "-t", ",".join(c[0] for c in cases), "-c", str(tmp_path / "b200_"), *files],
-                       capture_output=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
-    for i, (flag, stype, n) in enumerate(cases):
-        ref_csv = tmp_path / f"ref{i}.csv"
-        a = subprocess.run([REF, "-q", "-t", flag, "-c", str(ref_csv), files[i]], capture_output=True, timeout=600)
-        assert a.returncode == 0, a.stderr[-300:]
-        want, got = ref_csv.read_bytes(), (tmp_path / f"b200_{i}.csv").read_bytes()
-        assert want.count(b"\n") >= 3, (flag, want[:200])
-        # decode() passes an UNINITIALISED SondeData to the decoder (SD/decode.c:128) and e.g. dfm09_decode returns PARSED
-        # for an undecodable first window without touching it: the reference then logs a "data point" whose fields are
-        # whatever its stack held — a row of nothing but commas.  Such rows carry no data and are dropped from both files.
-        def rows(b):
-            return [l for l in b.split(b"\n") if l.strip(b",")]
-        rg, rw = rows(got), rows(want)
-        assert rg[0] == rw[0]
-        # start-up: the reference's per-decoder state is malloc()ed and not cleared (e.g. MRZ-N1 calibration,
-        # SD/sonde/mrz-n1/mrzn1.c:13-28), so whether the very first frame already yields a data point depends on heap
-        # garbage; this repo's parsers start from zeros (DESIGN.md §1).  At most one such leading row may differ — every
-        # row after it must be identical.
-        n = min(len(rg), len(rw)) - 1
-        assert abs(len(rg) - len(rw)) <= 1 and n >= 3 and rg[-n:] == rw[-n:], (flag, got[:300], want[:300])
-    # the AUTO path of the runner: same recordings, every channel autodetects its decoder
-    r2 = subprocess.run([BATCH, "-q", "-t", "auto", *files], capture_output=True, timeout=600)
-    assert r2.returncode == 0
-    locked = [l.split()[2].split("=")[1] for l in r2.stdout.decode().splitlines() if l.startswith("CH ")]
-    assert locked == [c[0] for c in cases], r2.stdout[-400:]
-
-
-def _write_wav(path, data, rate=48000):
-    """data: [n] or [n][channels], int16 or float32; the plain 44-byte header the reference's wav_parse expects"""
-    import struct
-    data = np.ascontiguousarray(data)
-    nch = 1 if data.ndim == 1 else data.shape[1]
-    bps = data.dtype.itemsize * 8
-    raw = data.tobytes()
-    hdr = b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE" + b"fmt " + struct.pack(
-        "<IHHIIHH", 16, 1 if bps == 16 else 3, nch, rate, rate * nch * bps // 8, nch * bps // 8, bps) + b"data" + struct.pack("<I", len(raw))
-    assert len(hdr) == 44
-    with open(path, "wb") as f:
-        f.write(hdr + raw)
+    """five recordings of five sonde types in ONE batch, every channel's CSV equal to the reference CLI's; then the AUTO
+    path of the runner (tests/batch_checks.py)"""
+    batch_checks.check_csv_per_channel(BATCH, tmp_path, auto=True)
 
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/sondedump_ref not built")
 def test_batch_runner_wav_inputs_equal_reference_cli(tmp_path):
-    """WAV recordings through sonde_b200_batch, read the way the reference reads them (SD/io/wavfile.c: 44-byte header,
-    first channel, raw sample values, 32 KiB blocks with the trailing partial block ignored): 16-bit mono, 32-bit float
-    stereo (second channel is noise) and a raw float32 file in one batch; every channel's CSV equals sondedump_ref's."""
-    rng = np.random.default_rng(3)
-    n = 48000 * 5 + 777
-    fm0 = synth.make_fm(synth.default_spec(synth.RS41, 21), n)
-    fm1 = synth.make_fm(synth.default_spec(synth.M10, 22), n)
-    fm2 = synth.make_fm(synth.default_spec(synth.DFM09, 23), n)
-    w0, w1, r2 = tmp_path / "a.wav", tmp_path / "b.wav", tmp_path / "c.raw"
-    _write_wav(w0, np.clip(np.round(fm0 * (12000.0 / np.abs(fm0).max())), -32768, 32767).astype(np.int16))
-    _write_wav(w1, np.stack([fm1.astype(np.float32), rng.standard_normal(n).astype(np.float32)], axis=1))
-    fm2.astype(np.float32).tofile(r2)
-    files, flags = [str(w0), str(w1), str(r2)], ["rs41", "m10", "dfm"]
-    r = subprocess.run([BATCH, "-q", "-t", ",".join(flags), "-c", str(tmp_path / "b200_"), *files], capture_output=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
-    for i, flag in enumerate(flags):
-        ref_csv = tmp_path / f"ref{i}.csv"
-        a = subprocess.run([REF, "-q", "-t", flag, "-c", str(ref_csv), files[i]], capture_output=True, timeout=600)
-        assert a.returncode == 0, a.stderr[-300:]
-
-        def rows(b):
-            # a time value that does not fit the reference's fixed buffer (the synthetic DFM's date decodes to an 8-digit
-            # year) is printed cut off, followed by whatever byte of the reference's stack comes next (SD/io/csv.c): the time
-            # field of such rows is masked in both files, everything else is compared
-            ok = re.compile(rb"^\d{4}-\d{2}-\d{2}T\d{2}:\d{2}:\d{2}Z,")
-            out = []
-            for l in b.split(b"\n"):
-                if not l.strip(b","):
-                    continue
-                out.append(l if (ok.match(l) or l.startswith(b"Time,")) else b"<time>," + l.split(b",", 1)[-1])
-            return out
-        rg, rw = rows((tmp_path / f"b200_{i}.csv").read_bytes()), rows(ref_csv.read_bytes())
-        assert len(rw) >= 4, (flag, rw[:2])
-        m = min(len(rg), len(rw)) - 1
-        assert abs(len(rg) - len(rw)) <= 1 and m >= 3 and rg[-m:] == rw[-m:], (flag, rg[:3], rw[:3])
+    """16-bit mono WAV, 32-bit float stereo WAV and a raw float32 file in one batch (tests/batch_checks.py)"""
+    batch_checks.check_wav_inputs(BATCH, tmp_path)
