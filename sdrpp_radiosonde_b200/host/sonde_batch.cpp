@@ -8,10 +8,14 @@
  * (SD/decode.c:278-376 append_data_point: fields accumulate in one `printable` record per channel, pressure falls back
  * to the barometric formula, one row per fragment that carried data).
  *
- *   sonde_b200_batch [-t type] [-b buflen] [-c prefix] [-g prefix] [-k prefix] [-l prefix] [-i] [-q] file0 [file1 ...]
+ *   sonde_b200_batch [-t type] [-b buflen] [-f format] [-o prefix] [-c prefix] [-g prefix] [-k prefix] [-l prefix] [-i] [-q]
+ *                    file0 [file1 ...]
  *     -t, --type     auto|c50|dfm|imet4|ims100|m10|mrzn1|rs41 (the reference's names, SD/main.c:66; default auto),
  *                    or a comma-separated list, one per file
  *     -b, --buflen   samples per channel per GPU call (default 1024 = the reference's BUFLEN, SD/main.c:32)
+ *     -f, --fmt      the reference's line format for a data point (SD/main.c:489-566: %S serial, %f frame counter, %t
+ *                    temperature, %l latitude, ... ; its default when -o is given without -f)
+ *     -o, --output   write <prefix><channel>.txt per channel: the lines the reference prints on stdout for that recording
  *     -c, --csv      write <prefix><channel>.csv per channel
  *     -g, --gpx      write <prefix><channel>.gpx per channel: one track per serial, points that carry position and speed
  *     -k, --kml      write <prefix><channel>.kml per channel
@@ -23,7 +27,8 @@
  * block is ignored, as there), anything else raw mono float32 at 48 kHz read from behind those 44 bytes.  All recordings
  * of a batch must have the same sample rate.
  *     -q, --quiet    no per-point lines on stdout
- * stdout (unless -q): one line per data point  "<channel> <serial> <seq> <lat> <lon> <alt> <temp>"
+ * stdout (unless -q): one line per data point  "<channel> <serial> <seq> <lat> <lon> <alt> <temp>", or with -f
+ *                                             "<channel> <the formatted line>"
  * and always one summary line per channel     "CH <channel> type=<decoder> frames=<n> ok=<n> points=<n>".
  * Exit code 3 when the CUDA path is unavailable: there is no CPU fallback.
  */
@@ -139,7 +144,8 @@ bool append_data_point(SondeData &printable, const SondeData &d)
 
 int main(int argc, char **argv)
 {
-	std::string type_arg = "auto", csv_prefix, gpx_prefix, kml_prefix, live_prefix;
+	std::string type_arg = "auto", csv_prefix, gpx_prefix, kml_prefix, live_prefix, txt_prefix, fmt;
+	bool have_fmt = false;
 	size_t buflen = 1024;
 	bool iq = false, quiet = false;
 	std::vector<std::string> files;
@@ -149,12 +155,14 @@ int main(int argc, char **argv)
 		if (a == "-t" || a == "--type") type_arg = need("-t");
 		else if (a == "-b" || a == "--buflen") buflen = strtoul(need("-b").c_str(), nullptr, 10);
 		else if (a == "-c" || a == "--csv") csv_prefix = need("-c");
+		else if (a == "-f" || a == "--fmt") { fmt = need("-f"); have_fmt = true; }
+		else if (a == "-o" || a == "--output") txt_prefix = need("-o");
 		else if (a == "-g" || a == "--gpx") gpx_prefix = need("-g");
 		else if (a == "-k" || a == "--kml") kml_prefix = need("-k");
 		else if (a == "-l" || a == "--live-kml") live_prefix = need("-l");
 		else if (a == "-i" || a == "--iq") iq = true;
 		else if (a == "-q" || a == "--quiet") quiet = true;
-		else if (a == "-h" || a == "--help") { printf("usage: %s [-t type[,type...]] [-b buflen] [-c csv_prefix] [-g gpx_prefix] [-k kml_prefix] [-l live_kml_prefix] [-i] [-q] file...\n", argv[0]); return 0; }
+		else if (a == "-h" || a == "--help") { printf("usage: %s [-t type[,type...]] [-b buflen] [-f format] [-o text_prefix] [-c csv_prefix] [-g gpx_prefix] [-k kml_prefix] [-l live_kml_prefix] [-i] [-q] file...\n", argv[0]); return 0; }
 		else files.push_back(a);
 	}
 	const size_t C = files.size();
@@ -199,7 +207,9 @@ int main(int argc, char **argv)
 		radiosonde::cli::CsvFile csv;
 		radiosonde::cli::GpxFile gpx;
 		radiosonde::cli::KmlFile kml, live;
+		FILE *txt = nullptr;
 	};
+	if (!have_fmt) fmt = radiosonde::cli::default_format();
 	std::vector<Outputs> out(C);
 	std::vector<long> n_frames(C, 0), n_ok(C, 0), n_points(C, 0);
 	for (size_t c = 0; c < C; c++) {
@@ -210,7 +220,8 @@ int main(int argc, char **argv)
 		if ((!csv_prefix.empty() && !out[c].csv.init((csv_prefix + ch + ".csv").c_str())) ||
 		    (!gpx_prefix.empty() && !out[c].gpx.init((gpx_prefix + ch + ".gpx").c_str())) ||
 		    (!kml_prefix.empty() && out[c].kml.init((kml_prefix + ch + ".kml").c_str(), false)) ||
-		    (!live_prefix.empty() && out[c].live.init((live_prefix + ch + ".kml").c_str(), true))) {
+		    (!live_prefix.empty() && out[c].live.init((live_prefix + ch + ".kml").c_str(), true)) ||
+		    (!txt_prefix.empty() && !(out[c].txt = fopen((txt_prefix + ch + ".txt").c_str(), "wb")))) {
 			fprintf(stderr, "cannot create the output files of channel %zu\n", c);
 			return 2;
 		}
@@ -274,9 +285,13 @@ int main(int argc, char **argv)
 				if (!append_data_point(printable[c], frag)) continue;
 				n_points[c]++;
 				const SondeData &d = printable[c];
-				if (!quiet) printf("%zu %s %d %.5f %.5f %.1f %.1f\n", c, d.serial, d.seq, d.lat, d.lon, d.alt, d.temp);
+				if (!quiet) {
+					if (have_fmt) { printf("%zu ", c); radiosonde::cli::print_data(stdout, fmt.c_str(), d); }
+					else printf("%zu %s %d %.5f %.5f %.1f %.1f\n", c, d.serial, d.seq, d.lat, d.lon, d.alt, d.temp);
+				}
 				/* SD/main.c:347-365 */
 				Outputs &o = out[c];
+				if (o.txt) radiosonde::cli::print_data(o.txt, fmt.c_str(), d);
 				o.csv.add_point(d);
 				o.kml.start_track(d.serial);
 				o.kml.add_trackpoint(d);
@@ -300,6 +315,7 @@ int main(int argc, char **argv)
 		out[c].live.close();
 		out[c].gpx.close();
 		out[c].csv.close();
+		if (out[c].txt) fclose(out[c].txt);
 		in[c].close();
 	}
 	sonde_b200_host_free(stage[0]);

@@ -12,6 +12,8 @@
  *   radiosonde::cli::CsvFile, GpxFile, KmlFile          the command-line tool's -c / -g / -k / -l files
  *                                                       (SD/io/csv.c:6-61, SD/io/gpx.c:11-117, SD/io/kml.c:11-192), fed
  *                                                       from SondeData the way SD/main.c:347-365 does
+ *   radiosonde::cli::print_data                         the tool's text line per data point and its -f format language
+ *                                                       (SD/main.c:111,489-566)
  *
  * All the XML files are kept well-formed while they grow: a body that only ever grows, followed by a provisional
  * trailer that the next update overwrites.  TrailerFile below is that mechanism; the writers differ in what they put in
@@ -29,6 +31,7 @@
 #include <string>
 
 #include "sonde_data.hpp"
+#include "telemetry.hpp"                                 /* tl::altitude_to_pressure */
 
 namespace radiosonde {
 namespace io {
@@ -452,6 +455,64 @@ private:
 	std::string m_serial;
 	float m_lat = 0, m_lon = 0, m_alt = 0;
 };
+
+/* The tool's line format when -f is not given (SD/main.c:111) */
+inline const char *default_format() { return "(%S) [%f] %t'C %r%%    %l %o %am    %sm/s %h' %cm/s\t%x"; }
+
+/* SD/physics.c:43-48: the tool's dew point (the SDR++ module computes its own, src/decode/decoder.hpp:132-140);
+ * float / double mix as there */
+inline float dew_point(float temp, float rh)
+{
+	const float q = (float)((logf((float)(rh / 100.0)) + (17.27 * temp / (237.3 + temp))) / 17.27);
+	return (float)(237.3 * q / (1 - q));
+}
+
+/*
+ * One text line per data point, SD/main.c:489-566.  `%` + letter inserts a value:
+ *   a altitude  b shutdown timer  c climb  d dew point  f frame counter  h heading  l latitude  o longitude  p pressure
+ *   r humidity  s speed  S serial  t temperature  T time (UTC)  x ozone (XDATA)
+ * any other character after a `%` is printed as it is (so `%%` is a percent sign), a lone `%` at the end prints
+ * nothing, and every line of a non-empty format ends with a newline.
+ */
+inline void print_data(FILE *f, const char *fmt, const SondeData &d)
+{
+	if (!*fmt) return;
+	for (const char *p = fmt; *p; p++) {
+		if (*p != '%') { fputc(*p, f); continue; }
+		if (!*++p) break;
+		switch (*p) {
+		case 'a': fprintf(f, "%6.0f", d.alt); break;
+		case 'b':
+			if (d.fields & DATA_SHUTDOWN) fprintf(f, "%d:%02d:%02d", d.shutdown / 3600, d.shutdown / 60 % 60, d.shutdown % 60);
+			else fputs("(disabled)", f);
+			break;
+		case 'c': fprintf(f, "%+5.1f", d.climb); break;
+		case 'd': fprintf(f, "%6.1f", dew_point(d.temp, d.rh)); break;
+		case 'f': fprintf(f, "%5d", d.seq); break;
+		case 'h': fprintf(f, "%3.0f", d.heading); break;
+		case 'l': fprintf(f, "%8.5f%c", fabs(d.lat), d.lat >= 0 ? 'N' : 'S'); break;
+		case 'o': fprintf(f, "%8.5f%c", fabs(d.lon), d.lon >= 0 ? 'E' : 'W'); break;
+		case 'p': fprintf(f, "%4.1f", std::isnormal(d.pressure) ? d.pressure : tl::altitude_to_pressure(d.alt)); break;
+		case 'r': fprintf(f, "%3.0f", d.rh); break;
+		case 's': fprintf(f, "%4.1f", d.speed); break;
+		case 'S': fputs(d.serial, f); break;
+		case 't': fprintf(f, "%5.1f", d.temp); break;
+		case 'T': {
+			char stamp[64];
+			struct tm tmv;
+			stamp[0] = 0;
+			if (gmtime_r(&d.time, &tmv)) strftime(stamp, sizeof(stamp), "%a %b %d %Y %H:%M:%S", &tmv);
+			fputs(stamp, f);
+			break;
+		}
+		case 'x':
+			if (d.fields & DATA_OZONE) fprintf(f, "O3=%.2f mPa", d.o3_mpa);
+			break;
+		default: fputc(*p, f); break;
+		}
+	}
+	fputc('\n', f);
+}
 
 }  // namespace cli
 }  // namespace radiosonde

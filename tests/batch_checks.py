@@ -168,3 +168,34 @@ def check_tracks(runner, tmp_path):
         live = (tmp_path / f"l_{i}.kml-live.kml").read_bytes()
         assert b"</Document>\n</kml>\n" in live and kml_parts(live)[1] == got_rows
         assert b"<NetworkLink>" in (tmp_path / f"l_{i}.kml").read_bytes()
+
+
+ALL_SPECIFIERS = "%S|%f|%t|%r|%d|%p|%l|%o|%a|%s|%h|%c|%b|%T|%x|%%|%q|100%"
+
+
+def check_text_output(runner, tmp_path):
+    """-o / -f: the per-channel text file of a batch holds the lines the reference's tool prints on stdout for that
+    recording alone — with its default format (SD/main.c:111) and with a format that uses every specifier of
+    SD/main.c:489-566, an unknown one, a doubled and a trailing percent sign."""
+    cases = [("rs41", synth.RS41, 48000 * 6, 31), ("m10", synth.M10, 48000 * 4 + 100, 32), ("mrzn1", synth.MRZN1, 48000 * 5, 33)]
+    files = []
+    for i, (flag, stype, n, seed) in enumerate(cases):
+        raw = tmp_path / f"in{i}.raw"
+        synth.make_fm(synth.default_spec(stype, seed), n).astype(np.float32).tofile(raw)
+        files.append(str(raw))
+    for tag, fmt in (("d", None), ("a", ALL_SPECIFIERS)):
+        extra = ["-f", fmt] if fmt else []
+        r = subprocess.run([runner, "-q", "-t", ",".join(c[0] for c in cases), "-o", str(tmp_path / f"{tag}_"), *extra, *files],
+                           capture_output=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+        for i, (flag, stype, n, seed) in enumerate(cases):
+            a = subprocess.run([REF, "-q", "-t", flag, *extra, files[i]], capture_output=True, timeout=600)
+            assert a.returncode == 0, a.stderr[-300:]
+            # the tool's log lines share stdout with the data lines ("[<file>:<line>] Could not recognize input file type")
+            want = [l for l in a.stdout.split(b"\n")[:-1] if not l.startswith(b"[\x1b[")]
+            got = (tmp_path / f"{tag}_{i}.txt").read_bytes().split(b"\n")[:-1]
+            assert same_but_first(got, want, 3), (flag, tag, got[:3], want[:3])
+    # without -q and with -f the same lines go to stdout behind the channel number
+    r = subprocess.run([runner, "-t", cases[0][0], "-f", "%S %f", files[0]], capture_output=True, timeout=600)
+    lines = [l for l in r.stdout.decode().splitlines() if not l.startswith("CH ")]
+    assert r.returncode == 0 and len(lines) >= 4 and all(re.fullmatch(r"0 \S+ +\d+", l) for l in lines), lines[:3]

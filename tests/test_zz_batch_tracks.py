@@ -31,3 +31,9 @@ def test_part_helpers():
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/sondedump_ref not built")
 def test_batch_runner_gpx_kml_equal_reference_cli_per_channel(tmp_path):
     batch_checks.check_tracks(BATCH, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/sondedump_ref not built")
+def test_batch_runner_text_output_equals_reference_cli_stdout(tmp_path):
+    batch_checks.check_text_output(BATCH, tmp_path)
