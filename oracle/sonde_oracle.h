@@ -53,6 +53,17 @@ int  orc_frames_run_iq(int type, int samplerate, const float *iq, size_t n, size
                        sonde_frame_rec *recs, int max_recs);
 
 /*
+ * One channel as a stream: the loops of orc_frames_run / orc_frames_run_iq, one buffer per call (any length).  Records
+ * of the frames that complete in a call are returned with chunk = call_index; the return value is their number (which
+ * may exceed max_recs: the surplus is decoded and dropped).  gain 0 -> 2/pi as everywhere.
+ */
+typedef struct orc_chan orc_chan;
+orc_chan *orc_chan_open(int type, int samplerate, float gain);
+int  orc_chan_push_fm(orc_chan *s, const float *fm, size_t len, int call_index, sonde_frame_rec *recs, int max_recs);
+int  orc_chan_push_iq(orc_chan *s, const float *iq /*[len][2]*/, size_t len, int call_index, sonde_frame_rec *recs, int max_recs);
+void orc_chan_close(orc_chan *s);
+
+/*
  * Multi-threaded batch runner for the CPU baseline: channels statically partitioned
  * over nthreads.  in = [C][n] float FM (is_iq=0) or [C][n][2] float IQ (is_iq=1).
  * frames_out/ok_out (may be NULL) receive per-channel counts.  Returns 0.

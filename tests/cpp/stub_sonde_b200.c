@@ -1,16 +1,16 @@
 /*
- * stub_sonde_b200.c — TEST INFRASTRUCTURE ONLY: the handful of batch-ABI entry points sonde_batch.cpp calls, served by
- * the CPU oracle (oracle/_build/libsonde_oracle.so), so that the HOST logic of the batch runner — reading recordings,
- * padding the last buffer, the two-deep submit / fetch pipeline, fragment aggregation, the CSV / GPX / KML writers — can
- * be checked against the reference's command-line tool where there is no GPU (tests/test_batch_host_logic.py).
+ * stub_sonde_b200.c — TEST INFRASTRUCTURE ONLY: the handful of batch-ABI entry points the host layer calls
+ * (sonde_batch.cpp, host/gpu_decoder.hpp), served by the CPU oracle (oracle/_build/libsonde_oracle.so, its streaming
+ * form orc_chan_*), so that the HOST logic — reading recordings, padding the last buffer, the two-deep submit / fetch
+ * pipeline, backlogs of streams that deliver unequal lengths, fragment aggregation, the CSV / GPX / KML writers — can be
+ * checked against the reference where there is no GPU (tests/test_batch_host_logic.py).
  *
- * Built by that test into build/stub/libbatch_abi_stub.so and linked ONLY into a test copy of the runner
- * (build/stub/sonde_b200_batch_stub).  The product library and the product runner never see this file; the product
- * runner exits with code 3 without an sm_100 device (tests/test_cli_dropin.py::test_batch_runner_fails_loudly_without_gpu).
+ * Built by that test into build/stub/libbatch_abi_stub.so and linked ONLY into test copies of the host programs under
+ * build/stub/.  The product library and the product binaries never see this file; without an sm_100 device they fail
+ * with SONDE_ERR_NODEVICE / exit code 3 (tests/test_cli_dropin.py, tests/test_host_cpp.py: *_fails_loudly_without_gpu).
  *
- * Streaming on top of the oracle's whole-recording call: every process_fm() appends its buffer to the channel's
- * recording; fetch() for call k re-decodes the first (k+1) buffers with the same chunking and hands out the records
- * whose `chunk` is k.  Quadratic, which is fine for recordings of a few seconds.
+ * Semantics kept from include/sonde_b200.h: buffers of any length up to max_chunk_len, at most two calls in flight,
+ * fetch() returns the records of the oldest call not fetched yet, [C][max_frames] records + [C] counts.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -21,26 +21,32 @@
 #define STUB_MAX_FRAMES 64
 
 struct sonde_b200 {
-	int C, samplerate;
-	size_t len;               /* buffer length: every call must use the same */
+	int C;
+	size_t max_len;
 	int32_t *types;
-	float **rec;              /* [C] growing recordings */
-	size_t n_calls, n_fetched, cap_calls;
+	orc_chan **chan;
+	sonde_frame_rec *recs[2];       /* [C][STUB_MAX_FRAMES] per call in flight */
+	int32_t *counts[2];
+	long n_calls, n_fetched;
 	char err[128];
 };
 
 int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 {
-	if (!out || !cfg || cfg->n_channels <= 0) return SONDE_ERR_ARG;
+	if (!out || !cfg || cfg->n_channels <= 0 || cfg->max_chunk_len <= 0) return SONDE_ERR_ARG;
 	for (int c = 0; c < cfg->n_channels; c++)
-		if (cfg->types[c] < 0 || cfg->types[c] >= SONDE_NTYPES) return SONDE_ERR_ARG;      /* no AUTO in the stub */
+		if (cfg->types[c] < 0 || cfg->types[c] >= SONDE_NTYPES) return SONDE_ERR_ARG;      /* no AUTO in the stand-in */
 	sonde_b200 *h = calloc(1, sizeof(*h));
 	h->C = cfg->n_channels;
-	h->samplerate = cfg->samplerate;
-	h->len = (size_t)cfg->max_chunk_len;
+	h->max_len = (size_t)cfg->max_chunk_len;
 	h->types = malloc(sizeof(int32_t) * h->C);
 	memcpy(h->types, cfg->types, sizeof(int32_t) * h->C);
-	h->rec = calloc(h->C, sizeof(float *));
+	h->chan = calloc(h->C, sizeof(*h->chan));
+	for (int c = 0; c < h->C; c++) h->chan[c] = orc_chan_open(cfg->types[c], cfg->samplerate, cfg->fm_gain);
+	for (int k = 0; k < 2; k++) {
+		h->recs[k] = malloc(sizeof(sonde_frame_rec) * STUB_MAX_FRAMES * h->C);
+		h->counts[k] = calloc(h->C, sizeof(int32_t));
+	}
 	*out = h;
 	return SONDE_OK;
 }
@@ -48,48 +54,41 @@ int sonde_b200_create(sonde_b200 **out, const sonde_b200_config *cfg)
 void sonde_b200_destroy(sonde_b200 *h)
 {
 	if (!h) return;
-	for (int c = 0; c < h->C; c++) free(h->rec[c]);
-	free(h->rec);
+	for (int c = 0; c < h->C; c++) orc_chan_close(h->chan[c]);
+	for (int k = 0; k < 2; k++) { free(h->recs[k]); free(h->counts[k]); }
+	free(h->chan);
 	free(h->types);
 	free(h);
 }
 
-int sonde_b200_process_fm(sonde_b200 *h, const float *fm, size_t len)
+static int process(sonde_b200 *h, const float *in, size_t len, int is_iq)
 {
-	if (len != h->len) { strcpy(h->err, "stub: every call must pass max_chunk_len samples"); return SONDE_ERR_ARG; }
-	if (h->n_calls - h->n_fetched >= 2) { strcpy(h->err, "stub: more than two calls in flight"); return SONDE_ERR_STATE; }
-	if (h->n_calls == h->cap_calls) {
-		h->cap_calls = h->cap_calls ? 2 * h->cap_calls : 64;
-		for (int c = 0; c < h->C; c++) h->rec[c] = realloc(h->rec[c], h->cap_calls * len * sizeof(float));
+	if (len > h->max_len) { strcpy(h->err, "stand-in: len > max_chunk_len"); return SONDE_ERR_TOOLONG; }
+	if (h->n_calls - h->n_fetched >= 2) { strcpy(h->err, "stand-in: more than two calls in flight"); return SONDE_ERR_STATE; }
+	const int slot = (int)(h->n_calls & 1);
+	for (int c = 0; c < h->C; c++) {
+		sonde_frame_rec *dst = h->recs[slot] + (size_t)c * STUB_MAX_FRAMES;
+		int n = is_iq ? orc_chan_push_iq(h->chan[c], in + 2 * (size_t)c * len, len, (int)h->n_calls, dst, STUB_MAX_FRAMES)
+		              : orc_chan_push_fm(h->chan[c], in + (size_t)c * len, len, (int)h->n_calls, dst, STUB_MAX_FRAMES);
+		if (n < 0) { strcpy(h->err, "stand-in: oracle failure"); return SONDE_ERR_CUDA; }
+		h->counts[slot][c] = n > STUB_MAX_FRAMES ? STUB_MAX_FRAMES : n;
 	}
-	for (int c = 0; c < h->C; c++) memcpy(h->rec[c] + h->n_calls * len, fm + (size_t)c * len, len * sizeof(float));
 	h->n_calls++;
 	return SONDE_OK;
 }
 
-int sonde_b200_process_iq(sonde_b200 *h, const float *iq, size_t len)
-{
-	(void)iq; (void)len;
-	strcpy(h->err, "stub: FM input only");
-	return SONDE_ERR_ARG;
-}
+int sonde_b200_process_fm(sonde_b200 *h, const float *fm, size_t len) { return process(h, fm, len, 0); }
+int sonde_b200_process_iq(sonde_b200 *h, const float *iq, size_t len) { return process(h, iq, len, 1); }
 
 int sonde_b200_max_frames(const sonde_b200 *h) { (void)h; return STUB_MAX_FRAMES; }
 
 int sonde_b200_fetch(sonde_b200 *h, sonde_frame_rec *recs, int32_t *counts)
 {
-	if (h->n_fetched >= h->n_calls) { strcpy(h->err, "stub: nothing to fetch"); return SONDE_ERR_STATE; }
-	const size_t k = h->n_fetched++;
-	const int cap = 4096;
-	sonde_frame_rec *all = malloc(sizeof(sonde_frame_rec) * cap);
-	for (int c = 0; c < h->C; c++) {
-		int n = orc_frames_run(h->types[c], h->samplerate, h->rec[c], (k + 1) * h->len, h->len, all, cap);
-		if (n > cap) n = cap;
-		counts[c] = 0;
-		for (int i = 0; i < n; i++)
-			if ((size_t)all[i].chunk == k && counts[c] < STUB_MAX_FRAMES) recs[(size_t)c * STUB_MAX_FRAMES + counts[c]++] = all[i];
-	}
-	free(all);
+	if (h->n_fetched >= h->n_calls) { strcpy(h->err, "stand-in: nothing to fetch"); return SONDE_ERR_STATE; }
+	const int slot = (int)(h->n_fetched++ & 1);
+	memcpy(counts, h->counts[slot], sizeof(int32_t) * h->C);
+	for (int c = 0; c < h->C; c++)
+		memcpy(recs + (size_t)c * STUB_MAX_FRAMES, h->recs[slot] + (size_t)c * STUB_MAX_FRAMES, sizeof(sonde_frame_rec) * counts[c]);
 	return SONDE_OK;
 }
 

@@ -1,12 +1,14 @@
-"""The HOST logic of the batch runner (sdrpp_radiosonde_b200/host/sonde_batch.cpp) on the CPU: recordings read the way the
-reference reads them (raw / WAV, ragged lengths, the padded last buffer), the two-deep submit / fetch pipeline, fragment
-aggregation (SD/decode.c:278-376) and the CSV / GPX / KML / live-KML writers, against the reference's command-line tool.
+"""The HOST logic on the CPU: the batch runner (sdrpp_radiosonde_b200/host/sonde_batch.cpp — recordings read the way the
+reference reads them, the padded last buffer, the two-deep submit / fetch pipeline, fragment aggregation
+SD/decode.c:278-376, the text / CSV / GPX / KML / live-KML outputs), the decoder block and the reference-signature compat
+layer (host/gpu_decoder.hpp GpuDecoder, csrc/compat.cpp) and the channel bank (GpuChannelBank: backlogs of streams that
+deliver unequal lengths), each against the reference's command-line tool or the compiled reference library.
 
-The runner source is compiled a second time, for this test only, against tests/cpp/stub_sonde_b200.c — a stand-in for
-the ten batch-ABI entry points the runner calls, served by the CPU oracle.  That copy lives in build/stub/ and is test
-infrastructure: the product runner links the CUDA library, has no CPU path and exits with code 3 without a GPU
-(test_cli_dropin.py::test_batch_runner_fails_loudly_without_gpu).  The same checks run against the product binary on the
-GPU box (test_cli_dropin.py, test_zz_batch_tracks.py)."""
+The host sources are compiled a second time, for this test only, against tests/cpp/stub_sonde_b200.c — a stand-in for
+the ten batch-ABI entry points they call, served by the CPU oracle's streaming form.  Those copies live in build/stub/
+and are test infrastructure: the product binaries link the CUDA library, have no CPU path and exit with code 3 without a
+GPU (test_cli_dropin.py / test_host_cpp.py: *_fails_loudly_without_gpu).  The same checks — literally the same functions,
+tests/batch_checks.py and the check_* functions of test_host_cpp.py — run against the product binaries on the GPU box."""
 import os
 import subprocess
 import sys
@@ -34,6 +36,40 @@ def runner():
     subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT}/include", os.path.join(ROOT, "sdrpp_radiosonde_b200", "host", "sonde_batch.cpp"),
                     "-o", RUNNER, f"-L{STUBDIR}", "-lbatch_abi_stub", f"-Wl,-rpath,{STUBDIR}"], check=True)
     return RUNNER
+
+
+def _build_host_program(name, extra_sources=()):
+    """a test copy of tests/cpp/<name>.cpp (and of product host sources it needs) linked to the stand-in library"""
+    exe = os.path.join(STUBDIR, name + "_stub")
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT}/include", os.path.join(ROOT, "tests", "cpp", name + ".cpp"), *extra_sources,
+                    "-o", exe, f"-L{STUBDIR}", "-lbatch_abi_stub", f"-Wl,-rpath,{STUBDIR}", "-lpthread"], check=True)
+    return exe
+
+
+def test_decoder_block_and_compat_api(runner, tmp_path):
+    """radiosonde::GpuDecoder (the dsp::block drop-in: worker thread, merge_fragment, callbacks) and the
+    reference-signature compat layer (csrc/compat.cpp, compiled into the test program) on the stand-in library: the
+    golden RS41 frame's serial / sequence number / position / time, PARSED counts and field values against the compiled
+    reference — the assertions of test_host_cpp.py::test_host_block_and_compat_api_on_gpu."""
+    import test_host_cpp
+    exe = _build_host_program("host_block_test", [os.path.join(ROOT, "sdrpp_radiosonde_b200", "csrc", "compat.cpp")])
+    test_host_cpp.check_host_block_and_compat_api(exe, tmp_path)
+
+
+def test_channel_bank_unequal_streams_lose_nothing(runner, tmp_path):
+    """radiosonde::GpuChannelBank with streams that deliver different lengths per pass, some beyond max_chunk: no
+    backlog left, the frames of a straight run all there, the barometric pressure fallback — the assertions of
+    test_host_cpp.py::test_channel_bank_unequal_streams_lose_nothing, with the oracle as the straight run."""
+    import numpy as np
+    import test_host_cpp
+    from tests import reflib
+    exe = _build_host_program("host_bank_test")
+    orc = reflib.OracleLib()
+
+    def straight(types, nb, n):
+        recs = [orc.frames_run_iq(t, nb[c], 48000) for c, t in enumerate(types)]
+        return np.array([len(r) for r in recs]), np.array([sum(int(x.ok) for x in r) for r in recs])
+    test_host_cpp.check_channel_bank(exe, tmp_path, straight)
 
 
 def test_csv_per_channel(runner, tmp_path):

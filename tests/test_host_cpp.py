@@ -96,12 +96,18 @@ def test_host_block_compiles_and_fails_loudly_without_gpu(tmp_path):
 @pytest.mark.gpu
 def test_host_block_and_compat_api_on_gpu(tmp_path):
     build_exe()
+    check_host_block_and_compat_api(EXE, tmp_path)
+
+
+def check_host_block_and_compat_api(exe, tmp_path):
+    """shared with tests/test_batch_host_logic.py, which runs it on the CPU against a test copy of the same program
+    linked to the oracle-backed stand-in of the batch ABI"""
     n, chunk = 48000 * 3, 4096
     spec = synth.default_spec(synth.RS41, 0)
     iq, fm = synth.make_iq(spec, n), synth.make_fm(spec, n)
     (tmp_path / "iq").write_bytes(iq.tobytes())
     (tmp_path / "fm").write_bytes(fm.tobytes())
-    r = subprocess.run([EXE, str(tmp_path / "iq"), str(tmp_path / "fm"), str(n), str(chunk)], capture_output=True,
+    r = subprocess.run([exe, str(tmp_path / "iq"), str(tmp_path / "fm"), str(n), str(chunk)], capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     out = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines())
@@ -156,10 +162,28 @@ def test_channel_bank_unequal_streams_lose_nothing(tmp_path):
     plugin's barometric fallback (src/decode/decoder.hpp:108-110) for the sonde without a pressure sensor."""
     from sdrpp_radiosonde_b200 import capi
     build_bank_exe()
+
+    def straight(types, nb, n):
+        dec = capi.BatchDecoder(types, 48000)
+        want_frames = np.zeros(len(types), dtype=int)
+        want_ok = np.zeros(len(types), dtype=int)
+        for pos in range(0, n, 48000):
+            dec.process_iq(np.ascontiguousarray(nb[:, pos:pos + 48000]))
+            recs, counts = dec.fetch()
+            want_frames += counts
+            want_ok += [sum(int(r_["ok"]) for r_ in recs[c, :counts[c]]) for c in range(len(types))]
+        dec.close()
+        return want_frames, want_ok
+    check_channel_bank(BEXE, tmp_path, straight)
+
+
+def check_channel_bank(exe, tmp_path, straight):
+    """shared with tests/test_batch_host_logic.py (CPU, stand-in library); `straight(types, iq[C][n], n)` returns the
+    per-channel frame and ok counts of a plain run in 48000-sample calls"""
     types = [synth.RS41, synth.M10, synth.DFM09]
     n = 48000 * 4
     nb = np.stack([synth.make_iq(synth.default_spec(t, 60 + c), n) for c, t in enumerate(types)])
-    args = [BEXE, str(len(types)), str(n), "5000"]
+    args = [exe, str(len(types)), str(n), "5000"]
     for c, t in enumerate(types):
         (tmp_path / f"iq{c}").write_bytes(nb[c].tobytes())
         args += [str(t), str(tmp_path / f"iq{c}")]
@@ -168,15 +192,7 @@ def test_channel_bank_unequal_streams_lose_nothing(tmp_path):
     lines = r.stdout.strip().splitlines()
     ch = [dict(kv.split("=") for kv in l.split()[2:]) for l in lines if l.startswith("CH ")]
     assert [l for l in lines if l.startswith("BACKLOG")][0].split()[1] == "0"
-    dec = capi.BatchDecoder(types, 48000)
-    want_frames = np.zeros(len(types), dtype=int)
-    want_ok = np.zeros(len(types), dtype=int)
-    for pos in range(0, n, 48000):
-        dec.process_iq(np.ascontiguousarray(nb[:, pos:pos + 48000]))
-        recs, counts = dec.fetch()
-        want_frames += counts
-        want_ok += [sum(int(r_["ok"]) for r_ in recs[c, :counts[c]]) for c in range(len(types))]
-    dec.close()
+    want_frames, want_ok = straight(types, nb, n)
     for c in range(len(types)):
         # the framer emits one window per frame length of bits whatever the buffering; the FEC gate is robust to it
         assert abs(int(ch[c]["frames"]) - want_frames[c]) <= 1, (c, ch[c], want_frames[c])

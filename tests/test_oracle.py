@@ -334,3 +334,53 @@ def test_gf_polynomial_evaluation_by_independent_terms():
                             e = e - 63 if e >= 63 else e
                             got ^= ex[e]
                     assert want == got, (msg, j)
+
+
+def test_oracle_stream_api_equals_whole_recording_calls():
+    """orc_chan_open / push_fm / push_iq / close (the streaming form the batch-ABI stand-in of the host-logic tests is
+    built on, tests/cpp/stub_sonde_b200.c) returns exactly the records of orc_frames_run / orc_frames_run_iq with the
+    same buffering, record for record, for FM and IQ input and for buffers of irregular lengths (chunk index aside)."""
+    import ctypes
+    lib = reflib.OracleLib().lib
+    lib.orc_chan_open.restype = ctypes.c_void_p
+    lib.orc_chan_open.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_float]
+    for fn in (lib.orc_chan_push_fm, lib.orc_chan_push_iq):
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(reflib.FrameRec), ctypes.c_int]
+    lib.orc_chan_close.argtypes = [ctypes.c_void_p]
+
+    def stream(stype, x, lens, iq):
+        h = lib.orc_chan_open(stype, 48000, 0.0)
+        assert h
+        out, pos, k = [], 0, 0
+        buf = (reflib.FrameRec * 64)()
+        while pos < len(x):
+            n = min(lens[k % len(lens)], len(x) - pos)
+            part = np.ascontiguousarray(x[pos:pos + n])
+            got = (lib.orc_chan_push_iq if iq else lib.orc_chan_push_fm)(h, part.ctypes.data, n, k, buf, 64)
+            assert 0 <= got <= 64
+            for i in range(got):
+                r = reflib.FrameRec()
+                ctypes.memmove(ctypes.byref(r), ctypes.byref(buf[i]), ctypes.sizeof(r))
+                assert r.chunk == k
+                out.append(r)
+            pos += n
+            k += 1
+        lib.orc_chan_close(h)
+        return out
+
+    def key(r):
+        return (r.type, r.sync_offset, r.inverted, r.status, r.ok, r.aux, r.data_len, bytes(r.raw), bytes(r.data))
+
+    orc = reflib.OracleLib()
+    for stype in (synth.RS41, synth.M10, synth.IMS100, synth.IMET4, synth.C50):
+        fm = synth.make_fm(synth.default_spec(stype, 5), 48000 * 3).astype(np.float32)
+        want = orc.frames_run(stype, fm, 1024)
+        got = stream(stype, fm, [1024], False)
+        assert len(want) >= 2 and [key(r) for r in got] == [key(r) for r in want] and [r.chunk for r in got] == [r.chunk for r in want]
+        ragged = stream(stype, fm, [1, 4099, 77, 20000, 513], False)
+        assert [key(r)[3:] for r in ragged] == [key(r)[3:] for r in want]          # same frames whatever the buffering
+    iq = synth.make_iq(synth.default_spec(synth.DFM09, 6), 48000 * 3).astype(np.complex64)
+    want = orc.frames_run_iq(synth.DFM09, iq, 4096)
+    got = stream(synth.DFM09, iq, [4096], True)
+    assert len(want) >= 2 and [key(r) for r in got] == [key(r) for r in want]
