@@ -3,9 +3,10 @@
  * (SD/include/*.h shape) as a thin adapter over the batch C ABI with C = 1.
  *
  * Call protocol (SD/include/rs41.h:23-33, src/decode/decoder.hpp:61): the caller re-invokes xxx_decode
- * with the same buffer until PROCEED.  The first call for a buffer runs the GPU path over the whole
- * buffer and queues its frame records; each further call pops one (PARSED) and the call after the
- * last one answers PROCEED and re-arms.
+ * with the same buffer until PROCEED.  The first call for a buffer runs the GPU path over the buffer — over its first
+ * kMaxChunk samples if it is longer — and queues the frame records; each further call pops one (PARSED); when the
+ * queue is empty the next piece of the buffer is decoded, and the call after the last record of the last piece answers
+ * PROCEED and re-arms.  Buffers of any length are decoded completely, as by the reference.
  */
 #include <cstdio>
 #include <cstdlib>
@@ -22,12 +23,19 @@ struct sonde_compat_decoder {
 	int type = 0, max_chunk = 0, max_frames = 0;
 	std::vector<sonde_frame_rec> recs;
 	int n_recs = 0, next = 0;
-	bool armed = false;              /* records of the current buffer are queued */
+	bool armed = false;              /* the caller is working through a buffer: `done` of its samples have been decoded */
+	size_t done = 0;
 	const sonde_frame_rec *last = nullptr;
 	radiosonde::Telemetry tele;
 };
 
 namespace {
+
+/* Samples per GPU call.  A caller's buffer may be any length (the plugin's dsp::stream hands over up to 1,000,000
+ * samples, the tool 1024): longer buffers are decoded in pieces of this size while the caller repeats its
+ * xxx_decode(d, dst, src, len) call, which is how the reference works through a buffer too (SD/sonde/rs41/rs41.c:107-125
+ * returns PARSED from the middle of `src` and continues there on the next call). */
+constexpr int kMaxChunk = 1 << 16;
 
 sonde_compat_decoder *make(int type, int samplerate)
 {
@@ -38,7 +46,7 @@ sonde_compat_decoder *make(int type, int samplerate)
 	memset(&cfg, 0, sizeof(cfg));
 	cfg.n_channels = 1;
 	cfg.samplerate = samplerate;
-	cfg.max_chunk_len = 1 << 20;
+	cfg.max_chunk_len = kMaxChunk;
 	cfg.types = &t;
 	const int rc = sonde_b200_create(&d->h, &cfg);
 	if (rc != SONDE_OK) {
@@ -70,20 +78,27 @@ ParserStatus step(sonde_compat_decoder *d, SondeData *dst, const float *src, siz
 	}
 	if (!src) return PROCEED;
 	if (!d->armed) {
-		int32_t count = 0;
 		d->n_recs = d->next = 0;
-		if (len == 0 || len > (size_t)d->max_chunk) return PROCEED;
-		if (sonde_b200_process_fm(d->h, src, len) != SONDE_OK) return PROCEED;
-		if (sonde_b200_fetch(d->h, d->recs.data(), &count) != SONDE_OK) return PROCEED;
-		d->n_recs = count;
+		d->done = 0;
 		d->armed = true;
 	}
-	if (d->next < d->n_recs) {
-		d->last = &d->recs[d->next++];
-		if (dst) {
-			d->tele.parse(*d->last, dst);
+	for (;;) {
+		if (d->next < d->n_recs) {
+			d->last = &d->recs[d->next++];
+			if (dst) {
+				d->tele.parse(*d->last, dst);
+			}
+			return PARSED;
 		}
-		return PARSED;
+		if (d->done >= len) break;
+		/* the records of the last piece are used up: decode the next piece of this buffer */
+		const size_t piece = (len - d->done < (size_t)d->max_chunk) ? len - d->done : (size_t)d->max_chunk;
+		int32_t count = 0;
+		d->n_recs = d->next = 0;
+		const int rc = sonde_b200_process_fm(d->h, src + d->done, piece);
+		d->done += piece;
+		if (rc != SONDE_OK || sonde_b200_fetch(d->h, d->recs.data(), &count) != SONDE_OK) break;
+		d->n_recs = count;
 	}
 	d->armed = false;
 	return PROCEED;

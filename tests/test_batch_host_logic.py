@@ -54,6 +54,9 @@ def test_decoder_block_and_compat_api(runner, tmp_path):
     import test_host_cpp
     exe = _build_host_program("host_block_test", [os.path.join(ROOT, "sdrpp_radiosonde_b200", "csrc", "compat.cpp")])
     test_host_cpp.check_host_block_and_compat_api(exe, tmp_path)
+    # buffers longer than the compat layer's GPU call size (compat.cpp kMaxChunk = 65536) are decoded in pieces while
+    # the caller repeats xxx_decode(): same PARSED count and telemetry as the reference's loop over the same buffers
+    test_host_cpp.check_host_block_and_compat_api(exe, tmp_path, chunk=100000)
 
 
 def test_channel_bank_unequal_streams_lose_nothing(runner, tmp_path):

@@ -99,10 +99,10 @@ def test_host_block_and_compat_api_on_gpu(tmp_path):
     check_host_block_and_compat_api(EXE, tmp_path)
 
 
-def check_host_block_and_compat_api(exe, tmp_path):
+def check_host_block_and_compat_api(exe, tmp_path, chunk=4096):
     """shared with tests/test_batch_host_logic.py, which runs it on the CPU against a test copy of the same program
     linked to the oracle-backed stand-in of the batch ABI"""
-    n, chunk = 48000 * 3, 4096
+    n = 48000 * 3
     spec = synth.default_spec(synth.RS41, 0)
     iq, fm = synth.make_iq(spec, n), synth.make_fm(spec, n)
     (tmp_path / "iq").write_bytes(iq.tobytes())
