@@ -67,3 +67,20 @@ int main(int argc, char **argv) {
         assert len(trks) == (1 if stop_after <= 6 else 2)
         assert len(pts) == min(max(stop_after - 1, 0), 5) + (1 if stop_after >= 8 else 0)
         assert trks[0].find("g:name", ns).text == "S1234567"
+
+
+def test_writers_match_committed_reference_digests(tmp_path):
+    """The same pin without the compiled reference: tests/golden/writers.json holds the digests of the files the
+    reference's writers produced for five of the driver's rounds (tests/golden/make_writers_golden.py); this repo's
+    writers, run alone, must reproduce them."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_writers_golden", os.path.join(ROOT, "tests", "golden", "make_writers_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", f"-I{ROOT}/include", os.path.join(ROOT, "tests", "cpp", "track_files_test.cpp"),
+                    "-o", EXE, "-ldl"], check=True)
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "writers.json")))["files"]
+    got = gen.digests("ours_", "-")
+    assert len(want) == 30 and got == want, [k for k in want if got.get(k) != want[k]]
