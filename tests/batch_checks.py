@@ -199,3 +199,30 @@ def check_text_output(runner, tmp_path):
     r = subprocess.run([runner, "-t", cases[0][0], "-f", "%S %f", files[0]], capture_output=True, timeout=600)
     lines = [l for l in r.stdout.decode().splitlines() if not l.startswith("CH ")]
     assert r.returncode == 0 and len(lines) >= 4 and all(re.fullmatch(r"0 \S+ +\d+", l) for l in lines), lines[:3]
+
+
+def check_iq_input(runner, tmp_path):
+    """-i: raw complex64 recordings.  The same recordings discriminated on the CPU (the oracle's discriminator, the stage
+    the IQ entry point adds in front of the chain) and fed as FM files must give the same per-channel CSV.  The FM
+    files carry 44 leading bytes because the runner, like the reference, reads raw FM files from behind its WAV header
+    probe (SD/main.c:248-259); lengths are whole buffers so that no padded tail differs."""
+    from tests import reflib
+    orc = reflib.OracleLib()
+    cases = [("rs41", synth.RS41, 1024 * 260, 41), ("m10", synth.M10, 1024 * 200, 42)]
+    iq_files, fm_files = [], []
+    for i, (flag, stype, n, seed) in enumerate(cases):
+        iq = synth.make_iq(synth.default_spec(stype, seed), n).astype(np.complex64)
+        fm = np.asarray(orc.discriminate(iq), dtype=np.float32)
+        assert fm.shape == (n,)
+        (tmp_path / f"in{i}.c64").write_bytes(iq.tobytes())
+        (tmp_path / f"in{i}.raw").write_bytes(b"\0" * 44 + fm.tobytes())
+        iq_files.append(str(tmp_path / f"in{i}.c64"))
+        fm_files.append(str(tmp_path / f"in{i}.raw"))
+    types = ",".join(c[0] for c in cases)
+    a = subprocess.run([runner, "-q", "-i", "-t", types, "-c", str(tmp_path / "iq_"), *iq_files], capture_output=True, timeout=600)
+    b = subprocess.run([runner, "-q", "-t", types, "-c", str(tmp_path / "fm_"), *fm_files], capture_output=True, timeout=600)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr[-300:] + b.stderr[-300:]
+    assert a.stdout == b.stdout and a.stdout.count(b"CH ") == len(cases)
+    for i in range(len(cases)):
+        got, want = (tmp_path / f"iq_{i}.csv").read_bytes(), (tmp_path / f"fm_{i}.csv").read_bytes()
+        assert want.count(b"\n") >= 5 and got == want, (cases[i][0], got[:300], want[:300])

@@ -89,3 +89,7 @@ def test_gpx_kml_tracks(runner, tmp_path):
 
 def test_text_output_and_format(runner, tmp_path):
     batch_checks.check_text_output(runner, tmp_path)
+
+
+def test_iq_input(runner, tmp_path):
+    batch_checks.check_iq_input(runner, tmp_path)

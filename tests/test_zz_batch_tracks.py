@@ -37,3 +37,11 @@ def test_batch_runner_gpx_kml_equal_reference_cli_per_channel(tmp_path):
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/sondedump_ref not built")
 def test_batch_runner_text_output_equals_reference_cli_stdout(tmp_path):
     batch_checks.check_text_output(BATCH, tmp_path)
+
+
+@pytest.mark.gpu
+def test_batch_runner_iq_input_equals_fm_input(tmp_path):
+    from tests import reflib
+    if not reflib.have_oracle():
+        pytest.skip("oracle/_build/libsonde_oracle.so not built")
+    batch_checks.check_iq_input(BATCH, tmp_path)
