@@ -76,7 +76,7 @@ def test_channel_bank_unequal_streams_lose_nothing(runner, tmp_path):
 
 
 def test_csv_per_channel(runner, tmp_path):
-    batch_checks.check_csv_per_channel(runner, tmp_path, auto=False)       # the stand-in has no AUTO
+    batch_checks.check_csv_per_channel(runner, tmp_path, auto=True)
 
 
 def test_wav_inputs(runner, tmp_path):
