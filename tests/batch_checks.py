@@ -226,3 +226,30 @@ def check_iq_input(runner, tmp_path):
     for i in range(len(cases)):
         got, want = (tmp_path / f"iq_{i}.csv").read_bytes(), (tmp_path / f"fm_{i}.csv").read_bytes()
         assert want.count(b"\n") >= 5 and got == want, (cases[i][0], got[:300], want[:300])
+
+
+def check_wall_clock_sondes(runner, tmp_path):
+    """iMS-100 and iMet-4 in one batch: their parsers take the DATE of the time stamp from time(NULL)
+    (SD/sonde/ims100/parser.c:26, imet4/parser.c:47,70), so dates are masked; everything else in the per-channel CSV
+    and text output must equal the reference tool's, with the usual tolerance for its very first data point."""
+    def mask(b):
+        return re.sub(rb"\d{4}-\d{2}-\d{2}", b"DATE", b)
+    cases = [("ims100", synth.IMS100, 48000 * 6, 51), ("imet4", synth.IMET4, 48000 * 6, 52)]
+    files = []
+    for i, (flag, stype, n, seed) in enumerate(cases):
+        raw = tmp_path / f"in{i}.raw"
+        synth.make_fm(synth.default_spec(stype, seed), n).astype(np.float32).tofile(raw)
+        files.append(str(raw))
+    fmt = "%S|%f|%t|%r|%p|%l|%o|%a|%s|%h|%c"
+    r = subprocess.run([runner, "-q", "-t", ",".join(c[0] for c in cases), "-c", str(tmp_path / "c_"), "-o", str(tmp_path / "o_"), "-f", fmt, *files],
+                       capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    for i, (flag, stype, n, seed) in enumerate(cases):
+        a = subprocess.run([REF, "-q", "-t", flag, "-c", str(tmp_path / f"ref{i}.csv"), "-f", fmt, files[i]], capture_output=True, timeout=600)
+        assert a.returncode == 0, a.stderr[-300:]
+        want = [l for l in mask((tmp_path / f"ref{i}.csv").read_bytes()).split(b"\n") if l.strip(b",")]
+        got = [l for l in mask((tmp_path / f"c_{i}.csv").read_bytes()).split(b"\n") if l.strip(b",")]
+        assert got[0] == want[0] and same_but_first(got[1:], want[1:], 3), (flag, got[:3], want[:3])
+        want_txt = [l for l in a.stdout.split(b"\n")[:-1] if not l.startswith(b"[\x1b[")]
+        got_txt = (tmp_path / f"o_{i}.txt").read_bytes().split(b"\n")[:-1]
+        assert same_but_first(got_txt, want_txt, 3), (flag, got_txt[:3], want_txt[:3])

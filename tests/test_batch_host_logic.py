@@ -93,3 +93,7 @@ def test_text_output_and_format(runner, tmp_path):
 
 def test_iq_input(runner, tmp_path):
     batch_checks.check_iq_input(runner, tmp_path)
+
+
+def test_wall_clock_sondes(runner, tmp_path):
+    batch_checks.check_wall_clock_sondes(runner, tmp_path)
