@@ -140,6 +140,27 @@ bool append_data_point(SondeData &printable, const SondeData &d)
 	return true;
 }
 
+void usage(const char *prog)
+{
+	printf("usage: %s [options] file0 [file1 ...]      one GPU batch, one channel per file\n"
+	       "   -t, --type <type[,type...]>  auto|c50|dfm|imet4|ims100|m10|mrzn1|rs41, one for all files or one per file (default auto)\n"
+	       "   -b, --buflen <samples>       samples per channel per GPU call (default 1024)\n"
+	       "   -i, --iq                     the files are raw complex64 IQ at 48 kS/s (default: WAV, or raw mono float32 FM audio)\n"
+	       "   -f, --fmt <format>           format of the text line per data point\n"
+	       "   -o, --output <prefix>        text lines to <prefix><channel>.txt\n"
+	       "   -c, --csv <prefix>           CSV to <prefix><channel>.csv\n"
+	       "   -g, --gpx <prefix>           GPX track to <prefix><channel>.gpx\n"
+	       "   -k, --kml <prefix>           KML track to <prefix><channel>.kml\n"
+	       "   -l, --live-kml <prefix>      live KML to <prefix><channel>.kml + <prefix><channel>.kml-live.kml\n"
+	       "   -q, --quiet                  no per-point lines on stdout\n"
+	       "\nFormat specifiers (default \"%s\"):\n"
+	       "   %%a altitude (m)        %%b shutdown timer      %%c climb rate (m/s)    %%d dew point ('C)\n"
+	       "   %%f frame counter       %%h heading (deg)       %%l latitude            %%o longitude\n"
+	       "   %%p pressure (hPa)      %%r rel. humidity (%%)   %%s speed (m/s)         %%S serial number\n"
+	       "   %%t temperature ('C)    %%T time stamp (UTC)    %%x decoded XDATA\n",
+	       prog, radiosonde::cli::default_format());
+}
+
 }  // namespace
 
 int main(int argc, char **argv)
@@ -162,7 +183,7 @@ int main(int argc, char **argv)
 		else if (a == "-l" || a == "--live-kml") live_prefix = need("-l");
 		else if (a == "-i" || a == "--iq") iq = true;
 		else if (a == "-q" || a == "--quiet") quiet = true;
-		else if (a == "-h" || a == "--help") { printf("usage: %s [-t type[,type...]] [-b buflen] [-f format] [-o text_prefix] [-c csv_prefix] [-g gpx_prefix] [-k kml_prefix] [-l live_kml_prefix] [-i] [-q] file...\n", argv[0]); return 0; }
+		else if (a == "-h" || a == "--help") { usage(argv[0]); return 0; }
 		else files.push_back(a);
 	}
 	const size_t C = files.size();
@@ -194,9 +215,13 @@ int main(int argc, char **argv)
 	cfg.types = types.data();
 	sonde_b200 *h = nullptr;
 	const int rc = sonde_b200_create(&h, &cfg);
-	if (rc != SONDE_OK) {
+	if (rc == SONDE_ERR_NODEVICE || rc == SONDE_ERR_CUDA) {
 		printf("NOGPU sonde_b200_create failed (%d): the CUDA path is required, there is no CPU fallback\n", rc);
 		return 3;
+	}
+	if (rc != SONDE_OK) {
+		fprintf(stderr, "sonde_b200_create failed (%d): check the sample rate (%d S/s) and the buffer length (%zu)\n", rc, in[0].rate, buflen);
+		return 2;
 	}
 	const int max_frames = sonde_b200_max_frames(h);
 	std::vector<sonde_frame_rec> recs(C * (size_t)max_frames);
