@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <string>
@@ -97,6 +98,18 @@ inline void utc_stamp(char (&out)[24], time_t t)
 }  // namespace io
 
 /* ---------------------------------------------------------------- the SDR++ module's files ---------------------- */
+
+/* src/utils.cpp:3-17: where the module puts its output files by default (src/main.cpp:41-42: "radiosonde.gpx",
+ * "radiosonde_ptu.csv") — $TMP, else $TEMP, else /tmp.  The reference joins directory and name with a backslash on
+ * every platform but Windows (its #ifdef is the wrong way round), which on Linux names a file "tmp\radiosonde.gpx" in
+ * the root directory; this joins with '/'. */
+inline std::string getTempFile(const std::string &file)
+{
+	const char *dir = getenv("TMP");
+	if (!dir) dir = getenv("TEMP");
+	if (!dir) dir = "/tmp";
+	return std::string(dir) + "/" + file;
+}
 
 /* src/gpx.hpp:11-59.  One GPX 1.1 file, one <trk> per sonde serial, complete after every call. */
 class GPXWriter {

@@ -84,3 +84,17 @@ def test_writers_match_committed_reference_digests(tmp_path):
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "writers.json")))["files"]
     got = gen.digests("ours_", "-")
     assert len(want) == 30 and got == want, [k for k in want if got.get(k) != want[k]]
+
+
+def test_default_output_paths(tmp_path):
+    """radiosonde::getTempFile (src/utils.cpp:3-17): $TMP, then $TEMP, then /tmp — joined with a slash"""
+    src = tmp_path / "p.cpp"
+    src.write_text('#include "sdrpp_radiosonde_b200/host/track_files.hpp"\n'
+                   'int main() { puts(radiosonde::getTempFile("radiosonde.gpx").c_str()); return 0; }\n')
+    exe = tmp_path / "p"
+    subprocess.run(["g++", "-O1", "-std=c++17", f"-I{ROOT}", f"-I{ROOT}/include", str(src), "-o", str(exe)], check=True)
+    env = {k: v for k, v in os.environ.items() if k not in ("TMP", "TEMP")}
+    run = lambda e: subprocess.run([str(exe)], env=e, capture_output=True, text=True, check=True).stdout.strip()
+    assert run(env) == "/tmp/radiosonde.gpx"
+    assert run(dict(env, TEMP="/var/t")) == "/var/t/radiosonde.gpx"
+    assert run(dict(env, TEMP="/var/t", TMP="/scratch")) == "/scratch/radiosonde.gpx"
