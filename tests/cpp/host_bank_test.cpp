@@ -4,7 +4,14 @@
  * be dropped (VERDICT r1 / ADVICE r1: run() used to decode min(count) and flush the rest away).
  *
  *   host_bank_test <n_channels> <n_samples> <max_chunk> <type0> <iq0.c64> <type1> <iq1.c64> ...
- * prints per channel:  CH <c> frames=<n> ok=<n> callbacks=<n> pressure_ok=<0|1>
+ * With BANK_TEST_SEED=<n> in the environment the buffer lengths are random (1 .. 40000, a third of them below 64)
+ * instead of the fixed patterns.
+ * prints per channel:  CH <c> frames=<n> ok=<n> callbacks=<n> pressure_ok=<0|1> digest=<FNV-1a over status and frame
+ *                      bytes of every record but the first, in order: equal digests = same frames in the same order.
+ *                      The first record is left out: the reference's demodulator forgets its mid-symbol sample at
+ *                      the start of every call (SD/demod/gfsk.c:73), so where a buffer ends matters to the timing loop
+ *                      while it is still acquiring (a first buffer of 55-57 samples flips the third bit of an RS41
+ *                      stream, in the compiled reference and in the oracle alike), and the bank chooses the call lengths>
  * and                  BACKLOG <samples left in the backlogs after the last pass>
  * exit code 3 when the CUDA path is unavailable (no CPU fallback).
  */
@@ -15,11 +22,22 @@
 
 #include "../../sdrpp_radiosonde_b200/host/gpu_decoder.hpp"
 
-struct Tally { int frames = 0, ok = 0, cb = 0; bool pressure_ok = true; };
+struct Tally { int frames = 0, ok = 0, cb = 0; bool pressure_ok = true; unsigned long long digest = 1469598103934665603ull; };
+static void fnv(unsigned long long &h, const void *p, size_t n)
+{
+	for (size_t i = 0; i < n; i++) { h ^= ((const unsigned char *)p)[i]; h *= 1099511628211ull; }
+}
 static std::vector<Tally> tally;
 static std::vector<SondeFullData *> slots;
 
-static void on_frame(int c, const sonde_frame_rec *r, void *) { tally[c].frames++; tally[c].ok += r->ok; }
+static void on_frame(int c, const sonde_frame_rec *r, void *)
+{
+	tally[c].frames++;
+	tally[c].ok += r->ok;
+	if (tally[c].frames == 1) return;      /* the first window holds the demodulator's start-up bits, see below */
+	fnv(tally[c].digest, &r->status, sizeof(r->status));
+	fnv(tally[c].digest, r->data, (size_t)r->data_len);
+}
 static void on_data(SondeFullData *d, void *)
 {
 	/* the bank hands out one persistent SondeFullData per channel: identify the channel by address */
@@ -66,10 +84,14 @@ int main(int argc, char **argv)
 	 * than max_chunk.  Every channel delivers n samples in total. */
 	static const int pattern[3][5] = {{4096, 1000, 12000, 7, 3001}, {1024, 9000, 333, 5000, 2048}, {2500, 2500, 16000, 1, 640}};
 	std::vector<size_t> pos(C, 0);
+	const char *seed_env = getenv("BANK_TEST_SEED");
+	unsigned long long lcg = seed_env ? strtoull(seed_env, nullptr, 10) * 2862933555777941757ull + 3037000493ull : 0;
+	auto rnd = [&lcg]() { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; return (unsigned)(lcg >> 33); };
 	for (int pass = 0;; pass++) {
 		bool any = false;
 		for (size_t c = 0; c < C; c++) {
 			size_t len = (size_t)pattern[c % 3][pass % 5];
+			if (seed_env) len = (rnd() % 3 == 0) ? 1 + rnd() % 63 : 1 + rnd() % 40000;
 			if (len > n - pos[c]) len = n - pos[c];
 			any |= len > 0;
 			memcpy(streams[c].writeBuf, iq[c].data() + pos[c], len * sizeof(dsp::complex_t));
@@ -84,7 +106,8 @@ int main(int argc, char **argv)
 	size_t left = 0;
 	for (size_t c = 0; c < C; c++) left += bank.backlog(c);
 	for (size_t c = 0; c < C; c++)
-		printf("CH %zu frames=%d ok=%d callbacks=%d pressure_ok=%d\n", c, tally[c].frames, tally[c].ok, tally[c].cb, (int)tally[c].pressure_ok);
+		printf("CH %zu frames=%d ok=%d callbacks=%d pressure_ok=%d digest=%016llx\n", c, tally[c].frames, tally[c].ok, tally[c].cb,
+		       (int)tally[c].pressure_ok, tally[c].digest);
 	printf("BACKLOG %zu\n", left);
 	bank.deinit();
 	return 0;

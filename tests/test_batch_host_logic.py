@@ -97,3 +97,49 @@ def test_iq_input(runner, tmp_path):
 
 def test_wall_clock_sondes(runner, tmp_path):
     batch_checks.check_wall_clock_sondes(runner, tmp_path)
+
+
+def test_channel_bank_random_buffer_lengths_deliver_every_sample_in_order(runner, tmp_path):
+    """GpuChannelBank fuzzed: per pass every stream hands over a buffer of a random length (1 .. 40000 samples, a third
+    below 64, max_chunk 5000), so backlogs grow and drain unevenly.  With the deterministic stand-in the frames are a
+    function of the sample sequence alone (test_oracle_stream_api_equals_whole_recording_calls: same frames whatever
+    the buffering), so the digest over every channel's records must equal the digest of one straight oracle run — any
+    sample lost, duplicated or reordered by the bank changes it.  (The first record of a stream is left out of the
+    digest: the reference's demodulator forgets its mid-symbol sample at the start of every call, SD/demod/gfsk.c:73,
+    so where a buffer ends matters while the timing loop is still acquiring — a first buffer of 55-57 samples flips the
+    third bit of this RS41 stream in the compiled reference and the oracle alike — and the bank chooses the call
+    lengths.)"""
+    import numpy as np
+    from sdrpp_radiosonde_b200 import synth
+    from tests import reflib
+    exe = _build_host_program("host_bank_test")
+    orc = reflib.OracleLib()
+    types = [synth.RS41, synth.M10, synth.DFM09, synth.C50]
+    n = 48000 * 3
+    nb = np.stack([synth.make_iq(synth.default_spec(t, 70 + c), n) for c, t in enumerate(types)])
+
+    def fnv(h, b):
+        for x in b:
+            h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+    want = []
+    for c, t in enumerate(types):
+        h = 1469598103934665603
+        recs = orc.frames_run_iq(t, nb[c], 4096)
+        for r in recs[1:]:
+            h = fnv(h, int(r.status).to_bytes(4, "little", signed=True))
+            h = fnv(h, bytes(r.data)[:r.data_len])
+        want.append((len(recs), f"{h:016x}"))
+        assert len(recs) >= 3
+    args = [exe, str(len(types)), str(n), "5000"]
+    for c, t in enumerate(types):
+        (tmp_path / f"iq{c}").write_bytes(nb[c].tobytes())
+        args += [str(t), str(tmp_path / f"iq{c}")]
+    for seed in range(1, 11):
+        r = subprocess.run(args, capture_output=True, text=True, timeout=300, env=dict(os.environ, BANK_TEST_SEED=str(seed)))
+        assert r.returncode == 0, r.stdout + r.stderr
+        lines = r.stdout.strip().splitlines()
+        assert [l for l in lines if l.startswith("BACKLOG")][0].split()[1] == "0"
+        ch = [dict(kv.split("=") for kv in l.split()[2:]) for l in lines if l.startswith("CH ")]
+        got = [(int(x["frames"]), x["digest"]) for x in ch]
+        assert got == want, (seed, got, want)
