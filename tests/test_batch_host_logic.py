@@ -57,6 +57,10 @@ def test_decoder_block_and_compat_api(runner, tmp_path):
     # buffers longer than the compat layer's GPU call size (compat.cpp kMaxChunk = 65536) are decoded in pieces while
     # the caller repeats xxx_decode(): same PARSED count and telemetry as the reference's loop over the same buffers
     test_host_cpp.check_host_block_and_compat_api(exe, tmp_path, chunk=100000)
+    # and very short ones (the reference's results depend on where buffers end, SD/demod/gfsk.c:73: the expected values
+    # come from the compiled reference run with the same buffers)
+    for chunk in (7, 1000):
+        test_host_cpp.check_host_block_and_compat_api(exe, tmp_path, chunk=chunk)
 
 
 def test_channel_bank_unequal_streams_lose_nothing(runner, tmp_path):
