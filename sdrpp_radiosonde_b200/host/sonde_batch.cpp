@@ -12,7 +12,11 @@
  *                    file0 [file1 ...]
  *     -t, --type     auto|c50|dfm|imet4|ims100|m10|mrzn1|rs41 (the reference's names, SD/main.c:66; default auto),
  *                    or a comma-separated list, one per file
- *     -b, --buflen   samples per channel per GPU call (default 1024 = the reference's BUFLEN, SD/main.c:32)
+ *     -b, --buflen   samples per channel per GPU call (default 1024 = the reference's BUFLEN, SD/main.c:32).  Larger buffers
+ *                    mean fewer, fuller GPU calls; the output then equals the reference LIBRARY driven with buffers of that
+ *                    length rather than the reference TOOL byte for byte, because the reference's demodulator forgets its
+ *                    mid-symbol sample at the start of every buffer (SD/demod/gfsk.c:73), which the timing loop feels
+ *                    while it is acquiring
  *     -f, --fmt      the reference's line format for a data point (SD/main.c:489-566: %S serial, %f frame counter, %t
  *                    temperature, %l latitude, ... ; its default when -o is given without -f)
  *     -o, --output   write <prefix><channel>.txt per channel: the lines the reference prints on stdout for that recording
