@@ -77,14 +77,14 @@ void sonde_b200_destroy(sonde_b200 *h)
 	free(h);
 }
 
-static int process(sonde_b200 *h, const float *in, size_t len, int is_iq)
+static int process(sonde_b200 *h, const float *in, size_t len, int is_iq, size_t row_stride)
 {
 	if (len > h->max_len) { strcpy(h->err, "stand-in: len > max_chunk_len"); return SONDE_ERR_TOOLONG; }
 	if (h->n_calls - h->n_fetched >= 2) { strcpy(h->err, "stand-in: more than two calls in flight"); return SONDE_ERR_STATE; }
 	const int slot = (int)(h->n_calls & 1);
 	for (int c = 0; c < h->C; c++) {
 		sonde_frame_rec *dst = h->recs[slot] + (size_t)c * STUB_MAX_FRAMES;
-		const float *row = in + (is_iq ? 2 : 1) * (size_t)c * len;
+		const float *row = in + (is_iq ? 2 : 1) * (size_t)c * row_stride;
 		h->counts[slot][c] = 0;
 		for (int k = 0; k < SONDE_NTYPES; k++) {
 			orc_chan *ch = h->chan[c * SONDE_NTYPES + k];
@@ -111,8 +111,11 @@ static int process(sonde_b200 *h, const float *in, size_t len, int is_iq)
 	return SONDE_OK;
 }
 
-int sonde_b200_process_fm(sonde_b200 *h, const float *fm, size_t len) { return process(h, fm, len, 0); }
-int sonde_b200_process_iq(sonde_b200 *h, const float *iq, size_t len) { return process(h, iq, len, 1); }
+int sonde_b200_process_fm(sonde_b200 *h, const float *fm, size_t len) { return process(h, fm, len, 0, len); }
+int sonde_b200_process_iq(sonde_b200 *h, const float *iq, size_t len) { return process(h, iq, len, 1, len); }
+/* "device" memory is host memory here (stub_sonde_chan.c hands out host pointers) */
+int sonde_b200_process_iq_device(sonde_b200 *h, const void *d_iq, size_t len, size_t row_stride) { return process(h, d_iq, len, 1, row_stride); }
+void *sonde_b200_stream(sonde_b200 *h) { (void)h; return NULL; }
 
 int sonde_b200_max_frames(const sonde_b200 *h) { (void)h; return STUB_MAX_FRAMES; }
 

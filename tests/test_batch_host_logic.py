@@ -1,11 +1,13 @@
 """The HOST logic on the CPU: the batch runner (sdrpp_radiosonde_b200/host/sonde_batch.cpp — recordings read the way the
 reference reads them, the padded last buffer, the two-deep submit / fetch pipeline, fragment aggregation
 SD/decode.c:278-376, the text / CSV / GPX / KML / live-KML outputs), the decoder block and the reference-signature compat
-layer (host/gpu_decoder.hpp GpuDecoder, csrc/compat.cpp) and the channel bank (GpuChannelBank: backlogs of streams that
-deliver unequal lengths), each against the reference's command-line tool or the compiled reference library.
+layer (host/gpu_decoder.hpp GpuDecoder, csrc/compat.cpp), the channel bank (GpuChannelBank: backlogs of streams that
+deliver unequal lengths) and the wideband bank (host/gpu_wideband.hpp GpuWidebandBank: staging and the n mod D carry),
+each against the reference's command-line tool, the compiled reference library or the oracle.
 
 The host sources are compiled a second time, for this test only, against tests/cpp/stub_sonde_b200.c — a stand-in for
-the ten batch-ABI entry points they call, served by the CPU oracle's streaming form.  Those copies live in build/stub/
+the batch-ABI entry points they call, served by the CPU oracle's streaming form — and tests/cpp/stub_sonde_chan.c, a
+plain C polyphase filter behind the channelizer entry points.  Those copies live in build/stub/
 and are test infrastructure: the product binaries link the CUDA library, have no CPU path and exit with code 3 without a
 GPU (test_cli_dropin.py / test_host_cpp.py: *_fails_loudly_without_gpu).  The same checks — literally the same functions,
 tests/batch_checks.py and the check_* functions of test_host_cpp.py — run against the product binaries on the GPU box."""
@@ -31,7 +33,7 @@ def runner():
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True)
     os.makedirs(STUBDIR, exist_ok=True)
     subprocess.run(["gcc", "-O2", "-std=gnu99", "-fPIC", "-shared", f"-I{ROOT}/include", os.path.join(ROOT, "tests", "cpp", "stub_sonde_b200.c"),
-                    "-o", os.path.join(STUBDIR, "libbatch_abi_stub.so"), f"-L{os.path.dirname(ORACLE)}", "-lsonde_oracle",
+                    os.path.join(ROOT, "tests", "cpp", "stub_sonde_chan.c"), "-lm", "-o", os.path.join(STUBDIR, "libbatch_abi_stub.so"), f"-L{os.path.dirname(ORACLE)}", "-lsonde_oracle",
                     f"-Wl,-rpath,{os.path.dirname(ORACLE)}"], check=True)
     subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT}/include", os.path.join(ROOT, "sdrpp_radiosonde_b200", "host", "sonde_batch.cpp"),
                     "-o", RUNNER, f"-L{STUBDIR}", "-lbatch_abi_stub", f"-Wl,-rpath,{STUBDIR}"], check=True)
@@ -147,3 +149,19 @@ def test_channel_bank_random_buffer_lengths_deliver_every_sample_in_order(runner
         ch = [dict(kv.split("=") for kv in l.split()[2:]) for l in lines if l.startswith("CH ")]
         got = [(int(x["frames"]), x["digest"]) for x in ch]
         assert got == want, (seed, got, want)
+
+
+def test_wideband_bank(runner, tmp_path):
+    """radiosonde::GpuWidebandBank (one wideband dsp::stream in, buffers of an odd length so the n mod D carry is
+    exercised, three sondes out with telemetry callbacks) on the stand-in: its channelizer part is a plain C polyphase
+    filter (tests/cpp/stub_sonde_chan.c) — the assertions of test_host_cpp.py::test_wideband_block_on_gpu with the
+    oracle as the straight run on the narrowband signals."""
+    import numpy as np
+    import test_host_cpp
+    from tests import reflib
+    exe = _build_host_program("host_wideband_test")
+    orc = reflib.OracleLib()
+
+    def straight(types, nb):
+        return np.array([sum(int(x.ok) for x in orc.frames_run_iq(t, nb[c], 48000)) for c, t in enumerate(types)])
+    test_host_cpp.check_wideband_block(exe, tmp_path, straight)

@@ -48,27 +48,37 @@ def test_wideband_block_on_gpu(tmp_path):
     """radiosonde::GpuWidebandBank: one wideband dsp::stream in (buffers of an odd length, so the n mod D carry is
     exercised), three sondes out with telemetry callbacks."""
     from sdrpp_radiosonde_b200 import capi
-    from tests.gpu_util import make_wideband
     build_wideband_exe()
+
+    def straight(types, nb):
+        dec = capi.BatchDecoder(types, 48000)
+        want_ok = np.zeros(len(types), dtype=int)
+        for pos in range(0, nb.shape[1], 48000):
+            dec.process_iq(np.ascontiguousarray(nb[:, pos:pos + 48000]))
+            recs, counts = dec.fetch()
+            want_ok += [sum(int(r_["ok"]) for r_ in recs[c, :counts[c]]) for c in range(len(types))]
+        dec.close()
+        return want_ok
+    check_wideband_block(WEXE, tmp_path, straight)
+
+
+def check_wideband_block(exe, tmp_path, straight):
+    """shared with tests/test_batch_host_logic.py (CPU, stand-in library); `straight(types, nb[C][n])` returns the
+    per-channel ok counts of a plain run over the narrowband signals"""
+    from tests.gpu_util import make_wideband
     D, nsec = 48, 4
     types = [synth.RS41, synth.M10, synth.RS41]
     freqs = [-400e3, 250e3, 31.25e3]
     nb, wide = make_wideband(types, freqs, D, nsec)
     (tmp_path / "w").write_bytes(wide.tobytes())
-    args = [WEXE, str(tmp_path / "w"), str(wide.size), str(D), "100003"]
+    args = [exe, str(tmp_path / "w"), str(wide.size), str(D), "100003"]
     for f, t in zip(freqs, types):
         args += [str(f), str(t)]
     r = subprocess.run(args, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = r.stdout.strip().splitlines()
     ch = [dict(kv.split("=") for kv in l.split()[2:]) for l in lines if l.startswith("CH ")]
-    dec = capi.BatchDecoder(types, 48000)
-    want_ok = np.zeros(len(types), dtype=int)
-    for pos in range(0, nb.shape[1], 48000):
-        dec.process_iq(np.ascontiguousarray(nb[:, pos:pos + 48000]))
-        recs, counts = dec.fetch()
-        want_ok += [sum(int(r_["ok"]) for r_ in recs[c, :counts[c]]) for c in range(len(types))]
-    dec.close()
+    want_ok = straight(types, nb)
     for c in range(len(types)):
         assert int(ch[c]["ok"]) >= want_ok[c] - 1 and want_ok[c] >= 3, (c, ch[c], want_ok[c])
     assert any(l.startswith("SERIAL R3551568:") for l in lines)          # the golden RS41 frame's serial (SURVEY.md §4)
