@@ -10,6 +10,7 @@
  *
  *   sonde_b200_batch [-t type] [-b buflen] [-f format] [-o prefix] [-c prefix] [-g prefix] [-k prefix] [-l prefix] [-i] [-q]
  *                    file0 [file1 ...]
+ *   sonde_b200_batch -w rate -F f0[,f1...] [the same options] wideband.c64
  *     -t, --type     auto|c50|dfm|imet4|ims100|m10|mrzn1|rs41 (the reference's names, SD/main.c:66; default auto),
  *                    or a comma-separated list, one per file
  *     -b, --buflen   samples per channel per GPU call (default 1024 = the reference's BUFLEN, SD/main.c:32).  Larger buffers
@@ -26,6 +27,11 @@
  *     -l, --live-kml write <prefix><channel>.kml (a network link) and <prefix><channel>.kml-live.kml, which is complete
  *                    after every point
  *     -i, --iq       the files are raw complex64 IQ at 48 kS/s instead of FM audio
+ *     -w, --wideband <rate>   ONE input file: raw complex64 IQ of a wideband receiver at <rate> S/s (rate * L / M = 48000 with
+ *                    1 <= L <= 16, e.g. 2304000, 2048000, 2500000).  The channels are cut out of it on the GPU
+ *                    (include/sonde_b200_channelizer.h: polyphase filter bank on the tensor cores, per-type channel
+ *                    bandwidths as the plugin's VFOs, src/main.hpp:45-51) and decoded without leaving the device
+ *     -F, --freqs <f0,f1,...> with -w: the channel centres in Hz relative to the centre of the recording, one channel each
  * Input files are read the way the reference reads them (SD/main.c:248-266, SD/io/wavfile.c): a file that starts with a
  * 44-byte RIFF/WAVE header is a WAV recording (8 / 16 / 32-bit samples, first channel, 32 KiB blocks — a trailing partial
  * block is ignored, as there), anything else raw mono float32 at 48 kHz read from behind those 44 bytes.  All recordings
@@ -45,6 +51,8 @@
 
 #include "../../include/sonde_b200.h"
 #include "sonde_data.hpp"
+#include "../../include/sonde_b200_channelizer.h"
+#include "gpu_wideband.hpp"                  /* GpuWidebandBank::typeCutoffHz: the per-type channel bandwidths */
 #include "telemetry.hpp"
 #include "track_files.hpp"
 
@@ -150,6 +158,8 @@ void usage(const char *prog)
 	       "   -t, --type <type[,type...]>  auto|c50|dfm|imet4|ims100|m10|mrzn1|rs41, one for all files or one per file (default auto)\n"
 	       "   -b, --buflen <samples>       samples per channel per GPU call (default 1024)\n"
 	       "   -i, --iq                     the files are raw complex64 IQ at 48 kS/s (default: WAV, or raw mono float32 FM audio)\n"
+	       "   -w, --wideband <rate>        ONE file of raw complex64 wideband IQ at <rate> S/s, channels cut out on the GPU\n"
+	       "   -F, --freqs <f0[,f1...]>     with -w: channel centres in Hz relative to the centre of the recording\n"
 	       "   -f, --fmt <format>           format of the text line per data point\n"
 	       "   -o, --output <prefix>        text lines to <prefix><channel>.txt\n"
 	       "   -c, --csv <prefix>           CSV to <prefix><channel>.csv\n"
@@ -171,6 +181,8 @@ int main(int argc, char **argv)
 {
 	std::string type_arg = "auto", csv_prefix, gpx_prefix, kml_prefix, live_prefix, txt_prefix, fmt;
 	bool have_fmt = false;
+	double wide_rate = 0;
+	std::vector<double> freqs;
 	size_t buflen = 1024;
 	bool iq = false, quiet = false;
 	std::vector<std::string> files;
@@ -186,12 +198,36 @@ int main(int argc, char **argv)
 		else if (a == "-k" || a == "--kml") kml_prefix = need("-k");
 		else if (a == "-l" || a == "--live-kml") live_prefix = need("-l");
 		else if (a == "-i" || a == "--iq") iq = true;
+		else if (a == "-w" || a == "--wideband") wide_rate = atof(need("-w").c_str());
+		else if (a == "-F" || a == "--freqs") {
+			const std::string list = need("-F");
+			for (size_t pos = 0; pos <= list.size();) {
+				const size_t c = list.find(',', pos);
+				freqs.push_back(atof(list.substr(pos, c == std::string::npos ? std::string::npos : c - pos).c_str()));
+				if (c == std::string::npos) break;
+				pos = c + 1;
+			}
+		}
 		else if (a == "-q" || a == "--quiet") quiet = true;
 		else if (a == "-h" || a == "--help") { usage(argv[0]); return 0; }
 		else files.push_back(a);
 	}
-	const size_t C = files.size();
+	const bool wideband = wide_rate > 0;
+	if (wideband && (files.size() != 1 || freqs.empty())) { fprintf(stderr, "-w takes one input file and -F f0[,f1...]\n"); return 2; }
+	const size_t C = wideband ? freqs.size() : files.size();
 	if (!C || !buflen) { fprintf(stderr, "no input files\n"); return 2; }
+	/* wideband: rate * L / D = 48000 (host/gpu_wideband.hpp:56-62); one call takes n_in = buflen / L * D input samples */
+	int L = 0, D = 0;
+	if (wideband) {
+		for (int l = 1; l <= 16 && !L; l++) {
+			const long long mi = (long long)(wide_rate * l / 48000.0 + 0.5);
+			if (mi >= 2 && mi > l && (double)mi * 48000.0 == wide_rate * l) { L = l; D = (int)mi; }
+		}
+		if (!L) { fprintf(stderr, "-w %g: rate * L / M must be 48000 with 1 <= L <= 16, M >= 2\n", wide_rate); return 2; }
+		buflen = (buflen + L - 1) / L * L;
+		iq = true;
+	}
+	const size_t n_in = wideband ? buflen / L * D : 0;
 	std::vector<int32_t> types;
 	{
 		size_t pos = 0;
@@ -202,19 +238,19 @@ int main(int argc, char **argv)
 			pos = c + 1;
 		}
 		if (types.size() == 1) types.assign(C, types[0]);
-		if (types.size() != C) { fprintf(stderr, "%zu types for %zu files\n", types.size(), C); return 2; }
+		if (types.size() != C) { fprintf(stderr, "%zu types for %zu channels\n", types.size(), C); return 2; }
 	}
 
 	const size_t esz = iq ? 8 : 4;
-	std::vector<Input> in(C);
-	for (size_t c = 0; c < C; c++) {
+	std::vector<Input> in(wideband ? 1 : C);
+	for (size_t c = 0; c < in.size(); c++) {
 		if (!in[c].open(files[c].c_str(), iq)) { fprintf(stderr, "cannot open %s\n", files[c].c_str()); return 2; }
 		if (in[c].rate != in[0].rate) { fprintf(stderr, "%s: %d S/s, the batch runs at %d S/s\n", files[c].c_str(), in[c].rate, in[0].rate); return 2; }
 	}
 
 	sonde_b200_config cfg = {};
 	cfg.n_channels = (int32_t)C;
-	cfg.samplerate = in[0].rate;
+	cfg.samplerate = wideband ? 48000 : in[0].rate;
 	cfg.max_chunk_len = (int32_t)buflen;
 	cfg.types = types.data();
 	sonde_b200 *h = nullptr;
@@ -226,6 +262,22 @@ int main(int argc, char **argv)
 	if (rc != SONDE_OK) {
 		fprintf(stderr, "sonde_b200_create failed (%d): check the sample rate (%d S/s) and the buffer length (%zu)\n", rc, in[0].rate, buflen);
 		return 2;
+	}
+	sonde_chan *chan = nullptr;
+	if (wideband) {
+		sonde_chan_config cc = {};
+		cc.n_channels = (int32_t)C;
+		cc.decim = D;
+		cc.fs_out = 48000;
+		cc.max_in_len = (int32_t)n_in;
+		cc.freq_hz = freqs.data();
+		std::vector<float> cut(C);
+		for (size_t c = 0; c < C; c++) cut[c] = radiosonde::GpuWidebandBank::typeCutoffHz(types[c]);
+		sonde_chan_options co = {};
+		co.interp = L;
+		co.cutoff_hz = cut.data();
+		const int crc = sonde_chan_create_ex(&chan, &cc, &co);
+		if (crc != SONDE_OK) { fprintf(stderr, "sonde_chan_create failed (%d) for %zu channels, L/M = %d/%d\n", crc, C, L, D); return crc == SONDE_ERR_NODEVICE ? 3 : 2; }
 	}
 	const int max_frames = sonde_b200_max_frames(h);
 	std::vector<sonde_frame_rec> recs(C * (size_t)max_frames);
@@ -256,7 +308,8 @@ int main(int argc, char **argv)
 		}
 	}
 	/* two pinned staging buffers: buffer k+1 is read and submitted while buffer k decodes (sonde_b200.h, fetch()) */
-	char *stage[2] = {(char *)sonde_b200_host_alloc(C * buflen * esz), (char *)sonde_b200_host_alloc(C * buflen * esz)};
+	const size_t stage_bytes = wideband ? n_in * 8 : C * buflen * esz;
+	char *stage[2] = {(char *)sonde_b200_host_alloc(stage_bytes), (char *)sonde_b200_host_alloc(stage_bytes)};
 	if (!stage[0] || !stage[1]) { fprintf(stderr, "pinned allocation failed\n"); return 2; }
 
 	long n_submitted = 0, n_delivered = 0;
@@ -268,6 +321,23 @@ int main(int argc, char **argv)
 		 * tail the previous read left in the buffer; a read of zero samples ends the recording.  Here a recording that
 		 * has ended contributes exact zeros (which the AGC passes through untouched, agc.c:23) until all have ended. */
 		bool any = false;
+		if (wideband) {
+			/* the next n_in samples of the recording (zeros behind its end), channelised on the decoder's stream into
+			 * [C][stride] rows that the decoder reads in place */
+			const size_t got = in[0].read(stage[slot], n_in, 8);
+			if (got == 0) return false;
+			if (got < n_in) memset(stage[slot] + got * 8, 0, (n_in - got) * 8);
+			void *d_rows = nullptr;
+			size_t stride = 0;
+			if (sonde_chan_process_c64(chan, (const float *)stage[slot], n_in, sonde_b200_stream(h), &d_rows, &stride) != SONDE_OK) {
+				fprintf(stderr, "sonde_chan: %s\n", sonde_chan_last_error(chan));
+				exit(1);
+			}
+			if (sonde_b200_process_iq_device(h, d_rows, buflen, stride) != SONDE_OK) { fprintf(stderr, "sonde_b200: %s\n", sonde_b200_last_error(h)); exit(1); }
+			for (size_t c = 0; c < C; c++) last_call[c] = n_submitted;
+			n_submitted++;
+			return true;
+		}
 		for (size_t c = 0; c < C; c++) {
 			char *row = stage[slot] + c * buflen * esz;
 			const size_t got = in[c].read(row, buflen, esz);
@@ -345,10 +415,11 @@ int main(int argc, char **argv)
 		out[c].gpx.close();
 		out[c].csv.close();
 		if (out[c].txt) fclose(out[c].txt);
-		in[c].close();
+		if (c < in.size()) in[c].close();
 	}
 	sonde_b200_host_free(stage[0]);
 	sonde_b200_host_free(stage[1]);
-	sonde_b200_destroy(h);
+	sonde_b200_destroy(h);                       /* the decoder first: it reads the channelizer's buffers */
+	sonde_chan_destroy(chan);
 	return 0;
 }

@@ -253,3 +253,34 @@ def check_wall_clock_sondes(runner, tmp_path):
         want_txt = [l for l in a.stdout.split(b"\n")[:-1] if not l.startswith(b"[\x1b[")]
         got_txt = (tmp_path / f"o_{i}.txt").read_bytes().split(b"\n")[:-1]
         assert same_but_first(got_txt, want_txt, 3), (flag, got_txt[:3], want_txt[:3])
+
+
+def check_wideband_input(runner, tmp_path):
+    """-w / -F: ONE wideband complex64 recording (three sondes at three offsets, 48 x 48 kS/s) channelised and decoded
+    in one batch.  Every channel's CSV rows must be rows the reference's tool writes for that sonde's own narrowband
+    signal (discriminated on the CPU), in the same order, all of them but possibly the first and the last (the channel
+    filter delays the signal by a few samples, so a frame at either end of the recording may be cut)."""
+    from tests import reflib
+    from tests.gpu_util import make_wideband
+    orc = reflib.OracleLib()
+    D, nsec = 48, 5
+    types, flags = [synth.RS41, synth.M10, synth.DFM09], ["rs41", "m10", "dfm"]
+    freqs = [-400e3, 250e3, 31.25e3]
+    nb, wide = make_wideband(types, freqs, D, nsec)
+    (tmp_path / "wide.c64").write_bytes(wide.tobytes())
+    r = subprocess.run([runner, "-q", "-w", str(48000 * D), "-F", ",".join(str(f) for f in freqs), "-t", ",".join(flags),
+                        "-c", str(tmp_path / "w_"), str(tmp_path / "wide.c64")], capture_output=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+
+    def rows(b):
+        return [l for l in b.split(b"\n")[1:] if l.strip(b",")]
+    for c, flag in enumerate(flags):
+        fm = np.asarray(orc.discriminate(nb[c].astype(np.complex64)), dtype=np.float32)
+        (tmp_path / f"nb{c}.raw").write_bytes(b"\0" * 44 + fm.tobytes())
+        a = subprocess.run([REF, "-q", "-t", flag, "-c", str(tmp_path / f"ref{c}.csv"), str(tmp_path / f"nb{c}.raw")], capture_output=True, timeout=600)
+        assert a.returncode == 0, a.stderr[-300:]
+        want, got = rows((tmp_path / f"ref{c}.csv").read_bytes()), rows((tmp_path / f"w_{c}.csv").read_bytes())
+        assert len(want) >= 4 and len(got) >= len(want) - 2, (flag, len(got), len(want))
+        # got[1:] must appear in want as one contiguous run
+        core = got[1:]
+        assert any(want[i:i + len(core)] == core for i in range(len(want) - len(core) + 1)), (flag, got[:3], want[:3])

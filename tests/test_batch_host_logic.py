@@ -165,3 +165,7 @@ def test_wideband_bank(runner, tmp_path):
     def straight(types, nb):
         return np.array([sum(int(x.ok) for x in orc.frames_run_iq(t, nb[c], 48000)) for c, t in enumerate(types)])
     test_host_cpp.check_wideband_block(exe, tmp_path, straight)
+
+
+def test_wideband_input(runner, tmp_path):
+    batch_checks.check_wideband_input(runner, tmp_path)

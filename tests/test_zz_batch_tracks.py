@@ -51,3 +51,12 @@ def test_batch_runner_iq_input_equals_fm_input(tmp_path):
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/sondedump_ref not built")
 def test_batch_runner_wall_clock_sondes(tmp_path):
     batch_checks.check_wall_clock_sondes(BATCH, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/sondedump_ref not built")
+def test_batch_runner_wideband_input(tmp_path):
+    from tests import reflib
+    if not reflib.have_oracle():
+        pytest.skip("oracle/_build/libsonde_oracle.so not built")
+    batch_checks.check_wideband_input(BATCH, tmp_path)
