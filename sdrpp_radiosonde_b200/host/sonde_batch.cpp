@@ -65,6 +65,7 @@ struct Input {
 	int bps = 32, nch = 1, rate = 48000;
 	std::vector<unsigned char> blk;
 	size_t off = 0;                              /* position in the current block, in samples of bps/8 bytes */
+	bool have_blk = false;
 
 	bool open(const char *name, bool iq)
 	{
@@ -82,26 +83,30 @@ struct Input {
 		return true;
 	}
 	/* raw: the number of samples read (a short last read is decoded with the previous buffer's tail, SD/main.c:328-333);
-	 * WAV: `count` or 0 — a read that cannot be completed ends the recording */
+	 * WAV: `count` or 0 — a read that cannot be completed ends the recording (SD/io/wavfile.c:53-113: blocks are read
+	 * when the first sample of a new block is needed, a block that cannot be read whole ends the file).  A frame of
+	 * interleaved channels may straddle two blocks (3 channels of 16 bits: 16384 words per block): the position of the
+	 * next first-channel sample is carried into the next block.  The reference's reader never advances in that case
+	 * and hangs (its copy count becomes 0 with data left, wavfile.c:66,110); with 1, 2, 4, ... channels, where frames
+	 * never straddle, both read the same samples. */
 	size_t read(void *dst_, size_t count, size_t esz)
 	{
 		if (!f) return 0;
 		if (!wav) return fread(dst_, esz, count, f);
+		if (bps != 8 && bps != 16 && bps != 32) return 0;
 		float *dst = (float *)dst_;
 		const size_t per = blk.size() / (size_t)(bps / 8), want = count;
 		while (count > 0) {
-			if (!off && fread(blk.data(), blk.size(), 1, f) != 1) return 0;
-			size_t n = (per - off) / (size_t)nch;
-			if (n > count) n = count;
-			if (n == 0) return 0;
-			for (size_t i = 0; i < n; i++, off += (size_t)nch) {
+			if (!have_blk) {
+				if (fread(blk.data(), blk.size(), 1, f) != 1) return 0;
+				have_blk = true;
+			}
+			for (; count > 0 && off < per; off += (size_t)nch, count--) {
 				if (bps == 8)       *dst++ = (float)(blk[off] - 127);
 				else if (bps == 16) { short v; memcpy(&v, &blk[2 * off], 2); *dst++ = (float)v; }
-				else if (bps == 32) { float v; memcpy(&v, &blk[4 * off], 4); *dst++ = v; }
-				else return 0;
+				else                { float v; memcpy(&v, &blk[4 * off], 4); *dst++ = v; }
 			}
-			count -= n;
-			off %= per;
+			if (off >= per) { off -= per; have_blk = false; }
 		}
 		return want;
 	}

@@ -169,3 +169,32 @@ def test_wideband_bank(runner, tmp_path):
 
 def test_wideband_input(runner, tmp_path):
     batch_checks.check_wideband_input(runner, tmp_path)
+
+
+def test_wav_8bit_and_three_channel_inputs(runner, tmp_path):
+    """The remaining WAV layouts of SD/io/wavfile.c:53-113.  8-bit samples (value - 127), stereo: CSV against the
+    reference tool.  Three interleaved channels: a 32 KiB block does not hold a whole number of 3-channel frames and the
+    reference's reader hangs at the first block boundary (its copy count becomes 0 with data left, wavfile.c:66,110), so
+    there is nothing to compare with; the runner carries the frame position across blocks and must give exactly what it
+    gives for a mono file of the same first channel."""
+    import numpy as np
+    from sdrpp_radiosonde_b200 import synth
+    rng = np.random.default_rng(8)
+    n = 48000 * 5
+    fm0 = synth.make_fm(synth.default_spec(synth.RS41, 61), n)
+    fm1 = synth.make_fm(synth.default_spec(synth.DFM09, 62), n)
+    w0, w3, w1 = tmp_path / "a8.wav", tmp_path / "b3.wav", tmp_path / "b1.wav"
+    u8 = np.clip(np.round(fm0 * (100.0 / np.abs(fm0).max())) + 127, 0, 255).astype(np.uint8)
+    batch_checks._write_wav(w0, np.stack([u8, rng.integers(0, 256, n).astype(np.uint8)], axis=1))
+    s16 = np.clip(np.round(fm1 * (9000.0 / np.abs(fm1).max())), -32768, 32767).astype(np.int16)
+    batch_checks._write_wav(w3, np.stack([s16, rng.integers(-3000, 3000, n).astype(np.int16), np.zeros(n, np.int16)], axis=1))
+    # the mono twin holds what a reader of whole 32 KiB blocks gets from the 3-channel file: its first 6n / 32768 blocks
+    batch_checks._write_wav(w1, s16[:(6 * n // 32768) * 32768 // 6 + 1])
+    r = subprocess.run([runner, "-q", "-t", "rs41,dfm,dfm", "-c", str(tmp_path / "o_"), str(w0), str(w3), str(w1)], capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    a = subprocess.run([batch_checks.REF, "-q", "-t", "rs41", "-c", str(tmp_path / "ref0.csv"), str(w0)], capture_output=True, timeout=600)
+    assert a.returncode == 0, a.stderr[-300:]
+    got, want = (tmp_path / "o_0.csv").read_bytes(), (tmp_path / "ref0.csv").read_bytes()
+    assert want.count(b"\n") >= 5 and got == want
+    three, mono = (tmp_path / "o_1.csv").read_bytes().split(b"\n"), (tmp_path / "o_2.csv").read_bytes().split(b"\n")
+    assert len(mono) >= 8 and three[:len(mono) - 2] == mono[:len(mono) - 2], (len(three), len(mono))
