@@ -102,3 +102,25 @@ def test_batch_layout_plan_host_only():
     # a batch whose groups are not evenly spaced falls back to row copies for that variant
     v, total = plan([synth.RS41, synth.M10, synth.RS41, synth.RS41, synth.M10, synth.RS41, synth.RS41] * 64)
     assert v[0][2] == 0
+
+
+def test_product_binaries_do_not_link_test_infrastructure():
+    """The shipped library, the compat layer and the batch runner depend on the CUDA runtime and on each other — never on
+    the CPU oracle, the compiled reference or the test stand-in of the ABI (tests/cpp/stub_*.c); and no product source
+    includes anything from oracle/ or tests/."""
+    import re
+    import subprocess
+    pkg = os.path.join(ROOT, "sdrpp_radiosonde_b200")
+    for name in ("libsonde_b200.so", "libsonde_b200_compat.so", "sonde_b200_batch"):
+        path = os.path.join(pkg, name)
+        assert os.path.exists(path), path
+        needed = re.findall(r"\(NEEDED\)\s+Shared library: \[([^\]]+)\]", subprocess.run(["readelf", "-d", path], capture_output=True, text=True, check=True).stdout)
+        assert needed and not [n for n in needed if re.search(r"oracle|_ref|stub|writers", n)], (name, needed)
+    bad = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h", ".c", ".py", ".inc")):
+                text = open(os.path.join(d, f), errors="replace").read()
+                if re.search(r'#include\s+"[^"]*(oracle|tests)/', text) or re.search(r"^\s*(from|import)\s+(oracle|tests)\b", text, flags=re.M):
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad
