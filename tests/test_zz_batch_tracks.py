@@ -1,6 +1,10 @@
-"""sonde_b200_batch -g / -k: the per-channel GPX and KML tracks of a batch against what the
-reference's command-line tool writes for each recording alone.  The writers themselves are checked byte for byte on the
-CPU (tests/test_track_files.py); this is the same check through the GPU decode."""
+"""sonde_b200_batch on the GPU, the outputs and inputs beyond the CSV of test_cli_dropin.py: per-channel
+GPX / KML / live KML (-g -k -l), text lines and the format language (-o -f), complex64 recordings (-i), the two sondes
+whose parsers read the wall clock, and one wideband recording through the channelizer (-w -F) — each against what the
+reference's command-line tool writes for every recording alone.  The check functions live in tests/batch_checks.py and
+also run on the CPU against a test copy of the runner linked to the oracle-backed stand-in of the ABI
+(tests/test_batch_host_logic.py); the writers themselves are compared byte for byte with the compiled reference writers in
+tests/test_track_files.py.  The file sorts last on purpose: these are the newest checks of the suite."""
 import os
 import sys
 
